@@ -1,0 +1,122 @@
+/*
+ * mst_b200.h -- C ABI of libmst_b200.so: the sm_100a (B200) compute library behind the segment-batched
+ * style-transfer forward path of jhtonyKoo/music_mixing_style_transfer.
+ *
+ * The reference is 100 % Python and has no FFI of its own: the drop-in boundary is its Python module
+ * surface (networks.FXencoder / networks.TCNModel / mixing_manipulator chain).  This header is what OUR modules
+ * bind (ctypes, music_mixing_style_transfer_b200/_cabi.py); INTEGRATION.md shows the binding a reference maintainer
+ * would add.  Every entry point cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host"
+ *   - no allocation inside: outputs and workspaces are caller-allocated (`*_bytes` queries)
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *   - return 0 on success, non-zero on error; mst_last_error() (thread-local) holds the message
+ *   - fp32 tensors are PyTorch-contiguous [B, C, T] (time fastest) exactly as the reference modules take them
+ */
+#ifndef MST_B200_H_
+#define MST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MST_MAX_ENC_BLOCKS 16
+#define MST_TCN_CH 128          /* channel_width the tcgen05 path is specialised for (inference/configs.yaml:27) */
+#define MST_TCN_K 15            /* kernel_size (configs.yaml:26) */
+#define MST_FX_NPARAMS 20       /* 13 EQ + 4 compressor + 1 imager + 2 gain, order in oracle/fx_oracle.py */
+
+/* ---- library ---------------------------------------------------------------------------------------------- */
+const char* mst_last_error(void);
+int mst_version(void);
+/* 0 if `device` is an sm_100 part with a driver that can encode TMA tensor maps */
+int mst_device_check(int device);
+
+/* ---- FXencoder: replaces FXencoder.forward (mixing_style_transfer/networks/architectures.py:65-70) and the
+ *      Conv1d_layer / Res_ConvBlock stack under it (networks/network_utils.py:15-89, 96-119) ------------------ */
+typedef struct {
+  int n_blocks;                              /* 12 (inference/configs.yaml:8-10) */
+  int channels[MST_MAX_ENC_BLOCKS + 1];      /* 2,16,32,...,2048: channels[i] -> channels[i+1] */
+  int kernels[MST_MAX_ENC_BLOCKS];
+  int strides[MST_MAX_ENC_BLOCKS];
+} mst_enc_config;
+
+/* Fold eval-mode BatchNorm1d into one Conv1d (network_utils.py:50,74): w_out[ci][k][co] = w[co][ci][k]*s[co]
+ * (transposed, co fastest), b_out[co] = (b[co]-mean[co])*s[co] + bn_b[co], s = bn_w/sqrt(var+eps).  */
+int mst_conv1d_fold_bn(const float* w, const float* b, const float* bn_w, const float* bn_b, const float* bn_mean,
+                       const float* bn_var, float eps, int c_out, int c_in, int k, float* w_out, float* b_out,
+                       void* stream);
+
+/* One Conv1d_layer (mode "conv", padding "SAME"): y = relu(conv_stride(reflect_pad(x)) + b) [+ residual]
+ * (network_utils.py:28-34,47-51,74,79-80; the `+ residual` is Res_ConvBlock's `conv1(x) + x`, :117).
+ * w_folded/b_folded come from mst_conv1d_fold_bn.  T_out = ceil(T_in/stride).  residual may be NULL. */
+int mst_enc_conv1d(const float* x, const float* w_folded, const float* b_folded, const float* residual, float* y,
+                   int B, int c_in, int t_in, int c_out, int k, int stride, int relu, void* stream);
+
+/* AdaptiveAvgPool1d(1).squeeze(-1) (architectures.py:62,67): y[B,C] = mean_t x[B,C,T] */
+int mst_enc_mean_pool(const float* x, float* y, int B, int C, int T, void* stream);
+
+size_t mst_enc_packed_bytes(const mst_enc_config* cfg);
+/* raw: host array of 12*n_blocks device pointers, per block: conv1 {w,b,bn_w,bn_b,bn_mean,bn_var}, conv2 {...} */
+int mst_enc_pack(const mst_enc_config* cfg, const float* const* raw, float* packed, void* stream);
+size_t mst_enc_workspace_bytes(const mst_enc_config* cfg, int B, int L);
+/* whole encoder: x[B,2,L] -> emb[B,channels[n_blocks]] */
+int mst_enc_forward(const mst_enc_config* cfg, const float* packed, const float* x, int B, int L, float* emb,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- MixFXcloner TCN: replaces TCNModel.forward (architectures.py:135-147), TCNBlock.forward (:222-234) and
+ *      FiLM.forward (network_utils.py:180-182) ------------------------------------------------------------- */
+typedef struct {
+  int n_blocks;          /* 14 */
+  int n_inputs;          /* 2  */
+  int n_outputs;         /* 2  */
+  int channels;          /* 128 (only value with a CUDA path) */
+  int kernel_size;       /* 15 (only value with a CUDA path) */
+  int dilation_growth;   /* 2  */
+  int stack_size;        /* 15 */
+  int cond_dim;          /* 2048 */
+} mst_tcn_config;
+
+size_t mst_tcn_packed_bytes(const mst_tcn_config* cfg);
+/* raw: host array of device pointers, per block n: {conv1.weight, bn.weight, bn.bias, bn.running_mean,
+ * bn.running_var, res.weight, film.film_fc.weight, film.film_fc.bias}, then {output.weight, output.bias}.
+ * Packs: BN folded into conv1 (block 0 fp32; blocks >=1 split into bf16 hi+lo, tap-major, K-major tiles),
+ * per-channel BN bias and residual scale, FiLM weights, output projection. */
+int mst_tcn_pack(const mst_tcn_config* cfg, const void* const* raw, void* packed, void* stream);
+
+/* FiLM for all blocks at once (network_utils.py:180-181): film[n][bc][c] = (bn_bias, gamma, beta, res_scale) as
+ * float4, gamma|beta = Linear_n(cond[bc]).  cond: [n_cond, cond_dim]; n_cond is 1 (broadcast) or B.
+ * film_out: float[n_blocks * n_cond * channels * 4]. */
+int mst_tcn_film_precompute(const mst_tcn_config* cfg, const void* packed, const float* cond, int n_cond,
+                            float* film_out, void* stream);
+
+size_t mst_tcn_workspace_bytes(const mst_tcn_config* cfg, int B, int L);
+/* whole TCN: x[B,n_inputs,L] fp32 -> y[B,n_outputs,L] fp32 = clamp(output(blocks(x)), -1, 1).
+ * `film` from mst_tcn_film_precompute with the same n_cond. */
+int mst_tcn_forward(const mst_tcn_config* cfg, const void* packed, const float* x, const float* film, int n_cond,
+                    float* y, int B, int L, void* workspace, size_t workspace_bytes, void* stream);
+
+/* single TCNBlock n on fp32 [B,C,L] tensors (module-level surface + per-dilation parity tests):
+ * y[B,128,L] = film(leaky_relu(bn(conv1(x)))) + res(x).  workspace >= mst_tcn_workspace_bytes(cfg,B,L). */
+int mst_tcn_block_forward(const mst_tcn_config* cfg, const void* packed, int block, const float* x, const float* film,
+                          int n_cond, float* y, int B, int L, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- FX chain: replaces AugmentationChain.__call__ over Equaliser/Compressor/MidSideImager/Gain
+ *      (mixing_manipulator/common_audioeffects.py:156-192, 501-525, 529-652, 965-992, 1038-1051) -------------- */
+#define MST_FX_EQ 1
+#define MST_FX_COMP 2
+#define MST_FX_IMAGER 4
+#define MST_FX_GAIN 8
+#define MST_FX_RMSNORM 16   /* apply the chain's RMS re-normalisation after EQ / comp / imager (:142-145) */
+size_t mst_fx_workspace_bytes(int B, int L);
+/* x,y: fp32 [B,2,L] (channel-major; the reference's arrays are [L,2]); params: fp32 [B,20]; stages: MST_FX_* mask */
+int mst_fx_chain_forward(const float* x, const float* params, float* y, int B, int L, float sample_rate, int stages,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MST_B200_H_ */

@@ -1,0 +1,49 @@
+// common.cuh -- shared host/device helpers for libmst_b200 (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mst_b200.h"
+
+namespace mst {
+
+// thread-local error slot behind mst_last_error()
+char* error_buffer();
+int fail(const char* fmt, ...);
+
+#define MST_CUDA_OK(expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ::mst::fail("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define MST_CHECK(cond, ...)                    \
+  do {                                          \
+    if (!(cond)) return ::mst::fail(__VA_ARGS__); \
+  } while (0)
+
+inline int launch_ok(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("launch of %s failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+int sm_count();  // cached multiProcessorCount of the current device
+
+// ---- driver entry point for TMA descriptors (no -lcuda link: resolved through the runtime) ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled tensor_map_encoder();  // nullptr (with last_error set) if the driver lacks it
+
+}  // namespace mst

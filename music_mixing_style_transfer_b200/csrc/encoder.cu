@@ -1,0 +1,384 @@
+// encoder.cu -- FXencoder forward for sm_100a.
+//
+// Replaces (reference paths relative to /root/reference/mixing_style_transfer/networks/):
+//   Conv1d_layer  = ReflectionPad1d -> Conv1d(bias) -> BatchNorm1d(eval) -> ReLU   network_utils.py:28-34,47-51,74,79-89
+//   Res_ConvBlock = conv1(x) + x ; conv2(.)                                        network_utils.py:116-119
+//   FXencoder.forward = 12 blocks -> AdaptiveAvgPool1d(1).squeeze(-1)              architectures.py:62-70
+//
+// Data layout: activations are fp32 [B][C][T] (PyTorch contiguous, time fastest).  Weights are BN-folded once
+// (mst_conv1d_fold_bn) and stored TRANSPOSED as w[ci][k][co] so a CTA's co-tile is contiguous.
+//
+// Kernel: im2col-free direct convolution on the fp32 CUDA cores.  One CTA computes a (CO_TILE x T_TILE) output tile of
+// one segment; lanes run along time (coalesced loads/stores, conflict-free shared reads), warps along output channels.
+// The input window is staged in shared memory DE-INTERLEAVED by stride phase (position p -> [p % S][p / S]) so that a
+// strided convolution still reads consecutive words per warp; reflection padding is resolved while staging.
+// Epilogue fuses bias(+BN) -> ReLU -> residual add.
+#include "common.cuh"
+
+namespace mst {
+
+template <int K, int S, int COT, int TT, int CI_TILE>
+struct EncTile {
+  static constexpr int kWarps = 8;
+  static constexpr int CO_TILE = kWarps * COT;
+  static constexpr int T_TILE = 32 * TT;
+  static constexpr int XW = T_TILE + (K - 1) / S + 1;        // per-phase row length
+  static constexpr int WIN = (T_TILE - 1) * S + K;           // input positions needed by the tile
+  static constexpr int SMEM_FLOATS = CI_TILE * K * CO_TILE + CI_TILE * S * XW;
+};
+
+__device__ __forceinline__ int reflect_index(int p, int t_in) {
+  // nn.ReflectionPad1d: mirror without repeating the edge sample; clamp covers the don't-care tail of the last tile
+  if (p < 0) p = -p;
+  if (p >= t_in) p = 2 * (t_in - 1) - p;
+  return min(max(p, 0), t_in - 1);
+}
+
+template <int K, int S, int COT, int TT, int CI_TILE>
+__global__ void __launch_bounds__(256)
+enc_conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  const float* __restrict__ residual, float* __restrict__ y, int c_in, int t_in, int c_out,
+                  int t_out, int pad_left, int relu) {
+  using Tile = EncTile<K, S, COT, TT, CI_TILE>;
+  __shared__ __align__(16) float smem[Tile::SMEM_FLOATS];
+  float* Ws = smem;                                        // [CI_TILE][K][CO_TILE]
+  float* Xs = smem + CI_TILE * K * Tile::CO_TILE;          // [CI_TILE][S][XW]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t_base = blockIdx.x * Tile::T_TILE;
+  const int co_base = blockIdx.y * Tile::CO_TILE;
+  const int b = blockIdx.z;
+  const float* xb = x + (size_t)b * c_in * t_in;
+  const int p0 = t_base * S - pad_left;
+
+  float acc[COT][TT];
+#pragma unroll
+  for (int c = 0; c < COT; ++c)
+#pragma unroll
+    for (int i = 0; i < TT; ++i) acc[c][i] = 0.f;
+
+  for (int ci0 = 0; ci0 < c_in; ci0 += CI_TILE) {
+    // ---- stage weights: contiguous co per (ci, k) ----
+    for (int idx = tid; idx < CI_TILE * K * Tile::CO_TILE; idx += 256) {
+      const int co = idx % Tile::CO_TILE;
+      const int r = idx / Tile::CO_TILE;  // ci * K + j
+      const int ci = r / K, j = r - ci * K;
+      float v = 0.f;
+      if (ci0 + ci < c_in && co_base + co < c_out) v = __ldg(w + ((size_t)(ci0 + ci) * K + j) * c_out + co_base + co);
+      Ws[idx] = v;
+    }
+    // ---- stage the input window, de-interleaved by stride phase, reflection resolved here ----
+    for (int idx = tid; idx < CI_TILE * Tile::WIN; idx += 256) {
+      const int ci = idx / Tile::WIN, m = idx - ci * Tile::WIN;
+      float v = 0.f;
+      if (ci0 + ci < c_in) v = __ldg(xb + (size_t)(ci0 + ci) * t_in + reflect_index(p0 + m, t_in));
+      Xs[(ci * S + (m % S)) * Tile::XW + m / S] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < CI_TILE; ++ci) {
+      const float* wrow = Ws + ci * K * Tile::CO_TILE + warp * COT;
+      const float* xrow = Xs + ci * S * Tile::XW + lane;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        float wv[COT];
+#pragma unroll
+        for (int c4 = 0; c4 < COT / 4; ++c4) {
+          const float4 q = *reinterpret_cast<const float4*>(wrow + j * Tile::CO_TILE + c4 * 4);  // warp-broadcast
+          wv[c4 * 4 + 0] = q.x; wv[c4 * 4 + 1] = q.y; wv[c4 * 4 + 2] = q.z; wv[c4 * 4 + 3] = q.w;
+        }
+        float xv[TT];
+#pragma unroll
+        for (int i = 0; i < TT; ++i) xv[i] = xrow[(j % S) * Tile::XW + (j / S) + 32 * i];
+#pragma unroll
+        for (int c = 0; c < COT; ++c)
+#pragma unroll
+          for (int i = 0; i < TT; ++i) acc[c][i] = fmaf(wv[c], xv[i], acc[c][i]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: folded bias -> ReLU -> residual ----
+#pragma unroll
+  for (int c = 0; c < COT; ++c) {
+    const int co = co_base + warp * COT + c;
+    if (co >= c_out) continue;
+    const float bv = __ldg(bias + co);
+    const size_t row = ((size_t)b * c_out + co) * t_out;
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+      const int t = t_base + lane + 32 * i;
+      if (t >= t_out) continue;
+      float v = acc[c][i] + bv;
+      if (relu) v = fmaxf(v, 0.f);
+      if (residual) v += __ldg(residual + row + t);
+      y[row + t] = v;
+    }
+  }
+}
+
+// generic (any k / stride) variant: same tiling, runtime tap loop.  Used only for configs outside configs.yaml.
+template <int COT, int TT, int CI_TILE>
+__global__ void __launch_bounds__(256)
+enc_conv1d_generic_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                          const float* __restrict__ residual, float* __restrict__ y, int c_in, int t_in, int c_out,
+                          int t_out, int pad_left, int relu, int K, int S) {
+  constexpr int CO_TILE = 8 * COT, T_TILE = 32 * TT;
+  extern __shared__ __align__(16) float dsm[];
+  const int XW = T_TILE + (K - 1) / S + 1, WIN = (T_TILE - 1) * S + K;
+  float* Ws = dsm;
+  float* Xs = dsm + CI_TILE * K * CO_TILE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t_base = blockIdx.x * T_TILE, co_base = blockIdx.y * CO_TILE, b = blockIdx.z;
+  const float* xb = x + (size_t)b * c_in * t_in;
+  const int p0 = t_base * S - pad_left;
+  float acc[COT][TT];
+#pragma unroll
+  for (int c = 0; c < COT; ++c)
+#pragma unroll
+    for (int i = 0; i < TT; ++i) acc[c][i] = 0.f;
+  for (int ci0 = 0; ci0 < c_in; ci0 += CI_TILE) {
+    for (int idx = tid; idx < CI_TILE * K * CO_TILE; idx += 256) {
+      const int co = idx % CO_TILE, r = idx / CO_TILE, ci = r / K, j = r - ci * K;
+      float v = 0.f;
+      if (ci0 + ci < c_in && co_base + co < c_out) v = __ldg(w + ((size_t)(ci0 + ci) * K + j) * c_out + co_base + co);
+      Ws[idx] = v;
+    }
+    for (int idx = tid; idx < CI_TILE * WIN; idx += 256) {
+      const int ci = idx / WIN, m = idx - ci * WIN;
+      float v = 0.f;
+      if (ci0 + ci < c_in) v = __ldg(xb + (size_t)(ci0 + ci) * t_in + reflect_index(p0 + m, t_in));
+      Xs[(ci * S + (m % S)) * XW + m / S] = v;
+    }
+    __syncthreads();
+    for (int ci = 0; ci < CI_TILE; ++ci) {
+      for (int j = 0; j < K; ++j) {
+        const float* wrow = Ws + (ci * K + j) * CO_TILE + warp * COT;
+        const float* xrow = Xs + (ci * S + (j % S)) * XW + (j / S) + lane;
+#pragma unroll
+        for (int c = 0; c < COT; ++c)
+#pragma unroll
+          for (int i = 0; i < TT; ++i) acc[c][i] = fmaf(wrow[c], xrow[32 * i], acc[c][i]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int c = 0; c < COT; ++c) {
+    const int co = co_base + warp * COT + c;
+    if (co >= c_out) continue;
+    const float bv = __ldg(bias + co);
+    const size_t row = ((size_t)b * c_out + co) * t_out;
+#pragma unroll
+    for (int i = 0; i < TT; ++i) {
+      const int t = t_base + lane + 32 * i;
+      if (t >= t_out) continue;
+      float v = acc[c][i] + bv;
+      if (relu) v = fmaxf(v, 0.f);
+      if (residual) v += __ldg(residual + row + t);
+      y[row + t] = v;
+    }
+  }
+}
+
+__global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ bn_w,
+                               const float* __restrict__ bn_b, const float* __restrict__ bn_mean,
+                               const float* __restrict__ bn_var, float eps, int c_out, int c_in, int k,
+                               float* __restrict__ w_out, float* __restrict__ b_out) {
+  const size_t n = (size_t)c_out * c_in * k;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    // output index order: [ci][j][co]
+    const int co = idx % c_out;
+    const size_t r = idx / c_out;
+    const int j = r % k;
+    const int ci = r / k;
+    const float s = bn_w[co] / sqrtf(bn_var[co] + eps);
+    w_out[idx] = w[((size_t)co * c_in + ci) * k + j] * s;
+  }
+  for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < c_out; co += gridDim.x * blockDim.x) {
+    const float s = bn_w[co] / sqrtf(bn_var[co] + eps);
+    b_out[co] = ((b ? b[co] : 0.f) - bn_mean[co]) * s + bn_b[co];
+  }
+}
+
+__global__ void mean_pool_kernel(const float* __restrict__ x, float* __restrict__ y, int rows, int T) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* p = x + (size_t)warp * T;
+  float s = 0.f;
+  for (int t = lane; t < T; t += 32) s += p[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) y[warp] = s / (float)T;
+}
+
+template <int K, int S, int COT, int TT, int CI_TILE>
+static int launch_conv(const float* x, const float* w, const float* b, const float* res, float* y, int B, int c_in,
+                       int t_in, int c_out, int t_out, int pad_left, int relu, cudaStream_t st) {
+  using Tile = EncTile<K, S, COT, TT, CI_TILE>;
+  static_assert(Tile::SMEM_FLOATS * 4 <= 48 * 1024, "static shared memory budget");
+  dim3 grid(cdiv(t_out, Tile::T_TILE), cdiv(c_out, Tile::CO_TILE), B);
+  enc_conv1d_kernel<K, S, COT, TT, CI_TILE><<<grid, 256, 0, st>>>(x, w, b, res, y, c_in, t_in, c_out, t_out, pad_left, relu);
+  return launch_ok("enc_conv1d_kernel");
+}
+
+template <int K, int S, int CI_TILE>
+static int launch_conv_by_shape(const float* x, const float* w, const float* b, const float* res, float* y, int B,
+                                int c_in, int t_in, int c_out, int t_out, int pad_left, int relu, cudaStream_t st) {
+  // long time axis: 8 co x 4 t per thread (64 x 128 tile); short time axis / many channels: 16 co x 2 t (128 x 64)
+  if (t_out > 64 || c_out < 128)
+    return launch_conv<K, S, 8, 4, CI_TILE>(x, w, b, res, y, B, c_in, t_in, c_out, t_out, pad_left, relu, st);
+  constexpr int CI_WIDE = (K * CI_TILE * 128 > 10000) ? CI_TILE / 2 : CI_TILE;  // 128-wide co tile: keep Ws <= 40 KB
+  return launch_conv<K, S, 16, 2, CI_WIDE>(x, w, b, res, y, B, c_in, t_in, c_out, t_out, pad_left, relu, st);
+}
+
+static int conv1d_dispatch(const float* x, const float* w, const float* b, const float* res, float* y, int B, int c_in,
+                           int t_in, int c_out, int k, int stride, int relu, cudaStream_t st) {
+  MST_CHECK(B > 0 && c_in > 0 && c_out > 0 && t_in > 0 && k > 0 && stride > 0, "enc_conv1d: bad shape");
+  const int pad = k - 1, pad_left = pad / 2;  // network_utils.py:31-34 (dilation 1)
+  MST_CHECK(t_in > pad - pad_left, "enc_conv1d: reflection padding (%d,%d) needs T_in > pad, got T_in=%d", pad_left,
+            pad - pad_left, t_in);
+  const int t_out = (t_in + pad - k) / stride + 1;  // == ceil(t_in / stride)
+#define MST_CONV_CASE(KK, SS, CI) \
+  if (k == KK && stride == SS)    \
+    return launch_conv_by_shape<KK, SS, CI>(x, w, b, res, y, B, c_in, t_in, c_out, t_out, pad_left, relu, st);
+  MST_CONV_CASE(25, 4, 4)
+  MST_CONV_CASE(25, 1, 4)
+  MST_CONV_CASE(15, 2, 8)
+  MST_CONV_CASE(15, 1, 8)
+  MST_CONV_CASE(10, 2, 8)
+  MST_CONV_CASE(10, 1, 8)
+  MST_CONV_CASE(5, 2, 8)
+  MST_CONV_CASE(5, 1, 8)
+#undef MST_CONV_CASE
+  {  // any other (k, stride): generic kernel, dynamic shared memory
+    constexpr int COT = 8, TT = 4, CI_TILE = 2;
+    const int XW = 32 * TT + (k - 1) / stride + 1;
+    const size_t smem = (size_t)(CI_TILE * k * 8 * COT + CI_TILE * stride * XW) * sizeof(float);
+    MST_CHECK(smem <= 200 * 1024, "enc_conv1d: kernel_size %d / stride %d too large for the generic kernel", k, stride);
+    auto kern = enc_conv1d_generic_kernel<COT, TT, CI_TILE>;
+    if (smem > 48 * 1024) MST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(cdiv(t_out, 32 * TT), cdiv(c_out, 8 * COT), B);
+    kern<<<grid, 256, smem, st>>>(x, w, b, res, y, c_in, t_in, c_out, t_out, pad_left, relu, k, stride);
+    return launch_ok("enc_conv1d_generic_kernel");
+  }
+}
+
+// packed layout: per block, conv1 {w[ci][k][co], b[co]} then conv2 {w, b}, 64-float aligned
+struct EncOffsets {
+  size_t w1[MST_MAX_ENC_BLOCKS], b1[MST_MAX_ENC_BLOCKS], w2[MST_MAX_ENC_BLOCKS], b2[MST_MAX_ENC_BLOCKS], total;
+};
+static int enc_offsets(const mst_enc_config* cfg, EncOffsets* o) {
+  MST_CHECK(cfg && cfg->n_blocks > 0 && cfg->n_blocks <= MST_MAX_ENC_BLOCKS, "enc config: n_blocks out of range");
+  size_t off = 0;
+  for (int i = 0; i < cfg->n_blocks; ++i) {
+    const size_t ci = cfg->channels[i], co = cfg->channels[i + 1], k = cfg->kernels[i];
+    MST_CHECK(ci > 0 && co > 0 && k > 0 && cfg->strides[i] > 0, "enc config: bad block %d", i);
+    o->w1[i] = off; off += align_up(ci * ci * k, 64);
+    o->b1[i] = off; off += align_up(ci, 64);
+    o->w2[i] = off; off += align_up(co * ci * k, 64);
+    o->b2[i] = off; off += align_up(co, 64);
+  }
+  o->total = off;
+  return 0;
+}
+
+}  // namespace mst
+
+using namespace mst;
+
+extern "C" {
+
+int mst_conv1d_fold_bn(const float* w, const float* b, const float* bn_w, const float* bn_b, const float* bn_mean,
+                       const float* bn_var, float eps, int c_out, int c_in, int k, float* w_out, float* b_out,
+                       void* stream) {
+  MST_CHECK(w && bn_w && bn_b && bn_mean && bn_var && w_out && b_out, "fold_bn: null pointer");
+  const size_t n = (size_t)c_out * c_in * k;
+  const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  fold_bn_kernel<<<blocks > 0 ? blocks : 1, 256, 0, (cudaStream_t)stream>>>(w, b, bn_w, bn_b, bn_mean, bn_var, eps, c_out,
+                                                                            c_in, k, w_out, b_out);
+  return launch_ok("fold_bn_kernel");
+}
+
+int mst_enc_conv1d(const float* x, const float* w_folded, const float* b_folded, const float* residual, float* y, int B,
+                   int c_in, int t_in, int c_out, int k, int stride, int relu, void* stream) {
+  MST_CHECK(x && w_folded && b_folded && y, "enc_conv1d: null pointer");
+  MST_CHECK(B <= 65535, "enc_conv1d: batch %d exceeds grid.z", B);
+  return conv1d_dispatch(x, w_folded, b_folded, residual, y, B, c_in, t_in, c_out, k, stride, relu, (cudaStream_t)stream);
+}
+
+int mst_enc_mean_pool(const float* x, float* y, int B, int C, int T, void* stream) {
+  MST_CHECK(x && y && B > 0 && C > 0 && T > 0, "mean_pool: bad arguments");
+  const int rows = B * C;
+  mean_pool_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, y, rows, T);
+  return launch_ok("mean_pool_kernel");
+}
+
+size_t mst_enc_packed_bytes(const mst_enc_config* cfg) {
+  EncOffsets o;
+  if (enc_offsets(cfg, &o)) return 0;
+  return o.total * sizeof(float);
+}
+
+int mst_enc_pack(const mst_enc_config* cfg, const float* const* raw, float* packed, void* stream) {
+  EncOffsets o;
+  if (enc_offsets(cfg, &o)) return 1;
+  MST_CHECK(raw && packed, "enc_pack: null pointer");
+  for (int i = 0; i < cfg->n_blocks; ++i) {
+    const float* const* r = raw + 12 * i;
+    const int ci = cfg->channels[i], co = cfg->channels[i + 1], k = cfg->kernels[i];
+    if (mst_conv1d_fold_bn(r[0], r[1], r[2], r[3], r[4], r[5], 1e-5f, ci, ci, k, packed + o.w1[i], packed + o.b1[i], stream))
+      return 1;
+    if (mst_conv1d_fold_bn(r[6], r[7], r[8], r[9], r[10], r[11], 1e-5f, co, ci, k, packed + o.w2[i], packed + o.b2[i], stream))
+      return 1;
+  }
+  return 0;
+}
+
+static size_t enc_max_act(const mst_enc_config* cfg, int B, int L) {
+  size_t mx = 0;
+  int t = L;
+  for (int i = 0; i < cfg->n_blocks; ++i) {
+    const size_t a1 = (size_t)B * cfg->channels[i] * t;  // conv1 output
+    t = cdiv(t, cfg->strides[i]);
+    const size_t a2 = (size_t)B * cfg->channels[i + 1] * t;  // conv2 output
+    mx = a1 > mx ? a1 : mx;
+    mx = a2 > mx ? a2 : mx;
+  }
+  return align_up(mx, 64);
+}
+
+size_t mst_enc_workspace_bytes(const mst_enc_config* cfg, int B, int L) {
+  if (!cfg || B <= 0 || L <= 0) return 0;
+  return 3 * enc_max_act(cfg, B, L) * sizeof(float);
+}
+
+int mst_enc_forward(const mst_enc_config* cfg, const float* packed, const float* x, int B, int L, float* emb,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  EncOffsets o;
+  if (enc_offsets(cfg, &o)) return 1;
+  MST_CHECK(packed && x && emb && workspace, "enc_forward: null pointer");
+  MST_CHECK(B > 0 && L > 0, "enc_forward: bad shape B=%d L=%d", B, L);
+  MST_CHECK(workspace_bytes >= mst_enc_workspace_bytes(cfg, B, L), "enc_forward: workspace too small (%zu < %zu)",
+            workspace_bytes, mst_enc_workspace_bytes(cfg, B, L));
+  const size_t stride = enc_max_act(cfg, B, L);
+  float* buf[3] = {(float*)workspace, (float*)workspace + stride, (float*)workspace + 2 * stride};
+  const float* cur = x;
+  int cur_buf = -1, t = L;
+  for (int i = 0; i < cfg->n_blocks; ++i) {
+    const int ci = cfg->channels[i], co = cfg->channels[i + 1], k = cfg->kernels[i], s = cfg->strides[i];
+    float* c1 = buf[(cur_buf + 1) % 3];
+    float* c2 = buf[(cur_buf + 2) % 3];
+    // c1 = relu(bn(conv1(x))) + x          (Res_ConvBlock, network_utils.py:117)
+    if (mst_enc_conv1d(cur, packed + o.w1[i], packed + o.b1[i], cur, c1, B, ci, t, ci, k, 1, 1, stream)) return 1;
+    // c2 = relu(bn(conv2(c1)))             (:118)
+    if (mst_enc_conv1d(c1, packed + o.w2[i], packed + o.b2[i], nullptr, c2, B, ci, t, co, k, s, 1, stream)) return 1;
+    t = cdiv(t, s);
+    cur = c2;
+    cur_buf = (cur_buf + 2) % 3;
+  }
+  return mst_enc_mean_pool(cur, emb, B, cfg->channels[cfg->n_blocks], t, stream);
+}
+
+}  // extern "C"

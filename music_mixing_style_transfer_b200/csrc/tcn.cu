@@ -1,0 +1,724 @@
+// tcn.cu -- MixFXcloner (FiLM-conditioned TCN) forward for sm_100a.
+//
+// Replaces (reference paths relative to /root/reference/mixing_style_transfer/networks/):
+//   TCNModel.forward   architectures.py:135-147   14 blocks, dilation 2^n, then clamp(Conv1d(128->2,k=1)(x), -1, 1)
+//   TCNBlock.forward   architectures.py:222-234   h = LeakyReLU(BN(conv1_dilated(x))); h = gamma*h + beta; h += res(x)
+//   FiLM.forward       network_utils.py:180-182   [gamma|beta] = Linear(2048 -> 256)(cond)
+//
+// ---- data layout in HBM --------------------------------------------------------------------------------------------
+// Between blocks the 128-channel activation is kept TIME-MAJOR (channels-last) and pre-split into two bf16 terms,
+// x = hi + lo (hi = bf16(x), lo = bf16(x - hi)): 16 mantissa bits in 4 bytes/element -- the same HBM bytes as fp32.
+// One time step is one 512-byte row of 4 "planes" of 64 bf16:  [ch 0-63 hi | ch 0-63 lo | ch 64-127 hi | ch 64-127 lo]
+//   act[b][t][plane][64]   (b = segment).  A plane row is exactly one 128-byte swizzle row, so a TMA box of
+// {64 ch, 128 t} lands in shared memory as a canonical K-major SWIZZLE_128B UMMA operand tile.  Zero padding of the
+// dilated convolution = TMA out-of-bounds zero fill along t (segments are a separate tensor dimension, so taps never
+// leak across segments).  Weights are BN-folded, split the same way and stored tap-major:
+//   w[tap][kc][hi|lo][co 128][ci 64]   (kc = input-channel half).
+//
+// ---- the hot kernel (blocks 1..13, 98 % of all FLOPs) ---------------------------------------------------------------
+// tcn_block_umma_kernel: im2col-free dilated implicit GEMM on the 5th-gen tensor cores.
+//   D[t, co] = sum_{tap, ci} X[t + (tap-7)*d, ci] * W[tap][co][ci]        M = 128 time rows, N = 128 co, K = 15*128
+// fp32-grade accuracy from bf16 tensor cores via the 3-product split  Xhi*Whi + Xlo*Whi + Xhi*Wlo  (fp32 accumulate in
+// TMEM; the dropped lo*lo term is ~2^-18 relative).  Persistent, warp-specialised, one CTA per SM:
+//   warp 0   TMA producer: streams 32 KB slots (W tap-chunk, X sub-tile hi+lo) through a 6-deep mbarrier ring
+//   warp 1   MMA issuer: one thread issues tcgen05.mma (128x128x16) x 12 per slot pair, commits slots back
+//   warp 2   TMEM allocator (512 columns = 2 tiles x 2 sub-tiles x 128 fp32 columns -> double-buffered accumulators)
+//   warps 4-7 epilogue: tcgen05.ld -> +BN bias -> LeakyReLU -> FiLM -> + res*x_in (x_in tile TMA-loaded) -> split to
+//            bf16 hi/lo -> swizzled shared tile -> TMA store;  the LAST block instead fuses Conv1d(128->2,k=1)+clamp
+//            and writes the fp32 [B,2,L] output directly (the 128-channel tensor of block 13 never touches HBM).
+// Taps whose shifted tile lies entirely in the zero padding are skipped by producer and issuer alike.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace mst {
+
+constexpr int kCh = MST_TCN_CH;      // 128
+constexpr int kTaps = MST_TCN_K;     // 15
+constexpr int kRowBytes = 512;       // one time step: 4 planes x 64 bf16
+constexpr int kSubRows = 128;        // UMMA M
+constexpr int kTileRows = 256;       // two sub-tiles share every weight slot
+constexpr int kSlotBytes = 32768;    // hi tile (128 x 128 B) + lo tile
+constexpr int kNumSlots = 6;
+constexpr int kWRowsPerLayer = kTaps * 2 * 2 * kCh;  // 7680 rows of 64 bf16
+
+struct TcnPacked {
+  size_t w0, wumma, bn_bias, res, film_w, film_b, out_w, out_b, total;
+};
+
+static int tcn_layout(const mst_tcn_config* c, TcnPacked* o) {
+  MST_CHECK(c, "tcn config is null");
+  MST_CHECK(c->channels == kCh && c->kernel_size == kTaps,
+            "tcn config: only channel_width=128 / kernel_size=15 has a CUDA path (got %d / %d)", c->channels,
+            c->kernel_size);
+  MST_CHECK(c->n_blocks >= 2 && c->n_blocks <= 32, "tcn config: n_blocks %d out of range [2,32]", c->n_blocks);
+  MST_CHECK(c->n_inputs >= 1 && c->n_inputs <= 2 && c->n_outputs >= 1 && c->n_outputs <= 2,
+            "tcn config: n_inputs/n_outputs must be 1 or 2");
+  MST_CHECK(c->cond_dim > 0 && c->cond_dim % 32 == 0 && c->cond_dim <= 4096, "tcn config: cond_dim %d unsupported", c->cond_dim);
+  MST_CHECK(c->dilation_growth >= 1 && c->stack_size >= 1, "tcn config: bad dilation");
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t r = off; off += align_up(bytes, 1024); return r; };
+  o->w0 = take((size_t)kCh * c->n_inputs * kTaps * 4);
+  o->wumma = take((size_t)(c->n_blocks - 1) * kWRowsPerLayer * 64 * 2);
+  o->bn_bias = take((size_t)c->n_blocks * kCh * 4);
+  o->res = take((size_t)c->n_blocks * kCh * 4);
+  o->film_w = take((size_t)c->n_blocks * 2 * kCh * c->cond_dim * 4);
+  o->film_b = take((size_t)c->n_blocks * 2 * kCh * 4);
+  o->out_w = take((size_t)c->n_outputs * kCh * 4);
+  o->out_b = take((size_t)c->n_outputs * 4);
+  o->total = off;
+  return 0;
+}
+
+static long long block_dilation(const mst_tcn_config* c, int n) {
+  long long d = 1;
+  for (int i = 0; i < n % c->stack_size; ++i) d *= c->dilation_growth;  // architectures.py:122
+  return d;
+}
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+__device__ __forceinline__ float bf16_lo_f(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// =====================================================================================================================
+// weight packing
+// =====================================================================================================================
+__global__ void tcn_pack_block0_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
+                                       const float* __restrict__ bn_var, int n_in, float* __restrict__ w0) {
+  const int n = kCh * n_in * kTaps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int co = i / (n_in * kTaps);
+    w0[i] = w[i] * (bn_w[co] / sqrtf(bn_var[co] + 1e-5f));
+  }
+}
+
+// w: [co 128][ci 128][tap 15] fp32  ->  out[tap][kc][split][co][ci 64] bf16, BN scale folded before the split
+__global__ void tcn_pack_umma_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
+                                     const float* __restrict__ bn_var, __nv_bfloat16* __restrict__ out) {
+  const int n = kTaps * 2 * kCh * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int cil = i & 63;
+    const int co = (i >> 6) & (kCh - 1);
+    const int kc = (i >> 13) & 1;
+    const int tap = i >> 14;
+    const float s = bn_w[co] / sqrtf(bn_var[co] + 1e-5f);
+    const float v = w[((size_t)co * kCh + kc * 64 + cil) * kTaps + tap] * s;
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    const size_t base = ((size_t)(tap * 2 + kc) * 2) * kCh * 64;
+    out[base + (size_t)co * 64 + cil] = hi;
+    out[base + (size_t)kCh * 64 + (size_t)co * 64 + cil] = lo;
+  }
+}
+
+__global__ void tcn_pack_vec_kernel(const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                                    const float* __restrict__ bn_mean, const float* __restrict__ bn_var,
+                                    const float* __restrict__ res_w, float* __restrict__ bn_bias,
+                                    float* __restrict__ res) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= kCh) return;
+  const float s = bn_w[c] / sqrtf(bn_var[c] + 1e-5f);
+  bn_bias[c] = bn_b[c] - bn_mean[c] * s;
+  res[c] = res_w[c];
+}
+
+// =====================================================================================================================
+// FiLM precompute: one warp per (block, output row of Linear(2048 -> 256)); weight row kept in registers and reused for
+// every conditioning row.  Emits float4 (bn_bias, gamma, beta, res_scale) per (block, cond row, channel).
+// =====================================================================================================================
+template <int MAX_PER_LANE>
+__global__ void __launch_bounds__(256)
+tcn_film_kernel(const float* __restrict__ film_w, const float* __restrict__ film_b, const float* __restrict__ bn_bias,
+                const float* __restrict__ res, const float* __restrict__ cond, int n_blocks, int n_cond, int cond_dim,
+                float* __restrict__ out) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= n_blocks * 2 * kCh) return;
+  const int n = gw / (2 * kCh), row = gw % (2 * kCh);
+  const float* wr = film_w + (size_t)gw * cond_dim;
+  float wreg[MAX_PER_LANE];
+  const int per_lane = cond_dim / 32;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_LANE; ++i) wreg[i] = (i < per_lane) ? __ldg(wr + lane + 32 * i) : 0.f;
+  const float bias = film_b[gw];
+  const int c = row & (kCh - 1);
+  const int comp = row < kCh ? 1 : 2;  // gamma rows first, then beta (torch.split, network_utils.py:181)
+  for (int bc = 0; bc < n_cond; ++bc) {
+    const float* cr = cond + (size_t)bc * cond_dim;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_PER_LANE; ++i)
+      if (i < per_lane) s = fmaf(wreg[i], __ldg(cr + lane + 32 * i), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      float* q = out + (((size_t)n * n_cond + bc) * kCh + c) * 4;
+      q[comp] = s + bias;
+      if (comp == 1) {
+        q[0] = bn_bias[n * kCh + c];
+        q[3] = res[n * kCh + c];
+      }
+    }
+  }
+}
+
+// =====================================================================================================================
+// block 0 (C_in = 1 or 2, K = 15 or 30): CUDA cores, fp32 in -> split-bf16 activation rows out.  HBM-write bound.
+// Lane l owns channels {2l, 2l+1, 64+2l, 65+2l} so each warp store is one full 128-byte plane row.
+// =====================================================================================================================
+template <int NIN>
+__global__ void __launch_bounds__(256)
+tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const float4* __restrict__ film, int n_cond,
+                  uint8_t* __restrict__ act, int T) {
+  constexpr int ROWS = 256, HALO = 7;
+  __shared__ float xs[NIN][ROWS + 2 * HALO];
+  const int b = blockIdx.y, t0 = blockIdx.x * ROWS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < NIN * (ROWS + 2 * HALO); i += 256) {
+    const int ci = i / (ROWS + 2 * HALO), m = i % (ROWS + 2 * HALO);
+    const int t = t0 - HALO + m;  // dilation 1, zero padding 7 (architectures.py:199-206)
+    xs[ci][m] = (t >= 0 && t < T) ? __ldg(x + ((size_t)b * NIN + ci) * T + t) : 0.f;
+  }
+  const int ch[4] = {2 * lane, 2 * lane + 1, 64 + 2 * lane, 65 + 2 * lane};
+  float wr[4][NIN * kTaps];
+  float4 P[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int i = 0; i < NIN * kTaps; ++i) wr[q][i] = __ldg(w0 + ch[q] * NIN * kTaps + i);
+    P[q] = __ldg(film + (size_t)(n_cond > 1 ? b : 0) * kCh + ch[q]);
+  }
+  __syncthreads();
+  for (int r = warp * 32; r < warp * 32 + 32; ++r) {
+    const int t = t0 + r;
+    if (t >= T) break;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ci = 0; ci < NIN; ++ci)
+#pragma unroll
+      for (int j = 0; j < kTaps; ++j) {
+        const float xv = xs[ci][r + j];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = fmaf(wr[q][ci * kTaps + j], xv, acc[q]);
+      }
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v = acc[q] + P[q].x;
+      v = v > 0.f ? v : 0.01f * v;
+      // res = Conv1d(in, 128, k=1, groups=in): out channel c reads input channel c / (128/in)  (architectures.py:216-220)
+      const float xin = xs[ch[q] / (kCh / NIN)][r + HALO];
+      v = fmaf(P[q].y, v, P[q].z) + P[q].w * xin;
+      split_bf16(v, hi[q], lo[q]);
+    }
+    uint32_t* row = reinterpret_cast<uint32_t*>(act + ((size_t)b * T + t) * kRowBytes);
+    row[0 * 32 + lane] = pack_bf16(hi[0], hi[1]);
+    row[1 * 32 + lane] = pack_bf16(lo[0], lo[1]);
+    row[2 * 32 + lane] = pack_bf16(hi[2], hi[3]);
+    row[3 * 32 + lane] = pack_bf16(lo[2], lo[3]);
+  }
+}
+
+// fp32 [B][128][T]  <->  split-bf16 activation rows (module-level TCNBlock surface and per-block parity tests)
+__global__ void __launch_bounds__(256) tcn_act_pack_kernel(const float* __restrict__ x, uint8_t* __restrict__ act, int T) {
+  __shared__ float tile[kCh][33];
+  const int b = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int c = warp; c < kCh; c += 8) {
+    const int t = t0 + lane;
+    tile[c][lane] = t < T ? x[((size_t)b * kCh + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int r = warp; r < 32; r += 8) {
+    const int t = t0 + r;
+    if (t >= T) continue;
+    __nv_bfloat16 hi[4], lo[4];
+    const int ch[4] = {2 * lane, 2 * lane + 1, 64 + 2 * lane, 65 + 2 * lane};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_bf16(tile[ch[q]][r], hi[q], lo[q]);
+    uint32_t* row = reinterpret_cast<uint32_t*>(act + ((size_t)b * T + t) * kRowBytes);
+    row[0 * 32 + lane] = pack_bf16(hi[0], hi[1]);
+    row[1 * 32 + lane] = pack_bf16(lo[0], lo[1]);
+    row[2 * 32 + lane] = pack_bf16(hi[2], hi[3]);
+    row[3 * 32 + lane] = pack_bf16(lo[2], lo[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256) tcn_act_unpack_kernel(const uint8_t* __restrict__ act, float* __restrict__ y, int T) {
+  __shared__ float tile[kCh][33];
+  const int b = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int r = warp; r < 32; r += 8) {
+    const int t = t0 + r;
+    if (t >= T) continue;
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(act + ((size_t)b * T + t) * kRowBytes);
+    const uint32_t h0 = row[lane], l0 = row[32 + lane], h1 = row[64 + lane], l1 = row[96 + lane];
+    tile[2 * lane][r] = bf16_lo_f(h0) + bf16_lo_f(l0);
+    tile[2 * lane + 1][r] = bf16_hi_f(h0) + bf16_hi_f(l0);
+    tile[64 + 2 * lane][r] = bf16_lo_f(h1) + bf16_lo_f(l1);
+    tile[65 + 2 * lane][r] = bf16_hi_f(h1) + bf16_hi_f(l1);
+  }
+  __syncthreads();
+  for (int c = warp; c < kCh; c += 8) {
+    const int t = t0 + lane;
+    if (t < T) y[((size_t)b * kCh + c) * T + t] = tile[c][lane];
+  }
+}
+
+// =====================================================================================================================
+// the tcgen05 kernel
+// =====================================================================================================================
+struct TcnLayerArgs {
+  int B, T, dilation, tiles_per_seg, n_tiles, n_cond;
+  const float4* film;   // this block's [n_cond][128] (bn_bias, gamma, beta, res)
+  int fuse_out;         // 1 on the last block: Conv1d(128 -> n_out, k=1) + clamp fused, fp32 [B][n_out][T] written
+  int n_out;
+  const float* out_w;   // [n_out][128]
+  const float* out_b;   // [n_out]
+  float* out;
+};
+
+struct __align__(8) TcnBarriers {
+  uint64_t full[kNumSlots], empty[kNumSlots];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint64_t stage_full;
+  uint32_t tmem_base;
+};
+
+constexpr size_t kTcnSmemBytes = 1024 /*align slack*/ + (size_t)kNumSlots * kSlotBytes + kSlotBytes /*staging*/ + 256;
+
+// rows [ts, ts+128) of a shifted sub-tile intersect the real signal [0, T)?  (otherwise it is all zero padding)
+__device__ __forceinline__ bool tap_live(long long ts, int T) { return ts < (long long)T && ts + kSubRows > 0; }
+
+__global__ void __launch_bounds__(256, 1)
+tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                      const __grid_constant__ CUtensorMap tm_y, const TcnLayerArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem;                                  // kNumSlots x 32 KB, 1024-aligned
+  uint8_t* staging = smem + (size_t)kNumSlots * kSlotBytes;   // 32 KB epilogue tile (hi 16 KB | lo 16 KB)
+  TcnBarriers* bars = reinterpret_cast<TcnBarriers*>(staging + kSlotBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_x);
+    ptx::prefetch_tensormap(&tm_w);
+    ptx::prefetch_tensormap(&tm_y);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kNumSlots; ++i) {
+      ptx::mbar_init(&bars->full[i], 1);
+      ptx::mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars->tmem_full[i], 1);
+      ptx::mbar_init(&bars->tmem_empty[i], 128);
+    }
+    ptx::mbar_init(&bars->stage_full, 1);
+    ptx::mbar_fence_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&bars->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  const long long d = a.dilation;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int b = tile / a.tiles_per_seg;
+        const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
+        const bool sub1 = t0 + kSubRows < a.T;
+        for (int j = 0; j < kTaps; ++j) {
+          const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
+          const bool live0 = tap_live(ts0, a.T), live1 = sub1 && tap_live(ts1, a.T);
+          if (!live0 && !live1) continue;
+          for (int kc = 0; kc < 2; ++kc) {
+            // weights: rows ((j*2+kc)*2 + split)*128 .. : hi tile then lo tile
+            ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
+            ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
+            uint8_t* dst = ring + (size_t)slot * kSlotBytes;
+            const int wrow = ((j * 2 + kc) * 2) * kCh;
+            ptx::tma_load_2d(&tm_w, &bars->full[slot], dst, 0, wrow);
+            ptx::tma_load_2d(&tm_w, &bars->full[slot], dst + 16384, 0, wrow + kCh);
+            next();
+            if (live0) {
+              ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
+              ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
+              dst = ring + (size_t)slot * kSlotBytes;
+              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, (2 * kc) * 64, (int)ts0, b);
+              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + 16384, (2 * kc + 1) * 64, (int)ts0, b);
+              next();
+            }
+            if (live1) {
+              ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
+              ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
+              dst = ring + (size_t)slot * kSlotBytes;
+              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, (2 * kc) * 64, (int)ts1, b);
+              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + 16384, (2 * kc + 1) * 64, (int)ts1, b);
+              next();
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kSubRows, kCh);
+      uint32_t slot = 0, phase = 0;
+      auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
+      // 3-product split: (Xhi, Whi) + (Xlo, Whi) + (Xhi, Wlo), 4 K16 steps per 64-channel chunk
+      auto issue_group = [&](uint32_t x_addr, uint32_t w_addr, uint32_t d_tmem, bool first) {
+        const uint64_t xh = ptx::umma_desc_kmajor_sw128(x_addr), xl = ptx::umma_desc_kmajor_sw128(x_addr + 16384);
+        const uint64_t wh = ptx::umma_desc_kmajor_sw128(w_addr), wl = ptx::umma_desc_kmajor_sw128(w_addr + 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t adv = (uint64_t)(k * 32 >> 4);  // +32 bytes along K inside the 128-byte swizzle row
+          ptx::umma_bf16(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u);
+          ptx::umma_bf16(d_tmem, xl + adv, wh + adv, idesc, 1u);
+          ptx::umma_bf16(d_tmem, xh + adv, wl + adv, idesc, 1u);
+        }
+      };
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const int b = tile / a.tiles_per_seg;
+        const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
+        const bool sub1 = t0 + kSubRows < a.T;
+        const int buf = it & 1;
+        ptx::mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 + 0) * kCh, acc1 = tmem_base + (uint32_t)(buf * 2 + 1) * kCh;
+        bool first0 = true, first1 = true;
+        for (int j = 0; j < kTaps; ++j) {
+          const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
+          const bool live0 = tap_live(ts0, a.T), live1 = sub1 && tap_live(ts1, a.T);
+          if (!live0 && !live1) continue;
+          for (int kc = 0; kc < 2; ++kc) {
+            const uint32_t wslot = slot;
+            ptx::mbar_wait(&bars->full[wslot], phase);
+            const uint32_t w_addr = ptx::smem_u32(ring + (size_t)wslot * kSlotBytes);
+            next();
+            if (live0) {
+              ptx::mbar_wait(&bars->full[slot], phase);
+              ptx::tc_fence_after();
+              issue_group(ptx::smem_u32(ring + (size_t)slot * kSlotBytes), w_addr, acc0, first0);
+              first0 = false;
+              ptx::umma_commit(&bars->empty[slot]);
+              next();
+            }
+            if (live1) {
+              ptx::mbar_wait(&bars->full[slot], phase);
+              ptx::tc_fence_after();
+              issue_group(ptx::smem_u32(ring + (size_t)slot * kSlotBytes), w_addr, acc1, first1);
+              first1 = false;
+              ptx::umma_commit(&bars->empty[slot]);
+              next();
+            }
+            ptx::umma_commit(&bars->empty[wslot]);
+          }
+        }
+        ptx::umma_commit(&bars->tmem_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue (128 threads, thread <-> one time row) ==============================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int et = threadIdx.x - 128;       // 0..127
+    const int rl = q * 32 + lane;           // row inside the sub-tile == TMEM lane
+    uint32_t stage_phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / a.tiles_per_seg;
+      const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
+      const int buf = it & 1;
+      const float4* film = a.film + (size_t)(a.n_cond > 1 ? b : 0) * kCh;
+      ptx::mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      for (int sub = 0; sub < 2; ++sub) {
+        const int ts = t0 + sub * kSubRows;
+        if (ts >= a.T) break;
+        float o0 = 0.f, o1 = 0.f;
+        for (int h = 0; h < 2; ++h) {
+          // staging is free once the previous TMA store has read it and every thread has left the previous half
+          if (et == 0) ptx::tma_store_wait_read0();
+          ptx::named_bar_sync(1, 128);
+          if (et == 0) {
+            ptx::mbar_expect_tx(&bars->stage_full, kSlotBytes);
+            ptx::tma_load_3d(&tm_x, &bars->stage_full, staging, (2 * h) * 64, ts, b);              // x_in hi, ch 64h..
+            ptx::tma_load_3d(&tm_x, &bars->stage_full, staging + 16384, (2 * h + 1) * 64, ts, b);  // x_in lo
+          }
+          uint32_t acc[64];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * kCh + h * 64);
+          ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+          ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+          ptx::tmem_ld_wait();
+          ptx::mbar_wait(&bars->stage_full, stage_phase);
+          stage_phase ^= 1;
+          uint8_t* rowp = staging + rl * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int off = ((c ^ (rl & 7)) << 4);  // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+            const uint4 xh = *reinterpret_cast<const uint4*>(rowp + off);
+            const uint4 xl = *reinterpret_cast<const uint4*>(rowp + 16384 + off);
+            const uint32_t xhw[4] = {xh.x, xh.y, xh.z, xh.w}, xlw[4] = {xl.x, xl.y, xl.z, xl.w};
+            uint32_t oh[4], ol[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float v[2];
+#pragma unroll
+              for (int s = 0; s < 2; ++s) {
+                const int cl = c * 8 + e * 2 + s;
+                const int ch = h * 64 + cl;
+                const float4 P = __ldg(film + ch);
+                const float xin = s == 0 ? bf16_lo_f(xhw[e]) + bf16_lo_f(xlw[e]) : bf16_hi_f(xhw[e]) + bf16_hi_f(xlw[e]);
+                float u = __uint_as_float(acc[cl]) + P.x;
+                u = u > 0.f ? u : 0.01f * u;
+                u = fmaf(P.y, u, P.z) + P.w * xin;
+                v[s] = u;
+                if (a.fuse_out) {
+                  o0 = fmaf(u, __ldg(a.out_w + ch), o0);
+                  if (a.n_out > 1) o1 = fmaf(u, __ldg(a.out_w + kCh + ch), o1);
+                }
+              }
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(v[0], h0, l0);
+              split_bf16(v[1], h1, l1);
+              oh[e] = pack_bf16(h0, h1);
+              ol[e] = pack_bf16(l0, l1);
+            }
+            if (!a.fuse_out) {
+              *reinterpret_cast<uint4*>(rowp + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+              *reinterpret_cast<uint4*>(rowp + 16384 + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+            }
+          }
+          if (!a.fuse_out) {
+            ptx::fence_proxy_async_smem();
+            ptx::named_bar_sync(2, 128);
+            if (et == 0) {
+              ptx::tma_store_3d(&tm_y, staging, (2 * h) * 64, ts, b);
+              ptx::tma_store_3d(&tm_y, staging + 16384, (2 * h + 1) * 64, ts, b);
+              ptx::tma_store_commit();
+            }
+          }
+        }
+        if (a.fuse_out) {
+          const int t = ts + rl;
+          if (t < a.T) {
+            // clamp(output(x), -1, 1)   architectures.py:143-145
+            a.out[((size_t)b * a.n_out + 0) * a.T + t] = fminf(fmaxf(o0 + __ldg(a.out_b), -1.f), 1.f);
+            if (a.n_out > 1) a.out[((size_t)b * a.n_out + 1) * a.T + t] = fminf(fmaxf(o1 + __ldg(a.out_b + 1), -1.f), 1.f);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars->tmem_empty[buf]);
+    }
+    if (et == 0) ptx::tma_store_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+static int encode_act_map(CUtensorMap* m, const void* base, int B, int T) {
+  PFN_encodeTiled enc = tensor_map_encoder();
+  if (!enc) return 1;
+  // dims (fastest first): 256 bf16 per time row (4 planes x 64), T rows, B segments; box = one plane x 128 rows
+  cuuint64_t dims[3] = {256, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)kRowBytes, (cuuint64_t)T * kRowBytes};
+  cuuint32_t box[3] = {64, (cuuint32_t)kSubRows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation B=%d T=%d) failed: CUresult %d", B, T, (int)r);
+  return 0;
+}
+
+static int encode_w_map(CUtensorMap* m, const void* base) {
+  PFN_encodeTiled enc = tensor_map_encoder();
+  if (!enc) return 1;
+  cuuint64_t dims[2] = {64, (cuuint64_t)kWRowsPerLayer};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, (cuuint32_t)kCh};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: CUresult %d", (int)r);
+  return 0;
+}
+
+// one dilated block (n >= 1): act_in -> act_out, or -> fp32 `out` when fuse_out
+static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, const TcnPacked& L, int n,
+                             const uint8_t* act_in, uint8_t* act_out, const float* film, int n_cond, int B, int T,
+                             bool fuse_out, float* out, cudaStream_t st) {
+  const long long d = block_dilation(cfg, n);
+  MST_CHECK(7 * d + kTileRows < (1ll << 31) - T, "tcn: dilation %lld too large", d);
+  CUtensorMap tm_x, tm_w, tm_y;
+  if (encode_act_map(&tm_x, act_in, B, T)) return 1;
+  if (encode_act_map(&tm_y, fuse_out ? act_in : act_out, B, T)) return 1;
+  if (encode_w_map(&tm_w, packed + L.wumma + (size_t)(n - 1) * kWRowsPerLayer * 128)) return 1;
+  TcnLayerArgs a;
+  a.B = B; a.T = T; a.dilation = (int)d;
+  a.tiles_per_seg = cdiv(T, kTileRows);
+  a.n_tiles = B * a.tiles_per_seg;
+  a.n_cond = n_cond;
+  a.film = reinterpret_cast<const float4*>(film) + (size_t)n * n_cond * kCh;
+  a.fuse_out = fuse_out ? 1 : 0;
+  a.n_out = cfg->n_outputs;
+  a.out_w = reinterpret_cast<const float*>(packed + L.out_w);
+  a.out_b = reinterpret_cast<const float*>(packed + L.out_b);
+  a.out = out;
+  MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));
+  const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
+  tcn_block_umma_kernel<<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_y, a);
+  return launch_ok("tcn_block_umma_kernel");
+}
+
+static int launch_block0(const mst_tcn_config* cfg, const uint8_t* packed, const TcnPacked& L, const float* x,
+                         const float* film, int n_cond, uint8_t* act, int B, int T, cudaStream_t st) {
+  dim3 grid(cdiv(T, 256), B);
+  const float* w0 = reinterpret_cast<const float*>(packed + L.w0);
+  const float4* f = reinterpret_cast<const float4*>(film);
+  if (cfg->n_inputs == 2) tcn_block0_kernel<2><<<grid, 256, 0, st>>>(x, w0, f, n_cond, act, T);
+  else tcn_block0_kernel<1><<<grid, 256, 0, st>>>(x, w0, f, n_cond, act, T);
+  return launch_ok("tcn_block0_kernel");
+}
+
+static size_t act_bytes(int B, int L) { return align_up((size_t)B * L * kRowBytes, 1024); }
+
+}  // namespace mst
+
+using namespace mst;
+
+extern "C" {
+
+size_t mst_tcn_packed_bytes(const mst_tcn_config* cfg) {
+  TcnPacked L;
+  if (tcn_layout(cfg, &L)) return 0;
+  return L.total;
+}
+
+int mst_tcn_pack(const mst_tcn_config* cfg, const void* const* raw, void* packed_v, void* stream) {
+  TcnPacked L;
+  if (tcn_layout(cfg, &L)) return 1;
+  MST_CHECK(raw && packed_v, "tcn_pack: null pointer");
+  MST_CHECK((reinterpret_cast<uintptr_t>(packed_v) & 1023) == 0, "tcn_pack: packed buffer must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* packed = reinterpret_cast<uint8_t*>(packed_v);
+  for (int n = 0; n < cfg->n_blocks; ++n) {
+    const float* conv_w = (const float*)raw[8 * n + 0];
+    const float* bn_w = (const float*)raw[8 * n + 1];
+    const float* bn_b = (const float*)raw[8 * n + 2];
+    const float* bn_m = (const float*)raw[8 * n + 3];
+    const float* bn_v = (const float*)raw[8 * n + 4];
+    const float* res_w = (const float*)raw[8 * n + 5];
+    const float* film_w = (const float*)raw[8 * n + 6];
+    const float* film_b = (const float*)raw[8 * n + 7];
+    MST_CHECK(conv_w && bn_w && bn_b && bn_m && bn_v && res_w && film_w && film_b, "tcn_pack: null weight in block %d", n);
+    if (n == 0) {
+      tcn_pack_block0_kernel<<<16, 256, 0, st>>>(conv_w, bn_w, bn_v, cfg->n_inputs, (float*)(packed + L.w0));
+    } else {
+      tcn_pack_umma_kernel<<<256, 256, 0, st>>>(
+          conv_w, bn_w, bn_v, (__nv_bfloat16*)(packed + L.wumma) + (size_t)(n - 1) * kWRowsPerLayer * 64);
+    }
+    tcn_pack_vec_kernel<<<1, 128, 0, st>>>(bn_w, bn_b, bn_m, bn_v, res_w, (float*)(packed + L.bn_bias) + n * kCh,
+                                           (float*)(packed + L.res) + n * kCh);
+    MST_CUDA_OK(cudaMemcpyAsync(packed + L.film_w + (size_t)n * 2 * kCh * cfg->cond_dim * 4, film_w,
+                                (size_t)2 * kCh * cfg->cond_dim * 4, cudaMemcpyDeviceToDevice, st));
+    MST_CUDA_OK(cudaMemcpyAsync(packed + L.film_b + (size_t)n * 2 * kCh * 4, film_b, (size_t)2 * kCh * 4,
+                                cudaMemcpyDeviceToDevice, st));
+  }
+  const void* out_w = raw[8 * cfg->n_blocks], *out_b = raw[8 * cfg->n_blocks + 1];
+  MST_CHECK(out_w && out_b, "tcn_pack: null output weight");
+  MST_CUDA_OK(cudaMemcpyAsync(packed + L.out_w, out_w, (size_t)cfg->n_outputs * kCh * 4, cudaMemcpyDeviceToDevice, st));
+  MST_CUDA_OK(cudaMemcpyAsync(packed + L.out_b, out_b, (size_t)cfg->n_outputs * 4, cudaMemcpyDeviceToDevice, st));
+  return launch_ok("tcn_pack kernels");
+}
+
+int mst_tcn_film_precompute(const mst_tcn_config* cfg, const void* packed_v, const float* cond, int n_cond,
+                            float* film_out, void* stream) {
+  TcnPacked L;
+  if (tcn_layout(cfg, &L)) return 1;
+  MST_CHECK(packed_v && cond && film_out && n_cond >= 1, "tcn_film_precompute: bad arguments");
+  const uint8_t* packed = reinterpret_cast<const uint8_t*>(packed_v);
+  const int warps = cfg->n_blocks * 2 * kCh;
+  tcn_film_kernel<128><<<cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>(
+      (const float*)(packed + L.film_w), (const float*)(packed + L.film_b), (const float*)(packed + L.bn_bias),
+      (const float*)(packed + L.res), cond, cfg->n_blocks, n_cond, cfg->cond_dim, film_out);
+  return launch_ok("tcn_film_kernel");
+}
+
+size_t mst_tcn_workspace_bytes(const mst_tcn_config* cfg, int B, int L) {
+  if (!cfg || B <= 0 || L <= 0) return 0;
+  return 2 * act_bytes(B, L);
+}
+
+int mst_tcn_forward(const mst_tcn_config* cfg, const void* packed_v, const float* x, const float* film, int n_cond,
+                    float* y, int B, int L, void* workspace, size_t workspace_bytes, void* stream) {
+  TcnPacked P;
+  if (tcn_layout(cfg, &P)) return 1;
+  MST_CHECK(packed_v && x && film && y && workspace, "tcn_forward: null pointer");
+  MST_CHECK(B > 0 && L > 0 && B <= 65535, "tcn_forward: bad shape B=%d L=%d", B, L);
+  MST_CHECK(n_cond == 1 || n_cond == B, "tcn_forward: n_cond must be 1 or B (got %d, B=%d)", n_cond, B);
+  MST_CHECK(workspace_bytes >= mst_tcn_workspace_bytes(cfg, B, L), "tcn_forward: workspace too small (%zu < %zu)",
+            workspace_bytes, mst_tcn_workspace_bytes(cfg, B, L));
+  MST_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "tcn_forward: workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint8_t* packed = reinterpret_cast<const uint8_t*>(packed_v);
+  uint8_t* act[2] = {(uint8_t*)workspace, (uint8_t*)workspace + act_bytes(B, L)};
+  if (launch_block0(cfg, packed, P, x, film, n_cond, act[0], B, L, st)) return 1;
+  int cur = 0;
+  for (int n = 1; n < cfg->n_blocks; ++n) {
+    const bool last = n == cfg->n_blocks - 1;
+    if (launch_umma_block(cfg, packed, P, n, act[cur], act[cur ^ 1], film, n_cond, B, L, last, y, st)) return 1;
+    cur ^= 1;
+  }
+  return 0;
+}
+
+int mst_tcn_block_forward(const mst_tcn_config* cfg, const void* packed_v, int block, const float* x, const float* film,
+                          int n_cond, float* y, int B, int L, void* workspace, size_t workspace_bytes, void* stream) {
+  TcnPacked P;
+  if (tcn_layout(cfg, &P)) return 1;
+  MST_CHECK(packed_v && x && film && y && workspace, "tcn_block_forward: null pointer");
+  MST_CHECK(block >= 0 && block < cfg->n_blocks, "tcn_block_forward: block %d out of range", block);
+  MST_CHECK(B > 0 && L > 0 && B <= 65535, "tcn_block_forward: bad shape B=%d L=%d", B, L);
+  MST_CHECK(n_cond == 1 || n_cond == B, "tcn_block_forward: n_cond must be 1 or B");
+  MST_CHECK(workspace_bytes >= mst_tcn_workspace_bytes(cfg, B, L), "tcn_block_forward: workspace too small");
+  MST_CHECK((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "tcn_block_forward: workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint8_t* packed = reinterpret_cast<const uint8_t*>(packed_v);
+  uint8_t* act[2] = {(uint8_t*)workspace, (uint8_t*)workspace + act_bytes(B, L)};
+  dim3 grid(cdiv(L, 32), B);
+  if (block == 0) {
+    // film for block 0 sits at the start of the table
+    if (launch_block0(cfg, packed, P, x, film, n_cond, act[1], B, L, st)) return 1;
+  } else {
+    tcn_act_pack_kernel<<<grid, 256, 0, st>>>(x, act[0], L);
+    if (launch_ok("tcn_act_pack_kernel")) return 1;
+    if (launch_umma_block(cfg, packed, P, block, act[0], act[1], film, n_cond, B, L, false, nullptr, st)) return 1;
+  }
+  tcn_act_unpack_kernel<<<grid, 256, 0, st>>>(act[1], y, L);
+  return launch_ok("tcn_act_unpack_kernel");
+}
+
+}  // extern "C"

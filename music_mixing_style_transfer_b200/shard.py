@@ -1,0 +1,94 @@
+"""Multi-GPU shard layer for the segment-batched forward (one process per GPU, torch.distributed over NCCL/NVLink).
+
+Segments are independent through the TCN (zero padding per segment, BatchNorm in eval mode, no cross-batch op --
+reference architectures.py:222-234), so the path partitions over the batch with NO data-path collective inside the
+network.  The only exchanges are the ones BASELINE's north_star names: one broadcast of the 2048-float reference
+embedding and one all-gather of the output segments.  The reference itself is single-device
+(inference/style_transfer.py:29-32,327); this layer is the B200 addition inside its orchestration level.
+
+Works with any initialised process group: `nccl` on the GPU box, `gloo` in the CPU tests of the index logic.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world(group=None) -> Tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_bounds(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous partition of range(n_items); the first n_items % world_size ranks get one extra item."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    base, rem = divmod(n_items, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_counts(n_items: int, world_size: int) -> List[int]:
+    return [shard_bounds(n_items, world_size, r)[1] - shard_bounds(n_items, world_size, r)[0] for r in range(world_size)]
+
+
+def broadcast_embedding(emb: Optional[torch.Tensor], shape, device, src: int = 0, group=None) -> torch.Tensor:
+    """Rank `src` holds `emb` ([2048] or [n, 2048]); every rank returns it.  8-16 KiB, latency bound."""
+    rank, ws = world(group)
+    if ws == 1:
+        return emb
+    if rank != src:
+        emb = torch.empty(shape, dtype=torch.float32, device=device)
+    else:
+        emb = emb.contiguous()
+    dist.broadcast(emb, src=src, group=group)
+    return emb
+
+
+def allgather_segments(local: torch.Tensor, counts: List[int], group=None) -> torch.Tensor:
+    """local: this rank's [counts[rank], C, L] output segments -> [sum(counts), C, L] on every rank, in rank order.
+    Even shards go through one all_gather_into_tensor (a single NCCL all-gather over NVLink); ragged shards are padded
+    to the largest count and trimmed."""
+    rank, ws = world(group)
+    if ws == 1:
+        return local
+    if local.shape[0] != counts[rank]:
+        raise RuntimeError(f"rank {rank}: local shard has {local.shape[0]} segments, expected {counts[rank]}")
+    mx = max(counts)
+    tail = tuple(local.shape[1:])
+    if mx == 0:
+        return local.new_empty((0,) + tail)
+    if local.shape[0] < mx:
+        pad = local.new_zeros((mx - local.shape[0],) + tail)
+        local = torch.cat([local, pad], dim=0)
+    local = local.contiguous()
+    out = local.new_empty((ws * mx,) + tail)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, local, group=group)
+    else:  # gloo (CPU tests)
+        parts = [local.new_empty(local.shape) for _ in range(ws)]
+        dist.all_gather(parts, local, group=group)
+        out = torch.cat(parts, dim=0)
+    if all(c == mx for c in counts):
+        return out
+    return torch.cat([out[r * mx:r * mx + counts[r]] for r in range(ws)], dim=0)
+
+
+def sharded_style_transfer(encoder, converter, reference_batch: Optional[torch.Tensor], input_shard: torch.Tensor,
+                           total_segments: int, cond_dim: int = 2048, gather: bool = True, group=None):
+    """One sharded forward step.
+      reference_batch: [B_ref, 2, L_ref] on rank 0 (ignored elsewhere)  -> encoder -> mean embedding -> broadcast
+      input_shard:     this rank's contiguous [B_local, 2, L] slice of the `total_segments` input segments
+    Returns (embedding [cond_dim], output) where output is the gathered [total_segments, 2, L] (gather=True) or the
+    local shard.  `encoder` / `converter` are callables with the FXencoder / TCNModel forward signatures."""
+    rank, ws = world(group)
+    emb = None
+    if rank == 0:
+        emb = encoder(reference_batch).mean(dim=0)       # inference/style_transfer.py:152-153
+    emb = broadcast_embedding(emb, (cond_dim,), input_shard.device, src=0, group=group)
+    out = converter(input_shard, emb.unsqueeze(0))       # :161 (cond broadcast over the batch)
+    if gather and ws > 1:
+        out = allgather_segments(out, shard_counts(total_segments, ws), group=group)
+    return emb, out
