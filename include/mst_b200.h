@@ -99,6 +99,17 @@ size_t mst_tcn_workspace_bytes(const mst_tcn_config* cfg, int B, int L);
 int mst_tcn_forward(const mst_tcn_config* cfg, const void* packed, const float* x, const float* film, int n_cond,
                     float* y, int B, int L, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Layer-granular launches on the INTERNAL activation format (DESIGN.md "data layout": act[b][t][4 planes][64] bf16,
+ * 512 bytes per time step, B*L*512 bytes per buffer, 1024-byte aligned).  mst_tcn_forward is exactly
+ * block0 + layer(1) ... layer(n_blocks-1, fuse_out=1); these entry points exist so a host can time or interleave
+ * individual launches (bench.py's roofline leg).
+ *   block0: x fp32 [B,n_inputs,L] -> act_out.   layer n>=1: act_in -> act_out, or, when fuse_out != 0 (last block),
+ *   -> y fp32 [B,n_outputs,L] = clamp(Conv1d(128->n_out,k=1)(block(act_in)), -1, 1) and act_out is not written. */
+int mst_tcn_block0_forward(const mst_tcn_config* cfg, const void* packed, const float* x, const float* film, int n_cond,
+                           void* act_out, int B, int L, void* stream);
+int mst_tcn_layer_forward(const mst_tcn_config* cfg, const void* packed, int block, const void* act_in, void* act_out,
+                          const float* film, int n_cond, int B, int L, int fuse_out, float* y, void* stream);
+
 /* single TCNBlock n on fp32 [B,C,L] tensors (module-level surface + per-dilation parity tests):
  * y[B,128,L] = film(leaky_relu(bn(conv1(x)))) + res(x).  workspace >= mst_tcn_workspace_bytes(cfg,B,L). */
 int mst_tcn_block_forward(const mst_tcn_config* cfg, const void* packed, int block, const float* x, const float* film,

@@ -48,6 +48,10 @@ SIGNATURES = {
     "mst_tcn_workspace_bytes": (c_size_t, [POINTER(TcnConfig), c_int, c_int]),
     "mst_tcn_forward": (c_int, [POINTER(TcnConfig), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                 c_void_p, c_size_t, c_void_p]),
+    "mst_tcn_block0_forward": (c_int, [POINTER(TcnConfig), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                                       c_void_p]),
+    "mst_tcn_layer_forward": (c_int, [POINTER(TcnConfig), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                      c_int, c_int, c_void_p, c_void_p]),
     "mst_tcn_block_forward": (c_int, [POINTER(TcnConfig), c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                       c_int, c_void_p, c_size_t, c_void_p]),
     "mst_fx_workspace_bytes": (c_size_t, [c_int, c_int]),

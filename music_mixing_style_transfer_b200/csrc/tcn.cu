@@ -695,6 +695,30 @@ int mst_tcn_forward(const mst_tcn_config* cfg, const void* packed_v, const float
   return 0;
 }
 
+int mst_tcn_block0_forward(const mst_tcn_config* cfg, const void* packed_v, const float* x, const float* film, int n_cond,
+                           void* act_out, int B, int L, void* stream) {
+  TcnPacked P;
+  if (tcn_layout(cfg, &P)) return 1;
+  MST_CHECK(packed_v && x && film && act_out, "tcn_block0_forward: null pointer");
+  MST_CHECK(B > 0 && L > 0 && B <= 65535 && (n_cond == 1 || n_cond == B), "tcn_block0_forward: bad shape");
+  return launch_block0(cfg, reinterpret_cast<const uint8_t*>(packed_v), P, x, film, n_cond, (uint8_t*)act_out, B, L,
+                       (cudaStream_t)stream);
+}
+
+int mst_tcn_layer_forward(const mst_tcn_config* cfg, const void* packed_v, int block, const void* act_in, void* act_out,
+                          const float* film, int n_cond, int B, int L, int fuse_out, float* y, void* stream) {
+  TcnPacked P;
+  if (tcn_layout(cfg, &P)) return 1;
+  MST_CHECK(packed_v && act_in && film, "tcn_layer_forward: null pointer");
+  MST_CHECK(block >= 1 && block < cfg->n_blocks, "tcn_layer_forward: block %d out of range [1,%d)", block, cfg->n_blocks);
+  MST_CHECK(B > 0 && L > 0 && (n_cond == 1 || n_cond == B), "tcn_layer_forward: bad shape");
+  MST_CHECK(fuse_out ? (y != nullptr) : (act_out != nullptr), "tcn_layer_forward: missing output buffer");
+  MST_CHECK((reinterpret_cast<uintptr_t>(act_in) & 1023) == 0 && (reinterpret_cast<uintptr_t>(act_out) & 1023) == 0,
+            "tcn_layer_forward: activation buffers must be 1024-byte aligned");
+  return launch_umma_block(cfg, reinterpret_cast<const uint8_t*>(packed_v), P, block, (const uint8_t*)act_in,
+                           (uint8_t*)act_out, film, n_cond, B, L, fuse_out != 0, y, (cudaStream_t)stream);
+}
+
 int mst_tcn_block_forward(const mst_tcn_config* cfg, const void* packed_v, int block, const float* x, const float* film,
                           int n_cond, float* y, int B, int L, void* workspace, size_t workspace_bytes, void* stream) {
   TcnPacked P;

@@ -264,6 +264,37 @@ class TCNModel(nn.Module):
                                                 ws.numel(), _cabi.current_stream()), "tcn_forward")
         return out
 
+    def forward_layers(self, x, cond, on_launch=None):
+        """Same computation as forward(), one C-ABI call per kernel launch.  `on_launch(name, phase)` is called with
+        phase 'begin' / 'end' around every launch (bench.py records CUDA events there for the roofline leg)."""
+        x = _cabi.require_cuda_f32(x, "TCNModel input")
+        hp = self.hparams
+        B, _, L = x.shape
+        eng = self._engine
+        eng.pack(self._raw(), _param_signature(self), x.device)
+        film = eng.film(cond, hp.nblocks)
+        n_cond = film.shape[1]
+        ws = eng.workspace(B, L, x.device)
+        half = ws.numel() // 2
+        act = [ws[:half], ws[half:]]
+        out = torch.empty(B, hp.noutputs, L, dtype=torch.float32, device=x.device)
+        lib, cfg, st = _cabi.lib(), ctypes.byref(eng.cfg), _cabi.current_stream()
+        note = on_launch if on_launch is not None else (lambda name, phase: None)
+        note("tcn_block0_kernel", "begin")
+        _cabi.check(lib.mst_tcn_block0_forward(cfg, _cabi.ptr(eng.packed), _cabi.ptr(x), _cabi.ptr(film), n_cond,
+                                               _cabi.ptr(act[0]), B, L, st), "tcn_block0_forward")
+        note("tcn_block0_kernel", "end")
+        cur = 0
+        for n in range(1, hp.nblocks):
+            last = n == hp.nblocks - 1
+            note("tcn_block_umma_kernel", "begin")
+            _cabi.check(lib.mst_tcn_layer_forward(cfg, _cabi.ptr(eng.packed), n, _cabi.ptr(act[cur]),
+                                                  _cabi.ptr(act[cur ^ 1]), _cabi.ptr(film), n_cond, B, L,
+                                                  1 if last else 0, _cabi.ptr(out), st), "tcn_layer_forward")
+            note("tcn_block_umma_kernel", "end")
+            cur ^= 1
+        return out
+
     def compute_receptive_field(self):
         """ Compute the receptive field in samples."""
         rf = self.hparams.kernel_size

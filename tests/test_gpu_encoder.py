@@ -1,0 +1,67 @@
+"""FXencoder parity on the GPU: every Conv1d_layer geometry of configs.yaml, Res_ConvBlock, full encoder, golden."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_helpers import err_stats, models, oracle_threads, state_dicts
+from oracle import fixtures, networks_oracle as O, weights as W
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_is_sm100():
+    from music_mixing_style_transfer_b200 import _cabi
+    _cabi.check(_cabi.lib().mst_device_check(0), "device_check")
+
+
+@pytest.mark.parametrize("blk", list(range(12)))
+def test_res_conv_block_matches_oracle(blk):
+    """Each of the 12 blocks alone (both convs: reflect pad even/odd k, stride, residual) on an odd-length input."""
+    oracle_threads()
+    enc, _ = models()
+    esd, _ = state_dicts()
+    cin = W.ENC_CHANNELS[blk]
+    k, s = W.ENC_KERNELS[blk], W.ENC_STRIDES[blk]
+    T = {0: 4099, 1: 2051, 2: 1027}.get(blk, 131 if cin >= 512 else 517)   # not multiples of the stride / tile
+    g = torch.Generator()
+    g.manual_seed(40 + blk)
+    x = torch.randn(2, cin, T, generator=g) * 0.5
+    with torch.no_grad():
+        ref = O.res_conv_block(x, esd, f"encoder.{blk}", k, s)
+        c1_ref = O.conv1d_layer(x, esd, f"encoder.{blk}.conv1.conv1d", k, 1)
+        got = enc.encoder[blk](x.cuda()).cpu()
+        c1 = enc.encoder[blk].conv1(x.cuda()).cpu()
+    assert got.shape == ref.shape == (2, W.ENC_CHANNELS[blk + 1], -(-T // s))
+    e1, e2 = err_stats(c1, c1_ref), err_stats(got, ref)
+    assert e1["max"] <= 2e-4 * max(1.0, e1["ref_rms"] * 10), (blk, e1)
+    assert e2["rms"] <= 1e-5 * max(1.0, e2["ref_rms"]) and e2["max"] <= 5e-4 * max(1.0, e2["ref_rms"]), (blk, e2)
+
+
+@pytest.mark.parametrize("B,L", [(2, 32768), (1, 44100), (3, 20011)])
+def test_full_encoder_matches_oracle(B, L):
+    oracle_threads()
+    enc, _ = models()
+    esd, _ = state_dicts()
+    x = W.synthetic_audio(B, L, seed=50 + B)
+    with torch.no_grad():
+        ref = O.fxencoder_forward(x, esd, W.ENC_KERNELS, W.ENC_STRIDES)
+        got = enc(x.cuda()).cpu()
+    e = err_stats(got, ref)
+    assert got.shape == (B, 2048)
+    assert e["max"] <= 1e-4 and e["rel"] <= 2e-5, e     # embeddings: max-abs and relative L2
+
+
+def test_encoder_golden_vector():
+    enc, _ = models()
+    x = W.synthetic_audio(2, 32768, seed=11)
+    with torch.no_grad():
+        got = enc(x.cuda()).cpu().numpy()
+    ref = fixtures.load_golden("enc_small.npz")["emb"]
+    e = err_stats(got, ref)
+    assert e["max"] <= 1e-4 and e["rel"] <= 2e-5, e
+
+
+def test_too_short_input_raises_like_reflection_pad():
+    enc, _ = models()
+    with pytest.raises(RuntimeError):
+        enc.encoder[0].conv1(torch.zeros(1, 2, 8).cuda())

@@ -1,0 +1,143 @@
+"""Host-side logic: module surfaces / state_dict layout, segmentation, shard partition, 2-rank gloo exchange (CPU)."""
+import copy
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+import yaml
+
+from music_mixing_style_transfer_b200 import shard
+from music_mixing_style_transfer_b200.networks import FXencoder, TCNModel, TCNBlock
+from oracle import weights as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_models():
+    cfg = yaml.full_load(open(os.path.join(ROOT, "music_mixing_style_transfer_b200", "inference", "configs.yaml")))
+    enc_cfg = cfg["Effects_Encoder"]["default"]
+    before = copy.deepcopy(enc_cfg)
+    enc = FXencoder(enc_cfg)
+    assert enc_cfg == before, "constructor must not mutate the caller's config"
+    FXencoder(enc_cfg)  # second construction from the same dict works (the reference's would not)
+    c = cfg["TCN"]["default"]
+    tcn = TCNModel(nparams=c["condition_dimension"], ninputs=2, noutputs=2, nblocks=c["nblocks"],
+                   dilation_growth=c["dilation_growth"], kernel_size=c["kernel_size"], channel_width=c["channel_width"],
+                   stack_size=c["stack_size"], cond_dim=c["condition_dimension"], causal=c["causal"])
+    return enc, tcn
+
+
+def test_state_dict_layout_matches_reference_keys():
+    enc, tcn = build_models()
+    esd, tsd = W.make_encoder_state_dict(0), W.make_tcn_state_dict(0)
+    assert list(enc.state_dict().keys()) == list(esd.keys())
+    assert list(tcn.state_dict().keys()) == list(tsd.keys())
+    for k, v in enc.state_dict().items():
+        assert v.shape == esd[k].shape, k
+    for k, v in tcn.state_dict().items():
+        assert v.shape == tsd[k].shape, k
+    enc.load_state_dict(esd)
+    tcn.load_state_dict(tsd)
+    # DDP checkpoints carry a 7-char `module.` prefix that reload_weights strips (inference/style_transfer.py:102)
+    ddp = {"module." + k: v for k, v in tsd.items()}
+    tcn.load_state_dict({k[7:]: v for k, v in ddp.items()})
+    assert tcn.compute_receptive_field() == 229363
+    assert tcn.hparams.kernel_size == 15 and tcn.hparams["nblocks"] == 14
+    assert isinstance(tcn.blocks[3], TCNBlock) and tcn.blocks[3].dilation == 8 and tcn.blocks[3].pad_length == 56
+
+
+def test_no_cpu_fallback():
+    enc, tcn = build_models()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc(torch.zeros(1, 2, 4096))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tcn(torch.zeros(1, 2, 4096), torch.zeros(1, 2048))
+    from music_mixing_style_transfer_b200.mixing_manipulator import fx_chain_forward
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fx_chain_forward(torch.zeros(1, 2, 64), torch.zeros(1, 20))
+
+
+def test_unsupported_variants_raise():
+    with pytest.raises(NotImplementedError):
+        TCNModel(nparams=2048, causal=True)
+    with pytest.raises(NotImplementedError):
+        TCNModel(nparams=2048, grouped=True)
+    from music_mixing_style_transfer_b200.mixing_manipulator import create_effects_augmentation_chain
+    with pytest.raises(NotImplementedError):
+        create_effects_augmentation_chain(["eq", "reverb"])
+    with pytest.raises(ValueError):
+        create_effects_augmentation_chain(["wobble"])
+    chain = create_effects_augmentation_chain(["eq", ("comp", 0.5), "imager", "gain"])
+    assert [(f.name, p, n) for f, p, n in chain.fxs] == [("Equaliser", 1, True), ("Compressor", 0.5, True),
+                                                          ("IMAGER", 1, True), ("Gain", 1, False)]
+    assert chain.param_tensor(3).shape == (3, 20)
+
+
+def test_entry_point_segmentation_matches_oracle():
+    from music_mixing_style_transfer_b200.inference.style_transfer import Mixing_Style_Transfer_Inference, build_parser
+    from oracle import networks_oracle as O
+    args = build_parser().parse_args(["--segment_length", "250", "--batch_size", "3"])
+    assert args.segment_length_ref == 2 ** 19 and args.interpolate_segments == 30 and args.normalize_input is True
+    obj = Mixing_Style_Transfer_Inference.__new__(Mixing_Style_Transfer_Inference)
+    obj.args = args
+    song = torch.randn(2, 1000)
+    ours = obj.batchwise_segmentization(song, "s", segment_length=250)
+    ref = O.batchwise_segmentization(song, 250, 3)
+    assert len(ours) == len(ref) and all(torch.equal(a, b) for a, b in zip(ours, ref))
+    with pytest.raises(AssertionError):
+        obj.batchwise_segmentization(torch.randn(2, 100), "s", segment_length=250)
+
+
+def test_shard_bounds_cover_everything_once():
+    for n in (0, 1, 7, 32, 33, 512):
+        for ws in (1, 2, 3, 4, 8):
+            spans = [shard.shard_bounds(n, ws, r) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+            counts = shard.shard_counts(n, ws)
+            assert sum(counts) == n and max(counts) - min(counts) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, ws, port, n_total, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        torch.manual_seed(0)
+        full = torch.randn(n_total, 2, 37)                       # every rank can rebuild the full batch
+        ref = torch.randn(5, 2, 64)
+        enc = lambda x: x.mean(dim=-1).repeat(1, 8)             # noqa: E731  stand-in encoder -> [B, 16]
+        conv = lambda x, c: x * 2.0 + c[0, :1]                   # noqa: E731  stand-in converter
+        lo, hi = shard.shard_bounds(n_total, ws, rank)
+        emb, out = shard.sharded_style_transfer(enc, conv, ref if rank == 0 else None, full[lo:hi], n_total, cond_dim=16)
+        expect_emb = enc(ref).mean(dim=0)
+        ok = torch.allclose(emb, expect_emb) and torch.equal(out, full * 2.0 + expect_emb[:1])
+        q.put((rank, bool(ok), tuple(out.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [8, 7, 1])
+def test_two_rank_gloo_broadcast_and_allgather(n_total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [True, True], res
+    assert all(r[2] == (n_total, 2, 37) for r in res)

@@ -1,0 +1,106 @@
+"""Pins the oracle (oracle/networks_oracle.py, oracle/fx_oracle.py) -- CPU only.
+
+ (1) against the committed golden vectors in tests/golden/ (outputs of the UNMODIFIED reference, produced by
+     oracle/make_golden.py in the build container), and
+ (2) against the reference modules themselves when /root/reference is present (it is not on the GPU box).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures, fx_oracle, networks_oracle as O, ref_import, weights as W
+
+torch.set_num_threads(8)
+ENC_SD = None
+TCN_SD = None
+
+
+def sds():
+    global ENC_SD, TCN_SD
+    if ENC_SD is None:
+        ENC_SD, TCN_SD = W.make_encoder_state_dict(0), W.make_tcn_state_dict(0)
+    return ENC_SD, TCN_SD
+
+
+def test_golden_encoder():
+    esd, _ = sds()
+    x = W.synthetic_audio(2, 32768, seed=11)
+    with torch.no_grad():
+        emb = O.fxencoder_forward(x, esd, W.ENC_KERNELS, W.ENC_STRIDES).numpy()
+    ref = fixtures.load_golden("enc_small.npz")["emb"]
+    assert emb.shape == ref.shape == (2, 2048)
+    assert np.abs(emb - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())
+
+
+def test_golden_tcn_small_and_percond():
+    _, tsd = sds()
+    with torch.no_grad():
+        y = O.tcn_forward(W.synthetic_audio(2, 8191, seed=12), fixtures.make_cond(1, 21), tsd).numpy()
+        y2 = O.tcn_forward(W.synthetic_audio(3, 4099, seed=13), fixtures.make_cond(3, 22), tsd).numpy()
+    assert np.abs(y - fixtures.load_golden("tcn_small.npz")["y"]).max() <= 2e-6
+    assert np.abs(y2 - fixtures.load_golden("tcn_percond.npz")["y"]).max() <= 2e-6
+
+
+def test_golden_tcn_blocks():
+    _, tsd = sds()
+    g = fixtures.load_golden("tcn_blocks.npz")
+    cond = fixtures.make_cond(1, 24)
+    for n in (0, 1, 4, 9, 13):
+        gen = torch.Generator()
+        gen.manual_seed(300 + n)
+        xb = torch.randn(1, 2 if n == 0 else 128, fixtures.BLOCK_LEN, generator=gen) * 0.5
+        with torch.no_grad():
+            y = O.tcn_block(xb, cond, tsd, f"blocks.{n}", 15, 2 ** n)[0, ::fixtures.BLOCK_CH_STRIDE].numpy()
+        assert np.abs(y - g[f"b{n}"]).max() <= 2e-5, n
+
+
+def test_golden_fx_chain():
+    g = fixtures.load_golden("fx_chain.npz")
+    P = g["params"]
+    assert np.array_equal(P, fx_oracle.random_params(3, seed=77))
+    for i in range(3):
+        y = fx_oracle.fx_chain(fixtures.fx_input(i, 16000), P[i])
+        d = y.astype(np.float64) - g[f"y{i}"]
+        assert np.sqrt(np.mean(d ** 2)) <= 1e-6, i
+
+
+def test_receptive_field_and_segmentation_quirks():
+    assert O.compute_receptive_field() == 229363                      # inference/configs.yaml:22 (5.2 s)
+    song = torch.arange(2 * 1000, dtype=torch.float32).reshape(2, 1000)
+    b = O.batchwise_segmentization(song, 250, 3)                      # exact multiple -> one extra all-zero segment (q1)
+    assert [t.shape[0] for t in b] == [3, 2] and float(b[-1][-1].abs().sum()) == 0.0
+    b = O.batchwise_segmentization(song, 300, 8)
+    assert b[0].shape == (4, 2, 300) and float(b[0][3, :, 100:].abs().sum()) == 0.0
+    with pytest.raises(AssertionError):
+        O.batchwise_segmentization(song, 2000, 1)
+
+
+needs_ref = pytest.mark.skipif(not ref_import.reference_available(), reason="/root/reference not present (GPU box)")
+
+
+@needs_ref
+def test_oracle_equals_reference_modules():
+    esd, tsd = sds()
+    enc, tcn = ref_import.build_reference_models(esd, tsd)
+    assert len(enc.state_dict()) == 168 and len(tcn.state_dict()) == 128
+    assert sum(p.numel() for p in enc.parameters()) == 81392682
+    assert sum(p.numel() for p in tcn.parameters()) == 10547970
+    assert tcn.compute_receptive_field() == O.compute_receptive_field()
+    x = W.synthetic_audio(2, 20011, seed=5)
+    with torch.no_grad():
+        assert torch.equal(enc(x), O.fxencoder_forward(x, esd, W.ENC_KERNELS, W.ENC_STRIDES))
+        cond = fixtures.make_cond(2, 6)
+        assert torch.equal(tcn(x, cond), O.tcn_forward(x, cond, tsd))
+        assert torch.equal(tcn(x, [cond] * 14), O.tcn_forward(x, [cond] * 14, tsd))
+
+
+@needs_ref
+def test_fx_oracle_equals_reference_code():
+    from oracle.make_golden import reference_fx_chain
+    ca = ref_import.import_reference_fx()
+    P = fx_oracle.random_params(4, seed=3)
+    for i in range(4):
+        x = fixtures.fx_input(10 + i, 12000)
+        y_ref = reference_fx_chain(ca, P[i])([x.copy()])[0]
+        d = y_ref.astype(np.float64) - fx_oracle.fx_chain(x, P[i])
+        assert np.sqrt(np.mean(d ** 2)) <= 1e-7
