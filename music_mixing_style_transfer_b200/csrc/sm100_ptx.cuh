@@ -132,17 +132,20 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- UMMA descriptors
-// Shared-memory matrix descriptor, K-major operand tile stored as rows of 128 bytes (64 bf16) with the 128-byte
-// swizzle (what TMA SWIZZLE_128B produces): 8-row groups are 1024 B apart (SBO), LBO unused for swizzled K-major.
+// Shared-memory matrix descriptor, K-major operand tile stored as rows of SWZ bytes (SWZ/2 bf16) with the SWZ-byte
+// swizzle (what TMA SWIZZLE_128B / SWIZZLE_64B produces): 8-row groups are 8*SWZ bytes apart (SBO), LBO unused for
+// swizzled K-major layouts.
 //   [0,14)  start address >> 4      [16,30) leading byte offset >> 4     [32,46) stride byte offset >> 4
-//   [46,48) descriptor version = 1  [49,52) base offset = 0              [61,64) layout type (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
+//   [46,48) descriptor version = 1  [49,52) base offset = 0              [61,64) layout type (2 = 128B, 4 = 64B swizzle)
+template <int SWZ>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
+  static_assert(SWZ == 128 || SWZ == 64, "swizzle span");
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8 * SWZ) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(SWZ == 128 ? 2 : 4) << 61;
   return d;
 }
 

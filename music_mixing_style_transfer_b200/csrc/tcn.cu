@@ -37,9 +37,22 @@ constexpr int kTaps = MST_TCN_K;     // 15
 constexpr int kRowBytes = 512;       // one time step: 4 planes x 64 bf16
 constexpr int kSubRows = 128;        // UMMA M
 constexpr int kTileRows = 256;       // two sub-tiles share every weight slot
-constexpr int kSlotBytes = 32768;    // hi tile (128 x 128 B) + lo tile
-constexpr int kNumSlots = 6;
-constexpr int kWRowsPerLayer = kTaps * 2 * 2 * kCh;  // 7680 rows of 64 bf16
+constexpr int kStageBytes = 32768;   // epilogue staging: 64-channel hi tile (128 x 128 B) + lo tile
+constexpr int kRingBytes = 196608;   // operand ring: 6 x 32 KB (64-channel slots) or 12 x 16 KB (32-channel slots)
+constexpr int kMaxSlots = 12;
+constexpr size_t kWBytesPerLayer = (size_t)kTaps * kCh * kCh * 2 * 2;  // hi + lo bf16 = 983,040 B
+
+// Input-channel chunk per pipeline slot: 64 (SWIZZLE_128B rows, 6 slots, 2 tap-chunks in flight) or
+// 32 (SWIZZLE_64B rows, 12 slots, 4 tap-chunks in flight).  MST_TCN_KCHUNK overrides; read once per process so that
+// weight packing and kernel launches agree.
+static int tcn_kchunk() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("MST_TCN_KCHUNK");
+    v = (e && atoi(e) == 64) ? 64 : ((e && atoi(e) == 32) ? 32 : 64);
+  }
+  return v;
+}
 
 struct TcnPacked {
   size_t w0, wumma, bn_bias, res, film_w, film_b, out_w, out_b, total;
@@ -58,7 +71,7 @@ static int tcn_layout(const mst_tcn_config* c, TcnPacked* o) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t r = off; off += align_up(bytes, 1024); return r; };
   o->w0 = take((size_t)kCh * c->n_inputs * kTaps * 4);
-  o->wumma = take((size_t)(c->n_blocks - 1) * kWRowsPerLayer * 64 * 2);
+  o->wumma = take((size_t)(c->n_blocks - 1) * kWBytesPerLayer);
   o->bn_bias = take((size_t)c->n_blocks * kCh * 4);
   o->res = take((size_t)c->n_blocks * kCh * 4);
   o->film_w = take((size_t)c->n_blocks * 2 * kCh * c->cond_dim * 4);
@@ -97,22 +110,24 @@ __global__ void tcn_pack_block0_kernel(const float* __restrict__ w, const float*
   }
 }
 
-// w: [co 128][ci 128][tap 15] fp32  ->  out[tap][kc][split][co][ci 64] bf16, BN scale folded before the split
+// w: [co 128][ci 128][tap 15] fp32  ->  out[tap][kc][split][co][ci KCH] bf16 (KCH = 64 or 32 input channels per
+// pipeline slot), BN scale folded before the split
 __global__ void tcn_pack_umma_kernel(const float* __restrict__ w, const float* __restrict__ bn_w,
-                                     const float* __restrict__ bn_var, __nv_bfloat16* __restrict__ out) {
-  const int n = kTaps * 2 * kCh * 64;
+                                     const float* __restrict__ bn_var, __nv_bfloat16* __restrict__ out, int kch) {
+  const int n = kTaps * kCh * kCh;
+  const int nkc = kCh / kch;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int cil = i & 63;
-    const int co = (i >> 6) & (kCh - 1);
-    const int kc = (i >> 13) & 1;
-    const int tap = i >> 14;
+    const int cil = i % kch;
+    const int co = (i / kch) % kCh;
+    const int kc = (i / (kch * kCh)) % nkc;
+    const int tap = i / (kch * kCh * nkc);
     const float s = bn_w[co] / sqrtf(bn_var[co] + 1e-5f);
-    const float v = w[((size_t)co * kCh + kc * 64 + cil) * kTaps + tap] * s;
+    const float v = w[((size_t)co * kCh + kc * kch + cil) * kTaps + tap] * s;
     __nv_bfloat16 hi, lo;
     split_bf16(v, hi, lo);
-    const size_t base = ((size_t)(tap * 2 + kc) * 2) * kCh * 64;
-    out[base + (size_t)co * 64 + cil] = hi;
-    out[base + (size_t)kCh * 64 + (size_t)co * 64 + cil] = lo;
+    const size_t base = ((size_t)(tap * nkc + kc) * 2) * kCh * kch;
+    out[base + (size_t)co * kch + cil] = hi;
+    out[base + (size_t)kCh * kch + (size_t)co * kch + cil] = lo;
   }
 }
 
@@ -281,31 +296,41 @@ struct TcnLayerArgs {
 };
 
 struct __align__(8) TcnBarriers {
-  uint64_t full[kNumSlots], empty[kNumSlots];
+  uint64_t full[kMaxSlots], empty[kMaxSlots];
   uint64_t tmem_full[2], tmem_empty[2];
   uint64_t stage_full;
   uint32_t tmem_base;
 };
 
-constexpr size_t kTcnSmemBytes = 1024 /*align slack*/ + (size_t)kNumSlots * kSlotBytes + kSlotBytes /*staging*/ + 256;
+constexpr size_t kTcnSmemBytes = 1024 /*align slack*/ + (size_t)kRingBytes + kStageBytes + 256;
 
 // rows [ts, ts+128) of a shifted sub-tile intersect the real signal [0, T)?  (otherwise it is all zero padding)
 __device__ __forceinline__ bool tap_live(long long ts, int T) { return ts < (long long)T && ts + kSubRows > 0; }
 
+template <int KCH>
 __global__ void __launch_bounds__(256, 1)
 tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                      const __grid_constant__ CUtensorMap tm_y, const TcnLayerArgs a) {
+                      const __grid_constant__ CUtensorMap tm_xs, const __grid_constant__ CUtensorMap tm_y,
+                      const TcnLayerArgs a) {
+  // tm_x / tm_w: operand boxes {KCH ch, 128 rows}, swizzle = 2*KCH bytes;  tm_xs / tm_y: epilogue boxes {64 ch, 128 rows}
+  constexpr int kKcPerTap = kCh / KCH;                 // 2 or 4 input-channel chunks per tap
+  constexpr int kHalf = kSubRows * KCH * 2;            // bytes of one hi (or lo) operand tile: 16 KB / 8 KB
+  constexpr int kSlotBytes = 2 * kHalf;
+  constexpr int kNumSlots = kRingBytes / kSlotBytes;   // 6 / 12
+  constexpr int kK16 = KCH / 16;                       // MMA K-steps per slot
+  constexpr int kSwz = KCH * 2;                        // swizzle span in bytes (128 / 64)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* ring = smem;                                  // kNumSlots x 32 KB, 1024-aligned
-  uint8_t* staging = smem + (size_t)kNumSlots * kSlotBytes;   // 32 KB epilogue tile (hi 16 KB | lo 16 KB)
-  TcnBarriers* bars = reinterpret_cast<TcnBarriers*>(staging + kSlotBytes);
+  uint8_t* ring = smem;                                  // kNumSlots x kSlotBytes, 1024-aligned
+  uint8_t* staging = smem + kRingBytes;                  // 32 KB epilogue tile (hi 16 KB | lo 16 KB), SWIZZLE_128B
+  TcnBarriers* bars = reinterpret_cast<TcnBarriers*>(staging + kStageBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_x);
     ptx::prefetch_tensormap(&tm_w);
+    ptx::prefetch_tensormap(&tm_xs);
     ptx::prefetch_tensormap(&tm_y);
   }
   if (warp == 1 && lane == 0) {
@@ -344,29 +369,31 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
           const bool live0 = tap_live(ts0, a.T), live1 = sub1 && tap_live(ts1, a.T);
           if (!live0 && !live1) continue;
-          for (int kc = 0; kc < 2; ++kc) {
-            // weights: rows ((j*2+kc)*2 + split)*128 .. : hi tile then lo tile
+          for (int kc = 0; kc < kKcPerTap; ++kc) {
+            // weights: rows ((j*kKcPerTap+kc)*2 + split)*128 .. : hi tile then lo tile
             ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
             ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
             uint8_t* dst = ring + (size_t)slot * kSlotBytes;
-            const int wrow = ((j * 2 + kc) * 2) * kCh;
+            const int wrow = ((j * kKcPerTap + kc) * 2) * kCh;
             ptx::tma_load_2d(&tm_w, &bars->full[slot], dst, 0, wrow);
-            ptx::tma_load_2d(&tm_w, &bars->full[slot], dst + 16384, 0, wrow + kCh);
+            ptx::tma_load_2d(&tm_w, &bars->full[slot], dst + kHalf, 0, wrow + kCh);
             next();
+            // activation columns of this chunk: plane (hi / lo) of channel half kc*KCH/64, offset inside the plane
+            const int c_hi = ((kc * KCH) / 64) * 128 + (kc * KCH) % 64, c_lo = c_hi + 64;
             if (live0) {
               ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
               ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
               dst = ring + (size_t)slot * kSlotBytes;
-              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, (2 * kc) * 64, (int)ts0, b);
-              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + 16384, (2 * kc + 1) * 64, (int)ts0, b);
+              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, c_hi, (int)ts0, b);
+              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + kHalf, c_lo, (int)ts0, b);
               next();
             }
             if (live1) {
               ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
               ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
               dst = ring + (size_t)slot * kSlotBytes;
-              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, (2 * kc) * 64, (int)ts1, b);
-              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + 16384, (2 * kc + 1) * 64, (int)ts1, b);
+              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, c_hi, (int)ts1, b);
+              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + kHalf, c_lo, (int)ts1, b);
               next();
             }
           }
@@ -379,12 +406,12 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kSubRows, kCh);
       uint32_t slot = 0, phase = 0;
       auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
-      // 3-product split: (Xhi, Whi) + (Xlo, Whi) + (Xhi, Wlo), 4 K16 steps per 64-channel chunk
+      // 3-product split: (Xhi, Whi) + (Xlo, Whi) + (Xhi, Wlo), KCH/16 K16 steps per slot
       auto issue_group = [&](uint32_t x_addr, uint32_t w_addr, uint32_t d_tmem, bool first) {
-        const uint64_t xh = ptx::umma_desc_kmajor_sw128(x_addr), xl = ptx::umma_desc_kmajor_sw128(x_addr + 16384);
-        const uint64_t wh = ptx::umma_desc_kmajor_sw128(w_addr), wl = ptx::umma_desc_kmajor_sw128(w_addr + 16384);
+        const uint64_t xh = ptx::umma_desc_kmajor<kSwz>(x_addr), xl = ptx::umma_desc_kmajor<kSwz>(x_addr + kHalf);
+        const uint64_t wh = ptx::umma_desc_kmajor<kSwz>(w_addr), wl = ptx::umma_desc_kmajor<kSwz>(w_addr + kHalf);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kK16; ++k) {
           const uint64_t adv = (uint64_t)(k * 32 >> 4);  // +32 bytes along K inside the 128-byte swizzle row
           ptx::umma_bf16(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u);
           ptx::umma_bf16(d_tmem, xl + adv, wh + adv, idesc, 1u);
@@ -405,7 +432,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
           const bool live0 = tap_live(ts0, a.T), live1 = sub1 && tap_live(ts1, a.T);
           if (!live0 && !live1) continue;
-          for (int kc = 0; kc < 2; ++kc) {
+          for (int kc = 0; kc < kKcPerTap; ++kc) {
             const uint32_t wslot = slot;
             ptx::mbar_wait(&bars->full[wslot], phase);
             const uint32_t w_addr = ptx::smem_u32(ring + (size_t)wslot * kSlotBytes);
@@ -455,9 +482,9 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           if (et == 0) ptx::tma_store_wait_read0();
           ptx::named_bar_sync(1, 128);
           if (et == 0) {
-            ptx::mbar_expect_tx(&bars->stage_full, kSlotBytes);
-            ptx::tma_load_3d(&tm_x, &bars->stage_full, staging, (2 * h) * 64, ts, b);              // x_in hi, ch 64h..
-            ptx::tma_load_3d(&tm_x, &bars->stage_full, staging + 16384, (2 * h + 1) * 64, ts, b);  // x_in lo
+            ptx::mbar_expect_tx(&bars->stage_full, kStageBytes);
+            ptx::tma_load_3d(&tm_xs, &bars->stage_full, staging, (2 * h) * 64, ts, b);              // x_in hi, ch 64h..
+            ptx::tma_load_3d(&tm_xs, &bars->stage_full, staging + 16384, (2 * h + 1) * 64, ts, b);  // x_in lo
           }
           uint32_t acc[64];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * kCh + h * 64);
@@ -537,31 +564,32 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-static int encode_act_map(CUtensorMap* m, const void* base, int B, int T) {
+static int encode_act_map(CUtensorMap* m, const void* base, int B, int T, int box_ch) {
   PFN_encodeTiled enc = tensor_map_encoder();
   if (!enc) return 1;
-  // dims (fastest first): 256 bf16 per time row (4 planes x 64), T rows, B segments; box = one plane x 128 rows
+  // dims (fastest first): 256 bf16 per time row (4 planes x 64), T rows, B segments; box = box_ch channels x 128 rows,
+  // swizzle span = the box's row bytes (64 ch -> SWIZZLE_128B, 32 ch -> SWIZZLE_64B)
   cuuint64_t dims[3] = {256, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[2] = {(cuuint64_t)kRowBytes, (cuuint64_t)T * kRowBytes};
-  cuuint32_t box[3] = {64, (cuuint32_t)kSubRows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_ch, (cuuint32_t)kSubRows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  MST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation B=%d T=%d) failed: CUresult %d", B, T, (int)r);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_ch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation B=%d T=%d box=%d) failed: CUresult %d", B, T, box_ch, (int)r);
   return 0;
 }
 
-static int encode_w_map(CUtensorMap* m, const void* base) {
+static int encode_w_map(CUtensorMap* m, const void* base, int kch) {
   PFN_encodeTiled enc = tensor_map_encoder();
   if (!enc) return 1;
-  cuuint64_t dims[2] = {64, (cuuint64_t)kWRowsPerLayer};
-  cuuint64_t strides[1] = {128};
-  cuuint32_t box[2] = {64, (cuuint32_t)kCh};
+  cuuint64_t dims[2] = {(cuuint64_t)kch, (cuuint64_t)(kWBytesPerLayer / (kch * 2))};
+  cuuint64_t strides[1] = {(cuuint64_t)kch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kch, (cuuint32_t)kCh};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed: CUresult %d", (int)r);
   return 0;
 }
@@ -572,10 +600,12 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
                              bool fuse_out, float* out, cudaStream_t st) {
   const long long d = block_dilation(cfg, n);
   MST_CHECK(7 * d + kTileRows < (1ll << 31) - T, "tcn: dilation %lld too large", d);
-  CUtensorMap tm_x, tm_w, tm_y;
-  if (encode_act_map(&tm_x, act_in, B, T)) return 1;
-  if (encode_act_map(&tm_y, fuse_out ? act_in : act_out, B, T)) return 1;
-  if (encode_w_map(&tm_w, packed + L.wumma + (size_t)(n - 1) * kWRowsPerLayer * 128)) return 1;
+  const int kch = tcn_kchunk();
+  CUtensorMap tm_x, tm_w, tm_xs, tm_y;
+  if (encode_act_map(&tm_x, act_in, B, T, kch)) return 1;
+  if (encode_act_map(&tm_xs, act_in, B, T, 64)) return 1;
+  if (encode_act_map(&tm_y, fuse_out ? act_in : act_out, B, T, 64)) return 1;
+  if (encode_w_map(&tm_w, packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer, kch)) return 1;
   TcnLayerArgs a;
   a.B = B; a.T = T; a.dilation = (int)d;
   a.tiles_per_seg = cdiv(T, kTileRows);
@@ -587,9 +617,14 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   a.out_w = reinterpret_cast<const float*>(packed + L.out_w);
   a.out_b = reinterpret_cast<const float*>(packed + L.out_b);
   a.out = out;
-  MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-  tcn_block_umma_kernel<<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_y, a);
+  if (kch == 64) {
+    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));
+    tcn_block_umma_kernel<64><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, a);
+  } else {
+    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));
+    tcn_block_umma_kernel<32><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, a);
+  }
   return launch_ok("tcn_block_umma_kernel");
 }
 
@@ -638,7 +673,7 @@ int mst_tcn_pack(const mst_tcn_config* cfg, const void* const* raw, void* packed
       tcn_pack_block0_kernel<<<16, 256, 0, st>>>(conv_w, bn_w, bn_v, cfg->n_inputs, (float*)(packed + L.w0));
     } else {
       tcn_pack_umma_kernel<<<256, 256, 0, st>>>(
-          conv_w, bn_w, bn_v, (__nv_bfloat16*)(packed + L.wumma) + (size_t)(n - 1) * kWRowsPerLayer * 64);
+          conv_w, bn_w, bn_v, (__nv_bfloat16*)(packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer), tcn_kchunk());
     }
     tcn_pack_vec_kernel<<<1, 128, 0, st>>>(bn_w, bn_b, bn_m, bn_v, res_w, (float*)(packed + L.bn_bias) + n * kCh,
                                            (float*)(packed + L.res) + n * kCh);
