@@ -46,4 +46,14 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled tensor_map_encoder();  // nullptr (with last_error set) if the driver lacks it
 
+// ---- encoder tensor-core path (enc_umma.cu), used by encoder.cu ----
+bool enc_umma_eligible(int c_in, int c_out, int k, int stride);
+size_t enc_umma_weight_bytes(int c_in, int c_out, int k);
+int enc_umma_pack(const float* w, const float* b, const float* bn_w, const float* bn_b, const float* bn_mean,
+                  const float* bn_var, int c_out, int c_in, int k, void* w_out, float* b_out, cudaStream_t st);
+int enc_umma_conv(const void* x, const void* w_packed, const float* bias, void* y, int B, int c_in, int t_in, int c_out,
+                  int k, int stride, bool residual, int out_l, int out_r, cudaStream_t st);
+int enc_split_from_f32(const float* x, void* y, int B, int C, int T, int halo_l, int halo_r, cudaStream_t st);
+int enc_pool_split(const void* x, float* emb, int B, int C, int T, int halo_l, int t_pad, cudaStream_t st);
+
 }  // namespace mst

@@ -265,23 +265,72 @@ static int conv1d_dispatch(const float* x, const float* w, const float* b, const
   }
 }
 
-// packed layout: per block, conv1 {w[ci][k][co], b[co]} then conv2 {w, b}, 64-float aligned
+// Packed layout (byte offsets, 1024-aligned).  Blocks before `first_umma` run on the fp32 CUDA cores and store
+// conv {w[ci][k][co] fp32, b[co]}; blocks from `first_umma` on run on tcgen05 (enc_umma.cu) and store
+// conv {w[tap][kc][hi|lo][co][64] bf16, b[co]}.
 struct EncOffsets {
   size_t w1[MST_MAX_ENC_BLOCKS], b1[MST_MAX_ENC_BLOCKS], w2[MST_MAX_ENC_BLOCKS], b2[MST_MAX_ENC_BLOCKS], total;
+  int first_umma;  // == n_blocks when no block is eligible
 };
+static bool enc_force_fp32() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MST_ENC_FP32"); v = (e && atoi(e) != 0) ? 1 : 0; }
+  return v == 1;
+}
 static int enc_offsets(const mst_enc_config* cfg, EncOffsets* o) {
   MST_CHECK(cfg && cfg->n_blocks > 0 && cfg->n_blocks <= MST_MAX_ENC_BLOCKS, "enc config: n_blocks out of range");
+  // the tensor-core path starts at the first block from which EVERY later conv is eligible
+  int first = cfg->n_blocks;
+  for (int i = cfg->n_blocks - 1; i >= 0; --i) {
+    const int ci = cfg->channels[i], co = cfg->channels[i + 1], k = cfg->kernels[i], s = cfg->strides[i];
+    if (enc_umma_eligible(ci, ci, k, 1) && enc_umma_eligible(ci, co, k, s)) first = i; else break;
+  }
+  if (enc_force_fp32()) first = cfg->n_blocks;
+  if (const char* e = getenv("MST_ENC_FIRST_UMMA")) { const int v = atoi(e); if (v > first && v <= cfg->n_blocks) first = v; }  // debug
+  o->first_umma = first;
   size_t off = 0;
+  auto take = [&](size_t bytes) { size_t r = off; off += align_up(bytes, 1024); return r; };
   for (int i = 0; i < cfg->n_blocks; ++i) {
     const size_t ci = cfg->channels[i], co = cfg->channels[i + 1], k = cfg->kernels[i];
     MST_CHECK(ci > 0 && co > 0 && k > 0 && cfg->strides[i] > 0, "enc config: bad block %d", i);
-    o->w1[i] = off; off += align_up(ci * ci * k, 64);
-    o->b1[i] = off; off += align_up(ci, 64);
-    o->w2[i] = off; off += align_up(co * ci * k, 64);
-    o->b2[i] = off; off += align_up(co, 64);
+    o->w1[i] = take(ci * ci * k * 4);
+    o->b1[i] = take((ci + 2) * 4);   // + 1/weight-scale + scratch (tensor-core blocks)
+    o->w2[i] = take(co * ci * k * 4);
+    o->b2[i] = take((co + 2) * 4);
   }
   o->total = off;
   return 0;
+}
+
+static void conv_halo(int k, int* l, int* r) { *l = (k - 1) / 2; *r = (k - 1) - *l; }
+
+// activation sizes of the two phases
+static size_t enc_max_act_f32(const mst_enc_config* cfg, const EncOffsets& o, int B, int L) {
+  size_t mx = 64;
+  int t = L;
+  for (int i = 0; i < o.first_umma; ++i) {
+    const size_t a1 = (size_t)B * cfg->channels[i] * t;
+    t = cdiv(t, cfg->strides[i]);
+    const size_t a2 = (size_t)B * cfg->channels[i + 1] * t;
+    mx = a1 > mx ? a1 : mx;
+    mx = a2 > mx ? a2 : mx;
+  }
+  return align_up(mx * sizeof(float), 1024);
+}
+static size_t enc_max_act_split(const mst_enc_config* cfg, const EncOffsets& o, int B, int L) {
+  size_t mx = 0;
+  int t = L;
+  for (int i = 0; i < cfg->n_blocks; ++i) {
+    const int tin = t;
+    t = cdiv(t, cfg->strides[i]);
+    if (i < o.first_umma) continue;
+    // every buffer of block i: input / c1 (T_in rows) and output (T_out rows), each with at most a 32-row halo
+    const size_t a1 = (size_t)B * (tin + 64) * cfg->channels[i] * 4;
+    const size_t a2 = (size_t)B * (t + 64) * cfg->channels[i + 1] * 4;
+    mx = a1 > mx ? a1 : mx;
+    mx = a2 > mx ? a2 : mx;
+  }
+  return align_up(mx, 1024);
 }
 
 }  // namespace mst
@@ -318,67 +367,99 @@ int mst_enc_mean_pool(const float* x, float* y, int B, int C, int T, void* strea
 size_t mst_enc_packed_bytes(const mst_enc_config* cfg) {
   EncOffsets o;
   if (enc_offsets(cfg, &o)) return 0;
-  return o.total * sizeof(float);
+  return o.total;
 }
 
-int mst_enc_pack(const mst_enc_config* cfg, const float* const* raw, float* packed, void* stream) {
+int mst_enc_pack(const mst_enc_config* cfg, const float* const* raw, float* packed_f, void* stream) {
   EncOffsets o;
   if (enc_offsets(cfg, &o)) return 1;
-  MST_CHECK(raw && packed, "enc_pack: null pointer");
+  MST_CHECK(raw && packed_f, "enc_pack: null pointer");
+  MST_CHECK((reinterpret_cast<uintptr_t>(packed_f) & 1023) == 0, "enc_pack: packed buffer must be 1024-byte aligned");
+  uint8_t* packed = reinterpret_cast<uint8_t*>(packed_f);
   for (int i = 0; i < cfg->n_blocks; ++i) {
     const float* const* r = raw + 12 * i;
     const int ci = cfg->channels[i], co = cfg->channels[i + 1], k = cfg->kernels[i];
-    if (mst_conv1d_fold_bn(r[0], r[1], r[2], r[3], r[4], r[5], 1e-5f, ci, ci, k, packed + o.w1[i], packed + o.b1[i], stream))
-      return 1;
-    if (mst_conv1d_fold_bn(r[6], r[7], r[8], r[9], r[10], r[11], 1e-5f, co, ci, k, packed + o.w2[i], packed + o.b2[i], stream))
-      return 1;
+    if (i < o.first_umma) {
+      if (mst_conv1d_fold_bn(r[0], r[1], r[2], r[3], r[4], r[5], 1e-5f, ci, ci, k, (float*)(packed + o.w1[i]),
+                             (float*)(packed + o.b1[i]), stream)) return 1;
+      if (mst_conv1d_fold_bn(r[6], r[7], r[8], r[9], r[10], r[11], 1e-5f, co, ci, k, (float*)(packed + o.w2[i]),
+                             (float*)(packed + o.b2[i]), stream)) return 1;
+    } else {
+      if (enc_umma_pack(r[0], r[1], r[2], r[3], r[4], r[5], ci, ci, k, packed + o.w1[i], (float*)(packed + o.b1[i]),
+                        (cudaStream_t)stream)) return 1;
+      if (enc_umma_pack(r[6], r[7], r[8], r[9], r[10], r[11], co, ci, k, packed + o.w2[i], (float*)(packed + o.b2[i]),
+                        (cudaStream_t)stream)) return 1;
+    }
   }
   return 0;
 }
 
-static size_t enc_max_act(const mst_enc_config* cfg, int B, int L) {
-  size_t mx = 0;
-  int t = L;
-  for (int i = 0; i < cfg->n_blocks; ++i) {
-    const size_t a1 = (size_t)B * cfg->channels[i] * t;  // conv1 output
-    t = cdiv(t, cfg->strides[i]);
-    const size_t a2 = (size_t)B * cfg->channels[i + 1] * t;  // conv2 output
-    mx = a1 > mx ? a1 : mx;
-    mx = a2 > mx ? a2 : mx;
-  }
-  return align_up(mx, 64);
-}
-
 size_t mst_enc_workspace_bytes(const mst_enc_config* cfg, int B, int L) {
-  if (!cfg || B <= 0 || L <= 0) return 0;
-  return 3 * enc_max_act(cfg, B, L) * sizeof(float);
+  EncOffsets o;
+  if (!cfg || B <= 0 || L <= 0 || enc_offsets(cfg, &o)) return 0;
+  return 3 * enc_max_act_f32(cfg, o, B, L) + 3 * enc_max_act_split(cfg, o, B, L) + 1024;
 }
 
-int mst_enc_forward(const mst_enc_config* cfg, const float* packed, const float* x, int B, int L, float* emb,
+int mst_enc_forward(const mst_enc_config* cfg, const float* packed_f, const float* x, int B, int L, float* emb,
                     void* workspace, size_t workspace_bytes, void* stream) {
   EncOffsets o;
   if (enc_offsets(cfg, &o)) return 1;
-  MST_CHECK(packed && x && emb && workspace, "enc_forward: null pointer");
-  MST_CHECK(B > 0 && L > 0, "enc_forward: bad shape B=%d L=%d", B, L);
+  MST_CHECK(packed_f && x && emb && workspace, "enc_forward: null pointer");
+  MST_CHECK(B > 0 && L > 0 && B <= 65535, "enc_forward: bad shape B=%d L=%d", B, L);
   MST_CHECK(workspace_bytes >= mst_enc_workspace_bytes(cfg, B, L), "enc_forward: workspace too small (%zu < %zu)",
             workspace_bytes, mst_enc_workspace_bytes(cfg, B, L));
-  const size_t stride = enc_max_act(cfg, B, L);
-  float* buf[3] = {(float*)workspace, (float*)workspace + stride, (float*)workspace + 2 * stride};
+  const uint8_t* packed = reinterpret_cast<const uint8_t*>(packed_f);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+  const size_t fstride = enc_max_act_f32(cfg, o, B, L), sstride = enc_max_act_split(cfg, o, B, L);
+  float* fbuf[3] = {(float*)ws, (float*)(ws + fstride), (float*)(ws + 2 * fstride)};
+  uint8_t* sbuf[3] = {ws + 3 * fstride, ws + 3 * fstride + sstride, ws + 3 * fstride + 2 * sstride};
+
+  // ---- phase 1: small-channel blocks on the fp32 CUDA cores, [B][C][T] ----
   const float* cur = x;
   int cur_buf = -1, t = L;
-  for (int i = 0; i < cfg->n_blocks; ++i) {
+  for (int i = 0; i < o.first_umma; ++i) {
     const int ci = cfg->channels[i], co = cfg->channels[i + 1], k = cfg->kernels[i], s = cfg->strides[i];
-    float* c1 = buf[(cur_buf + 1) % 3];
-    float* c2 = buf[(cur_buf + 2) % 3];
+    float* c1 = fbuf[(cur_buf + 1) % 3];
+    float* c2 = fbuf[(cur_buf + 2) % 3];
     // c1 = relu(bn(conv1(x))) + x          (Res_ConvBlock, network_utils.py:117)
-    if (mst_enc_conv1d(cur, packed + o.w1[i], packed + o.b1[i], cur, c1, B, ci, t, ci, k, 1, 1, stream)) return 1;
+    if (mst_enc_conv1d(cur, (const float*)(packed + o.w1[i]), (const float*)(packed + o.b1[i]), cur, c1, B, ci, t, ci, k,
+                       1, 1, stream)) return 1;
     // c2 = relu(bn(conv2(c1)))             (:118)
-    if (mst_enc_conv1d(c1, packed + o.w2[i], packed + o.b2[i], nullptr, c2, B, ci, t, co, k, s, 1, stream)) return 1;
+    if (mst_enc_conv1d(c1, (const float*)(packed + o.w2[i]), (const float*)(packed + o.b2[i]), nullptr, c2, B, ci, t, co,
+                       k, s, 1, stream)) return 1;
     t = cdiv(t, s);
     cur = c2;
     cur_buf = (cur_buf + 2) % 3;
   }
-  return mst_enc_mean_pool(cur, emb, B, cfg->channels[cfg->n_blocks], t, stream);
+  if (o.first_umma == cfg->n_blocks) return mst_enc_mean_pool(cur, emb, B, cfg->channels[cfg->n_blocks], t, stream);
+
+  // ---- hand-over: fp32 [B][C][T] -> split rows carrying the first tensor-core block's reflection halo ----
+  int l, r;
+  conv_halo(cfg->kernels[o.first_umma], &l, &r);
+  MST_CHECK(t > r, "enc_forward: length %d too short for reflection padding (%d,%d) at block %d", t, l, r, o.first_umma);
+  if (enc_split_from_f32(cur, sbuf[0], B, cfg->channels[o.first_umma], t, l, r, st)) return 1;
+
+  // ---- phase 2: tcgen05 blocks on split rows ----
+  int sb = 0;
+  for (int i = o.first_umma; i < cfg->n_blocks; ++i) {
+    const int ci = cfg->channels[i], co = cfg->channels[i + 1], k = cfg->kernels[i], s = cfg->strides[i];
+    conv_halo(k, &l, &r);
+    int nl = 0, nr = 0;
+    if (i + 1 < cfg->n_blocks) conv_halo(cfg->kernels[i + 1], &nl, &nr);
+    uint8_t* xin = sbuf[sb];
+    uint8_t* c1 = sbuf[(sb + 1) % 3];
+    uint8_t* c2 = sbuf[(sb + 2) % 3];
+    if (enc_umma_conv(xin, packed + o.w1[i], (const float*)(packed + o.b1[i]), c1, B, ci, t, ci, k, 1, true, l, r, st))
+      return 1;
+    if (enc_umma_conv(c1, packed + o.w2[i], (const float*)(packed + o.b2[i]), c2, B, ci, t, co, k, s, false, nl, nr, st))
+      return 1;
+    t = cdiv(t, s);
+    sb = (sb + 2) % 3;
+    if (i + 1 == cfg->n_blocks)
+      return enc_pool_split(c2, emb, B, co, t, 0, t, st);
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -99,7 +99,7 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void umma_mma_f16kind(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -154,6 +154,11 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
 //   [15] A major (0 = K)      [16] B major (0 = K)        [17,23) N >> 3            [24,29) M >> 4
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// same, FP16 x FP16 -> FP32 (A/B format 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace ptx

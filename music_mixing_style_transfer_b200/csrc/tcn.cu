@@ -413,9 +413,9 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #pragma unroll
         for (int k = 0; k < kK16; ++k) {
           const uint64_t adv = (uint64_t)(k * 32 >> 4);  // +32 bytes along K inside the 128-byte swizzle row
-          ptx::umma_bf16(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u);
-          ptx::umma_bf16(d_tmem, xl + adv, wh + adv, idesc, 1u);
-          ptx::umma_bf16(d_tmem, xh + adv, wl + adv, idesc, 1u);
+          ptx::umma_mma_f16kind(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u);
+          ptx::umma_mma_f16kind(d_tmem, xl + adv, wh + adv, idesc, 1u);
+          ptx::umma_mma_f16kind(d_tmem, xh + adv, wl + adv, idesc, 1u);
         }
       };
       int it = 0;

@@ -82,8 +82,11 @@ class FXencoder(nn.Module):
             nbytes = lib.mst_enc_packed_bytes(ctypes.byref(self._cfg))
             if nbytes == 0:
                 raise RuntimeError("libmst_b200 enc_packed_bytes: " + _cabi.last_error())
-            packed = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+            packed = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            off = (-packed.data_ptr()) % 1024
+            packed = packed[off:off + nbytes]
             _cabi.check(lib.mst_enc_pack(ctypes.byref(self._cfg), arr, _cabi.ptr(packed), _cabi.current_stream()), "enc_pack")
+            torch.cuda.current_stream().synchronize()  # `keep` temporaries may be freed after this returns
             self._packed, self._packed_sig = packed, sig
         return self._packed
 
