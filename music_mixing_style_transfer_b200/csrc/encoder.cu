@@ -118,6 +118,123 @@ enc_conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
   }
 }
 
+// Narrow-channel variant for the first encoder blocks (C_out <= 64, long time axis).  A thread owns COT output channels
+// x TT CONSECUTIVE time steps and keeps the input window of the current input channel in registers (one LDS.128 stream
+// per stride phase), so every staged input value is reused by all K taps and all COT channels from registers: the inner
+// loop is FMA-bound instead of LDS-bound.  CTA = GROUPS channel groups x (256 / GROUPS) time threads.
+template <int K, int S, int COT, int TT, int GROUPS, int CI_TILE>
+struct EncNarrow {
+  static constexpr int TPG = 256 / GROUPS;             // threads along time
+  static constexpr int T_TILE = TPG * TT;
+  static constexpr int CO_TILE = GROUPS * COT;
+  static constexpr int PH = TT + (K - 1) / S + 1;      // per-phase window length held in registers
+  static constexpr int XW = ((T_TILE + (K - 1) / S + 1 + 3) / 4) * 4 + 4;   // per-phase smem row (16-byte multiple)
+  static constexpr int WIN = (T_TILE - 1) * S + K;
+  static constexpr int SMEM_FLOATS = CI_TILE * K * CO_TILE + CI_TILE * S * XW;
+};
+
+template <int K, int S, int COT, int TT, int GROUPS, int CI_TILE>
+__global__ void __launch_bounds__(256)
+enc_conv1d_narrow_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                         const float* __restrict__ residual, float* __restrict__ y, int c_in, int t_in, int c_out,
+                         int t_out, int pad_left, int relu) {
+  using Tile = EncNarrow<K, S, COT, TT, GROUPS, CI_TILE>;
+  static_assert(TT % 4 == 0 && COT % 2 == 0, "vector widths");
+  __shared__ __align__(16) float smem[Tile::SMEM_FLOATS];
+  float* Ws = smem;                                        // [CI_TILE][K][CO_TILE]
+  float* Xs = smem + CI_TILE * K * Tile::CO_TILE;          // [CI_TILE][S][XW]
+  const int tid = threadIdx.x;
+  const int g = tid / Tile::TPG, tl = tid - g * Tile::TPG;
+  const int t_base = blockIdx.x * Tile::T_TILE, b = blockIdx.y;
+  const float* xb = x + (size_t)b * c_in * t_in;
+  const int p0 = t_base * S - pad_left;
+
+  float acc[COT][TT];
+#pragma unroll
+  for (int c = 0; c < COT; ++c)
+#pragma unroll
+    for (int i = 0; i < TT; ++i) acc[c][i] = 0.f;
+
+  for (int ci0 = 0; ci0 < c_in; ci0 += CI_TILE) {
+    for (int idx = tid; idx < CI_TILE * K * Tile::CO_TILE; idx += 256) {
+      const int co = idx % Tile::CO_TILE;
+      const int r = idx / Tile::CO_TILE;
+      const int ci = r / K, j = r - ci * K;
+      float v = 0.f;
+      if (ci0 + ci < c_in && co < c_out) v = __ldg(w + ((size_t)(ci0 + ci) * K + j) * c_out + co);
+      Ws[idx] = v;
+    }
+    for (int idx = tid; idx < CI_TILE * Tile::WIN; idx += 256) {
+      const int ci = idx / Tile::WIN, m = idx - ci * Tile::WIN;
+      float v = 0.f;
+      if (ci0 + ci < c_in) v = __ldg(xb + (size_t)(ci0 + ci) * t_in + reflect_index(p0 + m, t_in));
+      Xs[(ci * S + (m % S)) * Tile::XW + m / S] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < CI_TILE; ++ci) {
+      // register window: for every stride phase the TT + (K-1)/S + 1 values this thread's outputs touch
+      float xw[S][Tile::PH + 3];
+#pragma unroll
+      for (int ph = 0; ph < S; ++ph) {
+        const float* src = Xs + (ci * S + ph) * Tile::XW + tl * TT;
+#pragma unroll
+        for (int q = 0; q < (Tile::PH + 3) / 4; ++q) {
+          const float4 v4 = *reinterpret_cast<const float4*>(src + 4 * q);
+          xw[ph][4 * q] = v4.x; xw[ph][4 * q + 1] = v4.y; xw[ph][4 * q + 2] = v4.z; xw[ph][4 * q + 3] = v4.w;
+        }
+      }
+      const float* wrow = Ws + ci * K * Tile::CO_TILE + g * COT;
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        float wv[COT];
+#pragma unroll
+        for (int c2 = 0; c2 < COT / 2; ++c2) {
+          const float2 q = *reinterpret_cast<const float2*>(wrow + j * Tile::CO_TILE + c2 * 2);
+          wv[2 * c2] = q.x; wv[2 * c2 + 1] = q.y;
+        }
+#pragma unroll
+        for (int c = 0; c < COT; ++c)
+#pragma unroll
+          for (int i = 0; i < TT; ++i) acc[c][i] = fmaf(wv[c], xw[j % S][i + j / S], acc[c][i]);
+      }
+    }
+    __syncthreads();
+  }
+
+  const int t0 = t_base + tl * TT;
+  const bool vec = (t_out % 4) == 0;
+#pragma unroll
+  for (int c = 0; c < COT; ++c) {
+    const int co = g * COT + c;
+    if (co >= c_out) continue;
+    const float bv = __ldg(bias + co);
+    const size_t row = ((size_t)b * c_out + co) * t_out;
+#pragma unroll
+    for (int i4 = 0; i4 < TT / 4; ++i4) {
+      const int t = t0 + 4 * i4;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[e] = acc[c][4 * i4 + e] + bv;
+        if (relu) v[e] = fmaxf(v[e], 0.f);
+      }
+      if (vec && t + 3 < t_out) {
+        if (residual) {
+          const float4 r4 = __ldg(reinterpret_cast<const float4*>(residual + row + t));
+          v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+        }
+        *reinterpret_cast<float4*>(y + row + t) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (t + e < t_out) y[row + t + e] = v[e] + (residual ? __ldg(residual + row + t + e) : 0.f);
+        }
+      }
+    }
+  }
+}
+
 // generic (any k / stride) variant: same tiling, runtime tap loop.  Used only for configs outside configs.yaml.
 template <int COT, int TT, int CI_TILE>
 __global__ void __launch_bounds__(256)
@@ -240,6 +357,25 @@ static int conv1d_dispatch(const float* x, const float* w, const float* b, const
   MST_CHECK(t_in > pad - pad_left, "enc_conv1d: reflection padding (%d,%d) needs T_in > pad, got T_in=%d", pad_left,
             pad - pad_left, t_in);
   const int t_out = (t_in + pad - k) / stride + 1;  // == ceil(t_in / stride)
+  // narrow-channel layers of blocks 0-2 (inference/configs.yaml): {K, S, COT, TT, GROUPS, CI_TILE} by (k, stride, c_out)
+#define MST_NARROW_CASE(KK, SS, CO, COT, TT, GR, CI)                                                                  \
+  if (k == KK && stride == SS && c_out == CO) {                                                                        \
+    using Tile = EncNarrow<KK, SS, COT, TT, GR, CI>;                                                                   \
+    static_assert(Tile::SMEM_FLOATS * 4 <= 48 * 1024, "static shared memory budget");                                  \
+    dim3 grid(cdiv(t_out, Tile::T_TILE), B);                                                                           \
+    enc_conv1d_narrow_kernel<KK, SS, COT, TT, GR, CI><<<grid, 256, 0, st>>>(x, w, b, res, y, c_in, t_in, c_out, t_out,  \
+                                                                          pad_left, relu);                           \
+    return launch_ok("enc_conv1d_narrow_kernel");                                                                     \
+  }
+  if (t_out >= 2048) {
+    MST_NARROW_CASE(25, 1, 2, 2, 8, 1, 2)      // block 0 conv1:  2 ->  2
+    MST_NARROW_CASE(25, 4, 16, 16, 4, 1, 2)    // block 0 conv2:  2 -> 16
+    MST_NARROW_CASE(25, 1, 16, 16, 4, 1, 4)    // block 1 conv1: 16 -> 16
+    MST_NARROW_CASE(25, 4, 32, 16, 4, 2, 4)    // block 1 conv2: 16 -> 32
+    MST_NARROW_CASE(15, 1, 32, 16, 4, 2, 8)    // block 2 conv1: 32 -> 32
+    MST_NARROW_CASE(15, 2, 64, 16, 4, 4, 8)    // block 2 conv2: 32 -> 64
+  }
+#undef MST_NARROW_CASE
 #define MST_CONV_CASE(KK, SS, CI) \
   if (k == KK && stride == SS)    \
     return launch_conv_by_shape<KK, SS, CI>(x, w, b, res, y, B, c_in, t_in, c_out, t_out, pad_left, relu, st);

@@ -37,6 +37,25 @@ def test_res_conv_block_matches_oracle(blk):
     assert e2["rms"] <= 1e-5 * max(1.0, e2["ref_rms"]) and e2["max"] <= 5e-4 * max(1.0, e2["ref_rms"]), (blk, e2)
 
 
+@pytest.mark.parametrize("blk", [0, 1, 2])
+def test_narrow_channel_kernels_long_time_axis(blk):
+    """Blocks 0-2 at a length where BOTH convs take the register-window narrow-channel kernels (t_out >= 2048)."""
+    oracle_threads()
+    enc, _ = models()
+    esd, _ = state_dicts()
+    cin, k, s = W.ENC_CHANNELS[blk], W.ENC_KERNELS[blk], W.ENC_STRIDES[blk]
+    T = 9001 if s == 4 else 4999
+    g = torch.Generator()
+    g.manual_seed(90 + blk)
+    x = torch.randn(2, cin, T, generator=g) * 0.5
+    with torch.no_grad():
+        ref = O.res_conv_block(x, esd, f"encoder.{blk}", k, s)
+        got = enc.encoder[blk](x.cuda()).cpu()
+    e = err_stats(got, ref)
+    assert got.shape == ref.shape
+    assert e["rms"] <= 1e-5 * max(1.0, e["ref_rms"]) and e["max"] <= 5e-4 * max(1.0, e["ref_rms"]), (blk, e)
+
+
 @pytest.mark.parametrize("B,L", [(2, 32768), (1, 44100), (3, 20011)])
 def test_full_encoder_matches_oracle(B, L):
     oracle_threads()
