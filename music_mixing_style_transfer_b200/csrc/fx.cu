@@ -35,7 +35,7 @@ constexpr int kFxTile = kFxHalf * kFxChunk;  // 4096 frames
 constexpr int kFxStats = 16;          // doubles per segment
 
 // stats slots
-enum { S_X2_0 = 0, S_X2_1, S_Y1_0, S_Y1_1, S_U2_0, S_U2_1, S_Y2_0, S_Y2_1, S_LR };
+enum { S_X2_0 = 0, S_X2_1, S_Y1_0, S_Y1_1, S_U2_0, S_U2_1, S_Y2_0, S_Y2_1, S_LR, S_ROUNDS };  // S_ROUNDS: smoother iterations (diagnostic)
 
 struct Biquad { double b0, b1, b2, a1, a2; };
 
@@ -92,13 +92,19 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // =====================================================================================================================
 // pass A: EQ
+// Precision split: the recurrences have long memory (pole radius up to 0.997), so everything that is CARRIED -- the
+// per-chunk end states, the block scan of transition matrices, the tile carry -- is float64; everything LOCAL to a
+// 16-sample chunk (zero-state response, natural-response correction) is float32, where rounding cannot accumulate for
+// more than 16 steps (the double-integrator noise growth of a low-frequency section over 16 float32 steps is
+// ~16^2/2 * 2^-23 ~ 1.5e-5 relative).  Measured against the float64 scipy cascade + reference compressor/imager:
+// 2e-6 ... 1.1e-5 RMS absolute on signals of RMS 0.1-0.2 (budget 1e-4), tests/test_gpu_fx.py.
 // =====================================================================================================================
 struct EqShared {
-  Biquad bq[5];
   double mpow[5][33][4];     // (16-sample chunk transition)^l, l = 0..32, row-major 2x2
-  double h[5][kFxChunk][2];  // output natural response to unit initial state (s1, s2)
-  double carry[2][5][2];     // per channel, per biquad: state entering the current tile
-  double wtot[2][8][2];      // per channel: warp totals of the current scan
+  float2 h[5][kFxChunk];     // output natural response to unit initial state (s1, s2)
+  float coef[5][8];          // b0 b1 b2 a1 a2 as float
+  double carry[2][2][5][2];  // [tile parity][channel][biquad]: state entering the tile
+  double wtot[2][2][5][8][2];  // [tile parity][channel][biquad][warp]: warp totals of the scan
   double red[16][4];
 };
 
@@ -115,14 +121,15 @@ fx_eq_kernel(const float* __restrict__ x, const float* __restrict__ params, floa
     const int gi[5] = {0, 2, 5, 8, 11}, fi[5] = {1, 3, 6, 9, 12}, qi[5] = {-1, 4, 7, 10, -1}, ty[5] = {0, 1, 1, 1, 2};
     const double Q = qi[tid] < 0 ? 0.707 : (double)p[qi[tid]];
     const Biquad q = rbj((double)p[gi[tid]], Q, (double)p[fi[tid]], (double)sample_rate, ty[tid]);
-    sh.bq[tid] = q;
-    // natural response + chunk transition from the two unit states
+    sh.coef[tid][0] = (float)q.b0; sh.coef[tid][1] = (float)q.b1; sh.coef[tid][2] = (float)q.b2;
+    sh.coef[tid][3] = (float)q.a1; sh.coef[tid][4] = (float)q.a2;
+    // natural response + chunk transition from the two unit states (float64)
     double M[4];
     for (int u = 0; u < 2; ++u) {
       double s1 = u == 0 ? 1.0 : 0.0, s2 = u == 0 ? 0.0 : 1.0;
       for (int i = 0; i < kFxChunk; ++i) {
         const double yy = s1;
-        sh.h[tid][i][u] = yy;
+        if (u == 0) sh.h[tid][i].x = (float)yy; else sh.h[tid][i].y = (float)yy;
         s1 = s2 - q.a1 * yy;
         s2 = -q.a2 * yy;
       }
@@ -136,7 +143,7 @@ fx_eq_kernel(const float* __restrict__ x, const float* __restrict__ params, floa
       const double n2 = M[2] * P[0] + M[3] * P[2], n3 = M[2] * P[1] + M[3] * P[3];
       P[0] = n0; P[1] = n1; P[2] = n2; P[3] = n3;
     }
-    for (int c = 0; c < 2; ++c) { sh.carry[c][tid][0] = 0.0; sh.carry[c][tid][1] = 0.0; }  // state reset (:512)
+    for (int c = 0; c < 2; ++c) { sh.carry[0][c][tid][0] = 0.0; sh.carry[0][c][tid][1] = 0.0; }  // state reset (:512)
   }
   __syncthreads();
 
@@ -144,33 +151,32 @@ fx_eq_kernel(const float* __restrict__ x, const float* __restrict__ params, floa
   float* yrow = y + ((size_t)b * 2 + ch) * L;
   const bool vec = (L % 4) == 0;
   double sum_x2 = 0.0, sum_y2 = 0.0;
+  int par = 0;
 
-  for (int tile0 = 0; tile0 < L; tile0 += kFxTile) {
+  for (int tile0 = 0; tile0 < L; tile0 += kFxTile, par ^= 1) {
     const int s0 = tile0 + ct * kFxChunk;
-    float xv[kFxChunk];
-    load_chunk(xrow, L, s0, vec, xv);
-    double v[kFxChunk];
+    float v[kFxChunk];
+    load_chunk(xrow, L, s0, vec, v);
+    float sx = 0.f;
 #pragma unroll
-    for (int i = 0; i < kFxChunk; ++i) {
-      v[i] = (double)xv[i];
-      sum_x2 += v[i] * v[i];
-    }
+    for (int i = 0; i < kFxChunk; ++i) sx = fmaf(v[i], v[i], sx);
+    sum_x2 += (double)sx;
     if (enable) {
 #pragma unroll 1
       for (int k = 0; k < 5; ++k) {
-        const Biquad q = sh.bq[k];
-        // (1) zero-state response of this chunk (DF-II transposed, as scipy.signal.lfilter)
-        double s1 = 0.0, s2 = 0.0;
+        const float b0 = sh.coef[k][0], b1 = sh.coef[k][1], b2 = sh.coef[k][2], a1 = sh.coef[k][3], a2 = sh.coef[k][4];
+        // (1) zero-state response of this chunk (DF-II transposed like scipy.signal.lfilter; float32, local)
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < kFxChunk; ++i) {
-          const double xi = v[i];
-          const double yi = fma(q.b0, xi, s1);
-          s1 = fma(q.b1, xi, fma(-q.a1, yi, s2));
-          s2 = fma(q.b2, xi, -q.a2 * yi);
+          const float xi = v[i];
+          const float yi = fmaf(b0, xi, s1);
+          s1 = fmaf(b1, xi, fmaf(-a1, yi, s2));
+          s2 = fmaf(b2, xi, -a2 * yi);
           v[i] = yi;
         }
-        // (2) inclusive scan over the warp: I_l = sum_{i<=l} M^(l-i) z_i
-        double i1 = s1, i2 = s2;
+        // (2) inclusive scan over the warp (float64): I_l = sum_{i<=l} M^(l-i) z_i
+        double i1 = (double)s1, i2 = (double)s2;
 #pragma unroll
         for (int st = 0; st < 5; ++st) {
           const int off = 1 << st;
@@ -181,44 +187,45 @@ fx_eq_kernel(const float* __restrict__ x, const float* __restrict__ params, floa
             i2 += Mp[2] * o1 + Mp[3] * o2;
           }
         }
-        if (lane == 31) { sh.wtot[ch][wic][0] = i1; sh.wtot[ch][wic][1] = i2; }
-        // exclusive value of the previous lane
+        if (lane == 31) { sh.wtot[par][ch][k][wic][0] = i1; sh.wtot[par][ch][k][wic][1] = i2; }
         double e1 = __shfl_up_sync(0xffffffffu, i1, 1), e2 = __shfl_up_sync(0xffffffffu, i2, 1);
         if (lane == 0) { e1 = 0.0; e2 = 0.0; }
         __syncthreads();
         // state entering this warp: Q_0 = carry, Q_{w+1} = M^32 Q_w + W_w
-        double q1 = sh.carry[ch][k][0], q2 = sh.carry[ch][k][1];
+        double q1 = sh.carry[par][ch][k][0], q2 = sh.carry[par][ch][k][1];
         const double* M32 = sh.mpow[k][32];
         for (int w = 0; w < wic; ++w) {
-          const double n1 = M32[0] * q1 + M32[1] * q2 + sh.wtot[ch][w][0];
-          const double n2 = M32[2] * q1 + M32[3] * q2 + sh.wtot[ch][w][1];
+          const double n1 = M32[0] * q1 + M32[1] * q2 + sh.wtot[par][ch][k][w][0];
+          const double n2 = M32[2] * q1 + M32[3] * q2 + sh.wtot[par][ch][k][w][1];
           q1 = n1; q2 = n2;
         }
         const double* Ml = sh.mpow[k][lane];
         const double in1 = Ml[0] * q1 + Ml[1] * q2 + e1, in2 = Ml[2] * q1 + Ml[3] * q2 + e2;
-        // (3) add the natural response to the true incoming state
+        // (3) add the natural response to the true incoming state (float32, local)
+        const float f1 = (float)in1, f2 = (float)in2;
 #pragma unroll
-        for (int i = 0; i < kFxChunk; ++i) v[i] = fma(sh.h[k][i][0], in1, fma(sh.h[k][i][1], in2, v[i]));
-        __syncthreads();  // every thread has read carry / wtot
-        if (ct == 255) {   // state leaving the tile = M * in + z of the last chunk
+        for (int i = 0; i < kFxChunk; ++i) {
+          const float2 hh = sh.h[k][i];
+          v[i] = fmaf(hh.x, f1, fmaf(hh.y, f2, v[i]));
+        }
+        if (ct == 255) {   // state leaving the tile = M * in + z of the last chunk; read by the NEXT tile (other parity)
           const double* M1 = sh.mpow[k][1];
-          sh.carry[ch][k][0] = M1[0] * in1 + M1[1] * in2 + s1;
-          sh.carry[ch][k][1] = M1[2] * in1 + M1[3] * in2 + s2;
+          sh.carry[par ^ 1][ch][k][0] = M1[0] * in1 + M1[1] * in2 + (double)s1;
+          sh.carry[par ^ 1][ch][k][1] = M1[2] * in1 + M1[3] * in2 + (double)s2;
         }
       }
     }
-    float yv[kFxChunk];
+    float sy = 0.f;
 #pragma unroll
-    for (int i = 0; i < kFxChunk; ++i) {
-      yv[i] = (float)v[i];  // float64 -> float32 cast of the reference (:519)
-      if (s0 + i < L) sum_y2 += (double)yv[i] * (double)yv[i];
-    }
-    store_chunk(yrow, L, s0, vec, yv);
-    __syncthreads();  // carry of this tile visible before the next tile's scan
+    for (int i = 0; i < kFxChunk; ++i)
+      if (s0 + i < L) sy = fmaf(v[i], v[i], sy);
+    sum_y2 += (double)sy;
+    store_chunk(yrow, L, s0, vec, v);
   }
 
   sum_x2 = warp_sum(sum_x2);
   sum_y2 = warp_sum(sum_y2);
+  __syncthreads();
   if (lane == 0) { sh.red[tid >> 5][0] = sum_x2; sh.red[tid >> 5][1] = sum_y2; }
   __syncthreads();
   if (tid < 2) {
@@ -231,13 +238,17 @@ fx_eq_kernel(const float* __restrict__ x, const float* __restrict__ params, floa
 
 // =====================================================================================================================
 // pass B: compressor (in place on y)
+// Same precision split: the smoother state that is carried from chunk to chunk and tile to tile is float64 (chunk maps
+// y_out = A*y_in + B with A = alpha_att^na * alpha_rel^nr taken from float64 power tables); the 16 local steps, the
+// gain computer and the gain itself are float32 (the reference evaluates log10 in float32 as well).
 // =====================================================================================================================
 struct CompShared {
-  double wa[2][8], wb[2][8];   // per channel warp-total affine maps
-  double carry[2];             // smoother state entering the current tile
-  float xch[kFxTile];          // channel-1 output of the current tile (for sum L*R)
+  double wa[2][2][8], wb[2][2][8];   // [round parity][channel][warp]: warp-total affine maps
+  double carry[2][2];                // [tile parity][channel]: smoother state entering the tile
+  double pa[kFxChunk + 1], pr[kFxChunk + 1];   // alpha_att^k, alpha_rel^k
+  alignas(16) float xch[kFxTile];    // channel-1 output of the current tile (for sum L*R)
   double red[16][4];
-  int changed;
+  unsigned long long rounds;
 };
 
 __global__ void __launch_bounds__(kFxThreads)
@@ -256,90 +267,100 @@ fx_comp_kernel(const float* __restrict__ params, float* __restrict__ y, double* 
     const double mx = (st[S_X2_0] + st[S_X2_1]) / n, my = (st[S_Y1_0] + st[S_Y1_1]) / n;
     scale1 = (float)sqrt(mx / fmax(1e-7, my));
   }
-  const double thr = (double)p[13], att_ms = (double)p[14], rel_ms = (double)p[15], ratio = (double)p[16];
-  const double a_att = exp(-1.0 / (0.001 * (double)sample_rate * att_ms));   // :555
-  const double a_rel = exp(-1.0 / (0.001 * (double)sample_rate * rel_ms));   // :556
-  const bool active = enable && !(thr == 0.0 && ratio == 1.0);                // :635
+  const double thr_d = (double)p[13], att_ms = (double)p[14], rel_ms = (double)p[15], ratio_d = (double)p[16];
+  const double a_att_d = exp(-1.0 / (0.001 * (double)sample_rate * att_ms));   // :555
+  const double a_rel_d = exp(-1.0 / (0.001 * (double)sample_rate * rel_ms));   // :556
+  const bool active = enable && !(thr_d == 0.0 && ratio_d == 1.0);              // :635
+  const float thr = (float)thr_d, ratio = (float)ratio_d, inv_ratio = 1.f / ratio;
+  const float a_att = (float)a_att_d, a_rel = (float)a_rel_d;
+  const float c_att = (float)(1.0 - a_att_d), c_rel = (float)(1.0 - a_rel_d);
 
-  if (tid < 2) sh.carry[tid] = 0.0;  // yL_prev = 0 at every call (:553)
+  if (tid < 2) sh.carry[0][tid] = 0.0;  // yL_prev = 0 at every call (:553)
+  if (tid == 0) {
+    double pa = 1.0, pr = 1.0;
+    for (int k = 0; k <= kFxChunk; ++k) { sh.pa[k] = pa; sh.pr[k] = pr; pa *= a_att_d; pr *= a_rel_d; }
+    sh.rounds = 0ull;
+  }
   __syncthreads();
 
   float* yrow = y + ((size_t)b * 2 + ch) * L;
   const bool vec = (L % 4) == 0;
   double sum_u2 = 0.0, sum_y2 = 0.0, sum_lr = 0.0;
+  int tpar = 0, rpar = 0;
+  unsigned rounds_local = 0;
 
-  for (int tile0 = 0; tile0 < L; tile0 += kFxTile) {
+  for (int tile0 = 0; tile0 < L; tile0 += kFxTile, tpar ^= 1) {
     const int s0 = tile0 + ct * kFxChunk;
     float u[kFxChunk];
     load_chunk(yrow, L, s0, vec, u);
+    float su = 0.f;
 #pragma unroll
     for (int i = 0; i < kFxChunk; ++i) {
       u[i] = u[i] * scale1;
-      if (s0 + i < L) sum_u2 += (double)u[i] * (double)u[i];
+      if (s0 + i < L) su = fmaf(u[i], u[i], su);
     }
+    sum_u2 += (double)su;
     float out[kFxChunk];
     if (active) {
-      // gain computer (:559-575): x_g in dB (float32 log10 like numba), static curve, x_l = x_g - y_g
-      double xl[kFxChunk];
+      // gain computer (:559-575): x_g in dB, static curve, x_l = x_g - y_g   (float32)
+      float xl[kFxChunk];
 #pragma unroll
       for (int i = 0; i < kFxChunk; ++i) {
         const float ax = fabsf(u[i]);
-        const double xg = ax < 0.000001f ? -120.0 : 20.0 * (double)log10f(ax);
-        double yg;
-        if (ratio > 1.0) yg = xg >= thr ? thr + (xg - thr) / ratio : xg;
-        else if (ratio < 1.0) yg = xg <= thr ? thr + (xg - thr) / (1.0 / ratio) : xg;
-        else yg = 0.0;
+        const float xg = ax < 0.000001f ? -120.f : 20.f * log10f(ax);
+        float yg;
+        if (ratio > 1.f) yg = xg >= thr ? thr + (xg - thr) * inv_ratio : xg;
+        else if (ratio < 1.f) yg = xg <= thr ? thr + (xg - thr) * ratio : xg;   // (x_g - thr) / (1 / ratio)
+        else yg = 0.f;
         xl[i] = xg - yg;
       }
-      // smoother (:577-583) by pattern fixed-point iteration + affine block scan
-      double yl[kFxChunk];
-      double g_in = sh.carry[ch];
+      // smoother (:577-583): attack/release pattern fixed-point iteration + affine block scan
+      float yl[kFxChunk];
+      const double tile_in = sh.carry[tpar][ch];
+      double g_in = tile_in;
       unsigned prev_mask = 0xFFFFFFFFu;  // impossible 16-bit pattern -> first round always "changed"
-      const double tile_in = g_in;
-      for (int round = 0; round < kFxHalf + 2; ++round) {
-        double yy = g_in, A = 1.0, Bc = 0.0;
+      double end_state = 0.0;
+      for (int round = 0; round < kFxHalf + 2; ++round, rpar ^= 1) {
+        float yy = (float)g_in, Bc = 0.f;
         unsigned mask = 0;
 #pragma unroll
         for (int i = 0; i < kFxChunk; ++i) {
           const bool at = xl[i] > yy;
-          const double al = at ? a_att : a_rel;
-          const double c = (1.0 - al) * xl[i];
-          yy = al * yy + c;
-          A *= al;
-          Bc = al * Bc + c;
+          const float al = at ? a_att : a_rel;
+          const float c = (at ? c_att : c_rel) * xl[i];
+          yy = fmaf(al, yy, c);
+          Bc = fmaf(al, Bc, c);
           mask |= (at ? 1u : 0u) << i;
           yl[i] = yy;
         }
+        const int na = __popc(mask);
+        const double A = sh.pa[na] * sh.pr[kFxChunk - na];
+        end_state = A * g_in + (double)Bc;
         const int my_changed = mask != prev_mask;
         prev_mask = mask;
-        if (tid == 0) sh.changed = 0;
-        __syncthreads();
-        if (my_changed) sh.changed = 1;
         // inclusive affine scan over the warp: (A,B)_l <- map_l o ... o map_0
-        double sa = A, sb = Bc;
+        double sa = A, sb = (double)Bc;
 #pragma unroll
         for (int stp = 0; stp < 5; ++stp) {
           const int off = 1 << stp;
           const double oa = __shfl_up_sync(0xffffffffu, sa, off), ob = __shfl_up_sync(0xffffffffu, sb, off);
           if (lane >= off) { sb = sa * ob + sb; sa = sa * oa; }
         }
-        if (lane == 31) { sh.wa[ch][wic] = sa; sh.wb[ch][wic] = sb; }
+        if (lane == 31) { sh.wa[rpar][ch][wic] = sa; sh.wb[rpar][ch][wic] = sb; }
         double ea = __shfl_up_sync(0xffffffffu, sa, 1), eb = __shfl_up_sync(0xffffffffu, sb, 1);
         if (lane == 0) { ea = 1.0; eb = 0.0; }
-        __syncthreads();
-        double qv = tile_in;  // state entering this warp
-        for (int w = 0; w < wic; ++w) qv = sh.wa[ch][w] * qv + sh.wb[ch][w];
-        g_in = ea * qv + eb;   // state entering this thread's chunk under the current pattern
-        const int any = sh.changed;
-        __syncthreads();
-        if (!any) break;        // pattern reproduced itself -> yl[] is the sequential solution
+        const int any = __syncthreads_or(my_changed);
+        ++rounds_local;
+        if (!any) break;          // pattern reproduced itself -> yl[] is the sequential solution
+        double qv = tile_in;      // state entering this warp
+        for (int w = 0; w < wic; ++w) qv = sh.wa[rpar][ch][w] * qv + sh.wb[rpar][ch][w];
+        g_in = ea * qv + eb;      // state entering this thread's chunk under the current pattern
       }
-      // tile end state: last chunk's end value
-      if (ct == 255) sh.carry[ch] = yl[kFxChunk - 1];
+      if (ct == 255) sh.carry[tpar ^ 1][ch] = end_state;   // read by the next tile (other parity)
 #pragma unroll
       for (int i = 0; i < kFxChunk; ++i) {
-        const double c = pow(10.0, (0.0 - yl[i]) / 20.0);   // makeup 0 (:582, :646)
-        out[i] = (float)((double)u[i] * c);                  // float32 * float64 -> stored float32 (:585, :638)
+        const float c = exp2f(yl[i] * -0.16609640474436813f);   // 10^((0 - y_l)/20), makeup 0 (:582, :646)
+        out[i] = u[i] * c;                                       // (:585, :638)
       }
     } else {
 #pragma unroll
@@ -348,18 +369,22 @@ fx_comp_kernel(const float* __restrict__ params, float* __restrict__ y, double* 
     // sums for the compressor RMS factor and the imager energies
     if (ch == 1) {
 #pragma unroll
-      for (int i = 0; i < kFxChunk; ++i) sh.xch[ct * kFxChunk + i] = out[i];
+      for (int i = 0; i < kFxChunk / 4; ++i)
+        reinterpret_cast<float4*>(sh.xch + ct * kFxChunk)[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
     }
     __syncthreads();
+    float sy = 0.f, slr = 0.f;
 #pragma unroll
     for (int i = 0; i < kFxChunk; ++i) {
       if (s0 + i < L) {
-        sum_y2 += (double)out[i] * (double)out[i];
-        if (ch == 0) sum_lr += (double)out[i] * (double)sh.xch[ct * kFxChunk + i];
+        sy = fmaf(out[i], out[i], sy);
+        if (ch == 0) slr = fmaf(out[i], sh.xch[ct * kFxChunk + i], slr);
       }
     }
+    sum_y2 += (double)sy;
+    sum_lr += (double)slr;
     store_chunk(yrow, L, s0, vec, out);
-    __syncthreads();  // xch / carry reuse
+    __syncthreads();  // xch reuse
   }
 
   sum_u2 = warp_sum(sum_u2);
@@ -372,7 +397,7 @@ fx_comp_kernel(const float* __restrict__ params, float* __restrict__ y, double* 
     for (int w = 0; w < 8; ++w) { a += sh.red[tid * 8 + w][0]; c += sh.red[tid * 8 + w][1]; e += sh.red[tid * 8 + w][2]; }
     st[S_U2_0 + tid] = a;
     st[S_Y2_0 + tid] = c;
-    if (tid == 0) st[S_LR] = e;
+    if (tid == 0) { st[S_LR] = e; st[S_ROUNDS] = (double)rounds_local; }
   }
 }
 

@@ -36,6 +36,11 @@ gbs = bytes_alg / (ms * 1e-3) / 1e9
 print(json.dumps({"workload": f"configs[2]: FX chain B={B} L={L}", "ms": ms, "audio_s_per_s": B * L / 44100 / (ms * 1e-3),
                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                                "algorithmic_bytes": bytes_alg}}))
+from music_mixing_style_transfer_b200.mixing_manipulator import common_audioeffects as _ca
+for ws in _ca._ws_cache.values():
+    st = ws[:B * 16 * 8].view(torch.float64).reshape(B, 16).cpu().numpy()
+    tiles = (L + 4095) // 4096
+    print("compressor smoother rounds per tile: mean %.2f max %.2f" % (st[:, 9].mean() / tiles, st[:, 9].max() / tiles))
 # parity spot check on 2 segments at full length against the CPU oracle
 for i in (0, B - 1):
     ref = fx_oracle.fx_chain(np.ascontiguousarray(x[i].cpu().numpy().T), P[i].cpu().numpy()).T
