@@ -8,8 +8,9 @@
 //   Gain.process                                    :1038-1051
 //
 // Layout: x, y fp32 [B][2][L] (channel-major); params fp32 [B][20]; stats double [B][16].
-// One CTA per segment, 512 threads: threads 0-255 own channel 0, 256-511 channel 1.  The CTA streams its segment in
-// tiles of 4096 frames; inside a tile every thread owns 16 consecutive samples of its channel.
+// EQ: one CTA (256 threads) per (segment, channel).  Compressor: one CTA per segment, 512 threads (threads 0-255 own
+// channel 0, 256-511 channel 1; it needs the cross-channel sum L*R).  A CTA streams its data in tiles of 4096 frames;
+// inside a tile every thread owns 16 consecutive samples of its channel.
 //
 // The two recurrences are made time-parallel without changing their result:
 //  * EQ: each biquad is a 2-state linear system.  Per tile and biquad: (1) every thread runs its 16 samples from zero
@@ -102,18 +103,21 @@ __device__ __forceinline__ double warp_sum(double v) {
 struct EqShared {
   double mpow[5][33][4];     // (16-sample chunk transition)^l, l = 0..32, row-major 2x2
   float2 h[5][kFxChunk];     // output natural response to unit initial state (s1, s2)
+  double2 hd[2][kFxChunk];   // float64 copy for the two low-frequency sections
+  double coefd[2][5];        // float64 b0 b1 b2 a1 a2 of the two low-frequency sections
   float coef[5][8];          // b0 b1 b2 a1 a2 as float
-  double carry[2][2][5][2];  // [tile parity][channel][biquad]: state entering the tile
-  double wtot[2][2][5][8][2];  // [tile parity][channel][biquad][warp]: warp totals of the scan
-  double red[16][4];
+  double carry[2][5][2];     // [tile parity][biquad]: state entering the tile
+  double wtot[2][5][8][2];   // [tile parity][biquad][warp]: warp totals of the scan
+  double red[8][2];
 };
 
-__global__ void __launch_bounds__(kFxThreads)
+// one CTA (256 threads) per (segment, channel): the EQ needs no cross-channel term
+__global__ void __launch_bounds__(kFxHalf)
 fx_eq_kernel(const float* __restrict__ x, const float* __restrict__ params, float* __restrict__ y,
              double* __restrict__ stats, int L, float sample_rate, int enable) {
   __shared__ EqShared sh;
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int ch = tid >> 8, ct = tid & 255, lane = tid & 31, wic = ct >> 5;  // wic = warp index inside the channel
+  const int b = blockIdx.x >> 1, ch = blockIdx.x & 1, tid = threadIdx.x;
+  const int ct = tid, lane = tid & 31, wic = tid >> 5;
   const float* p = params + (size_t)b * MST_FX_NPARAMS;
 
   if (tid < 5) {
@@ -123,6 +127,7 @@ fx_eq_kernel(const float* __restrict__ x, const float* __restrict__ params, floa
     const Biquad q = rbj((double)p[gi[tid]], Q, (double)p[fi[tid]], (double)sample_rate, ty[tid]);
     sh.coef[tid][0] = (float)q.b0; sh.coef[tid][1] = (float)q.b1; sh.coef[tid][2] = (float)q.b2;
     sh.coef[tid][3] = (float)q.a1; sh.coef[tid][4] = (float)q.a2;
+    if (tid < 2) { sh.coefd[tid][0] = q.b0; sh.coefd[tid][1] = q.b1; sh.coefd[tid][2] = q.b2; sh.coefd[tid][3] = q.a1; sh.coefd[tid][4] = q.a2; }
     // natural response + chunk transition from the two unit states (float64)
     double M[4];
     for (int u = 0; u < 2; ++u) {
@@ -130,6 +135,7 @@ fx_eq_kernel(const float* __restrict__ x, const float* __restrict__ params, floa
       for (int i = 0; i < kFxChunk; ++i) {
         const double yy = s1;
         if (u == 0) sh.h[tid][i].x = (float)yy; else sh.h[tid][i].y = (float)yy;
+        if (tid < 2) { if (u == 0) sh.hd[tid][i].x = yy; else sh.hd[tid][i].y = yy; }
         s1 = s2 - q.a1 * yy;
         s2 = -q.a2 * yy;
       }
@@ -143,7 +149,7 @@ fx_eq_kernel(const float* __restrict__ x, const float* __restrict__ params, floa
       const double n2 = M[2] * P[0] + M[3] * P[2], n3 = M[2] * P[1] + M[3] * P[3];
       P[0] = n0; P[1] = n1; P[2] = n2; P[3] = n3;
     }
-    for (int c = 0; c < 2; ++c) { sh.carry[0][c][tid][0] = 0.0; sh.carry[0][c][tid][1] = 0.0; }  // state reset (:512)
+    sh.carry[0][tid][0] = 0.0; sh.carry[0][tid][1] = 0.0;  // state reset (:512)
   }
   __syncthreads();
 
@@ -164,19 +170,40 @@ fx_eq_kernel(const float* __restrict__ x, const float* __restrict__ params, floa
     if (enable) {
 #pragma unroll 1
       for (int k = 0; k < 5; ++k) {
-        const float b0 = sh.coef[k][0], b1 = sh.coef[k][1], b2 = sh.coef[k][2], a1 = sh.coef[k][3], a2 = sh.coef[k][4];
-        // (1) zero-state response of this chunk (DF-II transposed like scipy.signal.lfilter; float32, local)
-        float s1 = 0.f, s2 = 0.f;
+        // Sections 0-1 (low shelf 30-200 Hz, first band 200-1000 Hz) act as double integrators over a 16-sample chunk:
+        // float32 rounding noise grows ~n^2/2 there (up to 5e-5 absolute after the imager).  They run in float64; the
+        // three sections above 1 kHz are well conditioned over 16 steps and run in float32.
+        const bool dbl = k < 2;
+        double yd[kFxChunk];
+        double z1, z2;
+        if (dbl) {
+          const double b0 = sh.coefd[k][0], b1 = sh.coefd[k][1], b2 = sh.coefd[k][2], a1 = sh.coefd[k][3], a2 = sh.coefd[k][4];
+          double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-        for (int i = 0; i < kFxChunk; ++i) {
-          const float xi = v[i];
-          const float yi = fmaf(b0, xi, s1);
-          s1 = fmaf(b1, xi, fmaf(-a1, yi, s2));
-          s2 = fmaf(b2, xi, -a2 * yi);
-          v[i] = yi;
+          for (int i = 0; i < kFxChunk; ++i) {
+            const double xi = (double)v[i];
+            const double yi = fma(b0, xi, s1);
+            s1 = fma(b1, xi, fma(-a1, yi, s2));
+            s2 = fma(b2, xi, -a2 * yi);
+            yd[i] = yi;
+          }
+          z1 = s1; z2 = s2;
+        } else {
+          const float b0 = sh.coef[k][0], b1 = sh.coef[k][1], b2 = sh.coef[k][2], a1 = sh.coef[k][3], a2 = sh.coef[k][4];
+          // (1) zero-state response of this chunk (DF-II transposed like scipy.signal.lfilter; float32, local)
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < kFxChunk; ++i) {
+            const float xi = v[i];
+            const float yi = fmaf(b0, xi, s1);
+            s1 = fmaf(b1, xi, fmaf(-a1, yi, s2));
+            s2 = fmaf(b2, xi, -a2 * yi);
+            v[i] = yi;
+          }
+          z1 = (double)s1; z2 = (double)s2;
         }
         // (2) inclusive scan over the warp (float64): I_l = sum_{i<=l} M^(l-i) z_i
-        double i1 = (double)s1, i2 = (double)s2;
+        double i1 = z1, i2 = z2;
 #pragma unroll
         for (int st = 0; st < 5; ++st) {
           const int off = 1 << st;
@@ -187,31 +214,39 @@ fx_eq_kernel(const float* __restrict__ x, const float* __restrict__ params, floa
             i2 += Mp[2] * o1 + Mp[3] * o2;
           }
         }
-        if (lane == 31) { sh.wtot[par][ch][k][wic][0] = i1; sh.wtot[par][ch][k][wic][1] = i2; }
+        if (lane == 31) { sh.wtot[par][k][wic][0] = i1; sh.wtot[par][k][wic][1] = i2; }
         double e1 = __shfl_up_sync(0xffffffffu, i1, 1), e2 = __shfl_up_sync(0xffffffffu, i2, 1);
         if (lane == 0) { e1 = 0.0; e2 = 0.0; }
         __syncthreads();
         // state entering this warp: Q_0 = carry, Q_{w+1} = M^32 Q_w + W_w
-        double q1 = sh.carry[par][ch][k][0], q2 = sh.carry[par][ch][k][1];
+        double q1 = sh.carry[par][k][0], q2 = sh.carry[par][k][1];
         const double* M32 = sh.mpow[k][32];
         for (int w = 0; w < wic; ++w) {
-          const double n1 = M32[0] * q1 + M32[1] * q2 + sh.wtot[par][ch][k][w][0];
-          const double n2 = M32[2] * q1 + M32[3] * q2 + sh.wtot[par][ch][k][w][1];
+          const double n1 = M32[0] * q1 + M32[1] * q2 + sh.wtot[par][k][w][0];
+          const double n2 = M32[2] * q1 + M32[3] * q2 + sh.wtot[par][k][w][1];
           q1 = n1; q2 = n2;
         }
         const double* Ml = sh.mpow[k][lane];
         const double in1 = Ml[0] * q1 + Ml[1] * q2 + e1, in2 = Ml[2] * q1 + Ml[3] * q2 + e2;
-        // (3) add the natural response to the true incoming state (float32, local)
-        const float f1 = (float)in1, f2 = (float)in2;
+        // (3) add the natural response to the true incoming state
+        if (dbl) {
 #pragma unroll
-        for (int i = 0; i < kFxChunk; ++i) {
-          const float2 hh = sh.h[k][i];
-          v[i] = fmaf(hh.x, f1, fmaf(hh.y, f2, v[i]));
+          for (int i = 0; i < kFxChunk; ++i) {
+            const double2 hh = sh.hd[k][i];
+            v[i] = (float)(yd[i] + fma(hh.x, in1, hh.y * in2));
+          }
+        } else {
+          const float f1 = (float)in1, f2 = (float)in2;
+#pragma unroll
+          for (int i = 0; i < kFxChunk; ++i) {
+            const float2 hh = sh.h[k][i];
+            v[i] = fmaf(hh.x, f1, fmaf(hh.y, f2, v[i]));
+          }
         }
         if (ct == 255) {   // state leaving the tile = M * in + z of the last chunk; read by the NEXT tile (other parity)
           const double* M1 = sh.mpow[k][1];
-          sh.carry[par ^ 1][ch][k][0] = M1[0] * in1 + M1[1] * in2 + (double)s1;
-          sh.carry[par ^ 1][ch][k][1] = M1[2] * in1 + M1[3] * in2 + (double)s2;
+          sh.carry[par ^ 1][k][0] = M1[0] * in1 + M1[1] * in2 + z1;
+          sh.carry[par ^ 1][k][1] = M1[2] * in1 + M1[3] * in2 + z2;
         }
       }
     }
@@ -226,13 +261,13 @@ fx_eq_kernel(const float* __restrict__ x, const float* __restrict__ params, floa
   sum_x2 = warp_sum(sum_x2);
   sum_y2 = warp_sum(sum_y2);
   __syncthreads();
-  if (lane == 0) { sh.red[tid >> 5][0] = sum_x2; sh.red[tid >> 5][1] = sum_y2; }
+  if (lane == 0) { sh.red[wic][0] = sum_x2; sh.red[wic][1] = sum_y2; }
   __syncthreads();
-  if (tid < 2) {
+  if (tid == 0) {
     double a = 0.0, c = 0.0;
-    for (int w = 0; w < 8; ++w) { a += sh.red[tid * 8 + w][0]; c += sh.red[tid * 8 + w][1]; }
-    stats[(size_t)b * kFxStats + S_X2_0 + tid] = a;
-    stats[(size_t)b * kFxStats + S_Y1_0 + tid] = c;
+    for (int w = 0; w < 8; ++w) { a += sh.red[w][0]; c += sh.red[w][1]; }
+    stats[(size_t)b * kFxStats + S_X2_0 + ch] = a;
+    stats[(size_t)b * kFxStats + S_Y1_0 + ch] = c;
   }
 }
 
@@ -478,7 +513,7 @@ int mst_fx_chain_forward(const float* x, const float* params, float* y, int B, i
   cudaStream_t st = (cudaStream_t)stream;
   double* stats = reinterpret_cast<double*>(workspace);
   const int rms = (stages & MST_FX_RMSNORM) ? 1 : 0;
-  fx_eq_kernel<<<B, kFxThreads, 0, st>>>(x, params, y, stats, L, sample_rate, (stages & MST_FX_EQ) ? 1 : 0);
+  fx_eq_kernel<<<2 * B, kFxHalf, 0, st>>>(x, params, y, stats, L, sample_rate, (stages & MST_FX_EQ) ? 1 : 0);
   if (launch_ok("fx_eq_kernel")) return 1;
   fx_comp_kernel<<<B, kFxThreads, 0, st>>>(params, y, stats, L, sample_rate, (stages & MST_FX_COMP) ? 1 : 0,
                                            rms && (stages & MST_FX_EQ) ? 1 : 0);

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256)
 tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const float4* __restrict__ film, int n_cond,
                   uint8_t* __restrict__ act, int T) {
   constexpr int ROWS = 256, HALO = 7;
-  __shared__ float xs[NIN][ROWS + 2 * HALO];
+  __shared__ float xs[NIN][ROWS + 2 * HALO + 4];
   const int b = blockIdx.y, t0 = blockIdx.x * ROWS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < NIN * (ROWS + 2 * HALO); i += 256) {
@@ -208,33 +208,50 @@ tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, con
     P[q] = __ldg(film + (size_t)(n_cond > 1 ? b : 0) * kCh + ch[q]);
   }
   __syncthreads();
-  for (int r = warp * 32; r < warp * 32 + 32; ++r) {
-    const int t = t0 + r;
-    if (t >= T) break;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  // four consecutive rows per iteration share their input window: 18 broadcast reads per input channel feed 480 FMAs
+  constexpr int RB = 4;
+  for (int r = warp * 32; r < warp * 32 + 32; r += RB) {
+    if (t0 + r >= T) break;
+    float acc[RB][4];
 #pragma unroll
-    for (int ci = 0; ci < NIN; ++ci)
+    for (int u = 0; u < RB; ++u)
 #pragma unroll
-      for (int j = 0; j < kTaps; ++j) {
-        const float xv = xs[ci][r + j];
+      for (int q = 0; q < 4; ++q) acc[u][q] = 0.f;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] = fmaf(wr[q][ci * kTaps + j], xv, acc[q]);
+    for (int ci = 0; ci < NIN; ++ci) {
+#pragma unroll
+      for (int m = 0; m < kTaps + RB - 1; ++m) {
+        const float xv = xs[ci][r + m];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int j = m - u;   // tap of row r+u that touches window position m
+          if (j >= 0 && j < kTaps) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[u][q] = fmaf(wr[q][ci * kTaps + j], xv, acc[u][q]);
+          }
+        }
       }
-    __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float v = acc[q] + P[q].x;
-      v = v > 0.f ? v : 0.01f * v;
-      // res = Conv1d(in, 128, k=1, groups=in): out channel c reads input channel c / (128/in)  (architectures.py:216-220)
-      const float xin = xs[ch[q] / (kCh / NIN)][r + HALO];
-      v = fmaf(P[q].y, v, P[q].z) + P[q].w * xin;
-      split_bf16(v, hi[q], lo[q]);
     }
-    uint32_t* row = reinterpret_cast<uint32_t*>(act + ((size_t)b * T + t) * kRowBytes);
-    row[0 * 32 + lane] = pack_bf16(hi[0], hi[1]);
-    row[1 * 32 + lane] = pack_bf16(lo[0], lo[1]);
-    row[2 * 32 + lane] = pack_bf16(hi[2], hi[3]);
-    row[3 * 32 + lane] = pack_bf16(lo[2], lo[3]);
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      const int t = t0 + r + u;
+      if (t >= T) break;
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v = acc[u][q] + P[q].x;
+        v = v > 0.f ? v : 0.01f * v;
+        // res = Conv1d(in, 128, k=1, groups=in): out channel c reads input channel c / (128/in)  (architectures.py:216-220)
+        const float xin = xs[ch[q] / (kCh / NIN)][r + u + HALO];
+        v = fmaf(P[q].y, v, P[q].z) + P[q].w * xin;
+        split_bf16(v, hi[q], lo[q]);
+      }
+      uint32_t* row = reinterpret_cast<uint32_t*>(act + ((size_t)b * T + t) * kRowBytes);
+      row[0 * 32 + lane] = pack_bf16(hi[0], hi[1]);
+      row[1 * 32 + lane] = pack_bf16(lo[0], lo[1]);
+      row[2 * 32 + lane] = pack_bf16(hi[2], hi[3]);
+      row[3 * 32 + lane] = pack_bf16(lo[2], lo[3]);
+    }
   }
 }
 

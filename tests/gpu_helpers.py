@@ -47,4 +47,5 @@ def err_stats(got, ref):
 
 
 def oracle_threads():
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    # torch's CPU convolutions are fastest at ~16 intra-op threads on the 128-core GPU box (bench.py calibrates the same)
+    torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))
