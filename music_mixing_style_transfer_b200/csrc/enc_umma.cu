@@ -4,18 +4,20 @@
 // Res_ConvBlock: conv1(x) + x -> conv2; mst/networks/network_utils.py:28-34,47-51,74,79-89,116-119), different engine:
 // an im2col-free implicit GEMM   D[(b,t), co] = sum_{tap, ci} X[b, s*t + tap - l, ci] * W[tap][co][ci]
 // with the same split-bf16 3-product scheme and warp-specialised TMA / tcgen05 / TMEM pipeline as csrc/tcn.cu.
-// Accuracy note (measured, round 1): the embedding comes out 1.4e-4 relative off the fp32 CPU forward, and the error is
-// the SAME with FP16 operand pairs (22 mantissa bits) as with BF16 pairs (16 bits): it is not operand rounding but the
-// tensor core's FP32 accumulation, which truncates when aligning addends -- a bias of ~2^-24 of the running sum per
-// tcgen05.mma, over 45 ... 480 chained MMAs per output (K up to 10240), amplified ~10x by the 18 following
-// conv -> BN -> ReLU layers.  BF16 pairs are kept (no range hazard).  Effect on the final waveform: < 3e-5 RMS.
+// Accuracy note (measured, round 1): with the whole K loop chained in one TMEM accumulator the embedding came out 1.4e-4
+// relative off the fp32 CPU forward -- and identically so with FP16 operand pairs (22 mantissa bits) instead of BF16 pairs
+// (16 bits): the error is not operand rounding but the tensor core's FP32 accumulation, which truncates when aligning
+// addends (a bias of ~2^-24 of the running sum per tcgen05.mma, over 45 ... 480 chained MMAs per output at K up to
+// 10240, amplified ~10x by the following conv -> BN -> ReLU layers).  The kernel therefore accumulates at most
+// kFlushSteps K-steps (24 MMAs) in TMEM and adds these partial sums in fp32 registers (round-to-nearest) in the epilogue
+// warps, double-buffered against the next group.  BF16 pairs are kept (no range hazard).
 //
 // Activation format ("split rows"): channels-last, one time step = C*4 bytes = C/64 groups of [64 hi bf16 | 64 lo bf16],
 // x = hi + lo.  Every buffer carries the reflection halo of its CONSUMER: rows [0, l) and [l+T, l+T+r) hold the mirrored
 // samples (nn.ReflectionPad1d), written by the producing kernel's epilogue, so the consumer's taps are plain shifted TMA
 // boxes:  padded row = s*t + tap.  Stride-2 convolutions use the tensor map's element stride along time.
-// M tile = 128 rows = NB segments x TT time steps (TT = 128 ... 8), so late layers (T = 64) still fill the MMA; two
-// sub-tiles (256 rows) share every weight slot; N tile = 128 output channels (64 for the one 64-channel layer).
+// M tile = 128 rows = NB segments x TT time steps (TT = 128 ... 8), so late layers (T = 64) still fill the MMA;
+// N tile = 128 output channels (64 for the one 64-channel layer).
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -23,6 +25,7 @@ namespace mst {
 
 constexpr int kEncSlotBytes = 32768;
 constexpr int kEncSlots = 6;
+constexpr int kFlushSteps = 2;   // K64-steps (12 MMAs each) accumulated in TMEM before the fp32 register flush
 constexpr size_t kEncSmemBytes = 1024 + (size_t)kEncSlots * kEncSlotBytes + kEncSlotBytes + 256;
 
 struct ConvUmmaArgs {
@@ -86,7 +89,7 @@ enc_conv_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     ptx::mbar_fence_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(&bars->tmem_base, 512);
+    ptx::tmem_alloc(&bars->tmem_base, 256);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -95,18 +98,19 @@ enc_conv_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   const uint32_t tmem_base = bars->tmem_base;
   const uint32_t w_bytes = 2u * (uint32_t)a.nt * 128u;
 
-  // work item -> (n tile, m tile): consecutive CTAs share a weight tile (the big operand of the late layers)
+  // Work item = (n tile, 128-row sub-tile); consecutive CTAs share a weight tile (the big operand of the late layers).
+  // The K loop (taps x 64-channel chunks) is cut into GROUPS of kFlushSteps steps (= 12*kFlushSteps chained MMAs): each
+  // group accumulates from zero into one of two TMEM buffers and is then added into fp32 REGISTERS by the epilogue
+  // warps while the next group runs.  This bounds the tensor core's truncating accumulation chain (see file header).
+  const int n_steps = a.taps * a.kchunks;
   if (warp == 0) {
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
       auto next = [&]() { if (++slot == kEncSlots) { slot = 0; phase ^= 1; } };
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-        const int ntile = item / a.n_mtiles, mt = item - ntile * a.n_mtiles;
+        const int ntile = item / a.n_sub, su = item - ntile * a.n_sub;
         const int n0 = ntile * a.nt;
-        const int sub0 = 2 * mt, sub1 = 2 * mt + 1;
-        const bool has1 = sub1 < a.n_sub;
-        const int bg0 = sub0 / a.ntt, t00 = (sub0 - bg0 * a.ntt) * a.TT;
-        const int bg1 = sub1 / a.ntt, t01 = (sub1 - bg1 * a.ntt) * a.TT;
+        const int bg = su / a.ntt, t0 = (su - bg * a.ntt) * a.TT;
         for (int j = 0; j < a.taps; ++j) {
           for (int kc = 0; kc < a.kchunks; ++kc) {
             ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
@@ -119,17 +123,9 @@ enc_conv_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
             ptx::mbar_expect_tx(&bars->full[slot], kEncSlotBytes);
             dst = ring + (size_t)slot * kEncSlotBytes;
-            ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, kc * 128, a.stride * t00 + j, bg0 * a.NB);
-            ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + 16384, kc * 128 + 64, a.stride * t00 + j, bg0 * a.NB);
+            ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, kc * 128, a.stride * t0 + j, bg * a.NB);
+            ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + 16384, kc * 128 + 64, a.stride * t0 + j, bg * a.NB);
             next();
-            if (has1) {
-              ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
-              ptx::mbar_expect_tx(&bars->full[slot], kEncSlotBytes);
-              dst = ring + (size_t)slot * kEncSlotBytes;
-              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, kc * 128, a.stride * t01 + j, bg1 * a.NB);
-              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + 16384, kc * 128 + 64, a.stride * t01 + j, bg1 * a.NB);
-              next();
-            }
           }
         }
       }
@@ -150,38 +146,30 @@ enc_conv_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           ptx::umma_mma_f16kind(d_tmem, xh + adv, wl + adv, idesc, 1u);
         }
       };
-      int it = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
-        const int ntile = item / a.n_mtiles, mt = item - ntile * a.n_mtiles;
-        const bool has1 = 2 * mt + 1 < a.n_sub;
-        const int buf = it & 1;
-        ptx::mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 + 0) * 128, acc1 = tmem_base + (uint32_t)(buf * 2 + 1) * 128;
-        bool first = true;
-        for (int j = 0; j < a.taps; ++j) {
-          for (int kc = 0; kc < a.kchunks; ++kc) {
-            const uint32_t wslot = slot;
-            ptx::mbar_wait(&bars->full[wslot], phase);
-            const uint32_t w_addr = ptx::smem_u32(ring + (size_t)wslot * kEncSlotBytes);
-            next();
-            ptx::mbar_wait(&bars->full[slot], phase);
+      uint32_t gtotal = 0;   // accumulation groups issued so far (buffer = gtotal & 1)
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        for (int s = 0; s < n_steps; ++s) {
+          const uint32_t buf = gtotal & 1u;
+          const bool group_start = (s % kFlushSteps) == 0;
+          if (group_start) {
+            ptx::mbar_wait(&bars->tmem_empty[buf], ((gtotal >> 1) & 1u) ^ 1u);
             ptx::tc_fence_after();
-            issue_group(ptx::smem_u32(ring + (size_t)slot * kEncSlotBytes), w_addr, acc0, first);
-            ptx::umma_commit(&bars->empty[slot]);
-            next();
-            if (has1) {
-              ptx::mbar_wait(&bars->full[slot], phase);
-              ptx::tc_fence_after();
-              issue_group(ptx::smem_u32(ring + (size_t)slot * kEncSlotBytes), w_addr, acc1, first);
-              ptx::umma_commit(&bars->empty[slot]);
-              next();
-            }
-            first = false;
-            ptx::umma_commit(&bars->empty[wslot]);
+          }
+          const uint32_t wslot = slot;
+          ptx::mbar_wait(&bars->full[wslot], phase);
+          const uint32_t w_addr = ptx::smem_u32(ring + (size_t)wslot * kEncSlotBytes);
+          next();
+          ptx::mbar_wait(&bars->full[slot], phase);
+          ptx::tc_fence_after();
+          issue_group(ptx::smem_u32(ring + (size_t)slot * kEncSlotBytes), w_addr, tmem_base + buf * 128u, group_start);
+          ptx::umma_commit(&bars->empty[slot]);
+          next();
+          ptx::umma_commit(&bars->empty[wslot]);
+          if ((s % kFlushSteps) == kFlushSteps - 1 || s == n_steps - 1) {
+            ptx::umma_commit(&bars->tmem_full[buf]);
+            ++gtotal;
           }
         }
-        ptx::umma_commit(&bars->tmem_full[buf]);
       }
     }
   } else if (warp >= 4) {
@@ -190,44 +178,58 @@ enc_conv_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     const int rl = q * 32 + lane;              // row of the sub-tile == TMEM lane
     const int nb = rl / a.TT, tt = rl - nb * a.TT;
     uint32_t stage_phase = 0;
-    int it = 0;
+    uint32_t gtotal = 0;
     const int halves = a.nt / 64;
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
-      const int ntile = item / a.n_mtiles, mt = item - ntile * a.n_mtiles;
+    const int n_groups = (n_steps + kFlushSteps - 1) / kFlushSteps;
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      const int ntile = item / a.n_sub, su = item - ntile * a.n_sub;
       const int n0 = ntile * a.nt;
-      const int buf = it & 1;
-      ptx::mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
-      ptx::tc_fence_after();
-      for (int sub = 0; sub < 2; ++sub) {
-        const int su = 2 * mt + sub;
-        if (su >= a.n_sub) break;
-        const int bg = su / a.ntt, t0 = (su - bg * a.ntt) * a.TT;
-        const int b = bg * a.NB + nb, t = t0 + tt;
-        const bool row_ok = b < a.B && t < a.T_out;
-        // mirrored destination rows of this thread's time step, if it falls into the consumer's reflection halo
-        // (a short segment can need BOTH: t = 2 of T = 5 with halo (2,2) is mirrored to the left and to the right)
-        long long mirror_off[2] = {-1, -1};
-        if (row_ok) {
-          const long long seg = (long long)b * a.out_seg_bytes;
-          if (t >= 1 && t <= a.out_halo_l) mirror_off[0] = seg + (long long)(a.out_halo_l - t) * a.out_row_bytes;
-          if (t <= a.T_out - 2 && t >= a.T_out - 1 - a.out_halo_r)
-            mirror_off[1] = seg + (long long)(a.out_halo_l + 2 * (a.T_out - 1) - t) * a.out_row_bytes;
+      const int bg = su / a.ntt, t0 = (su - bg * a.ntt) * a.TT;
+      const int b = bg * a.NB + nb, t = t0 + tt;
+      const bool row_ok = b < a.B && t < a.T_out;
+      // ---- fp32 register accumulation of the K groups ----
+      float sum[128];
+#pragma unroll
+      for (int i = 0; i < 128; ++i) sum[i] = 0.f;
+      for (int g = 0; g < n_groups; ++g, ++gtotal) {
+        const uint32_t buf = gtotal & 1u;
+        ptx::mbar_wait(&bars->tmem_full[buf], (gtotal >> 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u;
+#pragma unroll
+        for (int c32 = 0; c32 < 4; ++c32) {
+          if (c32 * 32 < a.nt) {
+            uint32_t part[32];
+            ptx::tmem_ld_32x32(taddr + c32 * 32, part);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[c32 * 32 + i] += __uint_as_float(part[i]);
+          }
         }
-        for (int h = 0; h < halves; ++h) {
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars->tmem_empty[buf]);
+      }
+      // mirrored destination rows of this thread's time step, if it falls into the consumer's reflection halo
+      // (a short segment can need BOTH: t = 2 of T = 5 with halo (2,2) is mirrored to the left and to the right)
+      long long mirror_off[2] = {-1, -1};
+      if (row_ok) {
+        const long long seg = (long long)b * a.out_seg_bytes;
+        if (t >= 1 && t <= a.out_halo_l) mirror_off[0] = seg + (long long)(a.out_halo_l - t) * a.out_row_bytes;
+        if (t <= a.T_out - 2 && t >= a.T_out - 1 - a.out_halo_r)
+          mirror_off[1] = seg + (long long)(a.out_halo_l + 2 * (a.T_out - 1) - t) * a.out_row_bytes;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h < halves) {
           const int cg = n0 / 64 + h;   // 64-channel group of the output
           if (et == 0) ptx::tma_store_wait_read0();
           ptx::named_bar_sync(1, 128);
-          if (a.res_row_off >= 0 && et == 0) {
-            ptx::mbar_expect_tx(&bars->stage_full, kEncSlotBytes);
-            ptx::tma_load_3d(&tm_r, &bars->stage_full, staging, cg * 128, a.res_row_off + t0, bg * a.NB);
-            ptx::tma_load_3d(&tm_r, &bars->stage_full, staging + 16384, cg * 128 + 64, a.res_row_off + t0, bg * a.NB);
-          }
-          uint32_t acc[64];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * 128 + h * 64);
-          ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
-          ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
-          ptx::tmem_ld_wait();
           if (a.res_row_off >= 0) {
+            if (et == 0) {
+              ptx::mbar_expect_tx(&bars->stage_full, kEncSlotBytes);
+              ptx::tma_load_3d(&tm_r, &bars->stage_full, staging, cg * 128, a.res_row_off + t0, bg * a.NB);
+              ptx::tma_load_3d(&tm_r, &bars->stage_full, staging + 16384, cg * 128 + 64, a.res_row_off + t0, bg * a.NB);
+            }
             ptx::mbar_wait(&bars->stage_full, stage_phase);
             stage_phase ^= 1;
           }
@@ -247,12 +249,12 @@ enc_conv_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             for (int e = 0; e < 4; ++e) {
               float v[2];
 #pragma unroll
-              for (int s = 0; s < 2; ++s) {
-                const int cl = c * 8 + e * 2 + s;
-                float u = __uint_as_float(acc[cl]) + __ldg(a.bias + n0 + h * 64 + cl);
+              for (int s2 = 0; s2 < 2; ++s2) {
+                const int cl = c * 8 + e * 2 + s2;
+                float u = sum[h * 64 + cl] + __ldg(a.bias + n0 + h * 64 + cl);
                 u = fmaxf(u, 0.f);                                       // ReLU (network_utils.py:79-80)
-                const float xin = s == 0 ? enc_lo_f(xhw[e]) + enc_lo_f(xlw[e]) : enc_hi_f(xhw[e]) + enc_hi_f(xlw[e]);
-                v[s] = u + xin;                                          // conv1(x) + x (network_utils.py:117); xin = 0 for conv2
+                const float xin = s2 == 0 ? enc_lo_f(xhw[e]) + enc_lo_f(xlw[e]) : enc_hi_f(xhw[e]) + enc_hi_f(xlw[e]);
+                v[s2] = u + xin;                                         // conv1(x) + x (network_utils.py:117); xin = 0 for conv2
               }
               __nv_bfloat16 h0, l0, h1, l1;
               enc_split(v[0], h0, l0);
@@ -280,8 +282,6 @@ enc_conv_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           }
         }
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&bars->tmem_empty[buf]);
     }
     if (et == 0) ptx::tma_store_wait_all();
   }
@@ -290,7 +290,7 @@ enc_conv_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    ptx::tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -441,10 +441,10 @@ int enc_umma_conv(const void* x, const void* w_packed, const float* bias, void* 
   pick_tile(t_out, &a.TT, &a.NB);
   a.ntt = cdiv(t_out, a.TT);
   a.n_sub = cdiv(B, a.NB) * a.ntt;
-  a.n_mtiles = cdiv(a.n_sub, 2);
+  a.n_mtiles = a.n_sub;
   a.nt = c_out >= 128 ? 128 : 64;
   a.n_ntiles = c_out / a.nt;
-  a.n_items = a.n_mtiles * a.n_ntiles;
+  a.n_items = a.n_sub * a.n_ntiles;
   a.taps = k; a.kchunks = c_in / 64; a.stride = stride; a.c_out = c_out;
   a.res_row_off = residual ? l : -1;
   a.out_halo_l = out_l; a.out_halo_r = out_r;

@@ -28,9 +28,9 @@ def test_stem_style_transfer_matches_oracle():
         outs = [tcn(b.cuda(), emb.unsqueeze(0)).cpu() for b in in_b]
     y = torch.cat([torch.cat(torch.unbind(o, 0), -1) for o in outs], -1)[:, :inp.shape[-1]]
     ee, ey = err_stats(emb.cpu(), emb_ref), err_stats(y, y_ref)
-    assert ee["max"] <= 1.5e-3 and ee["rel"] <= 3e-4, ee
+    assert ee["max"] <= 1e-4 and ee["rel"] <= 2e-5, ee
     print("e2e stem parity", ee, ey)
-    assert ey["rms"] <= RMS_TOL and ey["rms"] <= 5e-5, ey
+    assert ey["rms"] <= RMS_TOL and ey["rms"] <= 2e-5, ey
 
 
 def _write_wav(path, x):
