@@ -304,11 +304,48 @@ def main():
     roofline = {"kernel": "tcn_block_umma_kernel", "bound": "tensor", "achieved": achieved,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
                 "peak_source": f"{pk['source']} bf16 dense (sustained: kernel timed inside a long step)",
-                "traffic": None, "ms_per_launch": umma_ms, "launches_per_step": n_umma, "share_of_step": share,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
+                # this command (profiles/r01_summary.md section 2); = 1.00x the algorithmic activation bytes
+                "traffic": 8.555e9 if (B == BATCH_PER_GPU and L == SEG_LEN) else None,
+                "traffic_algorithmic": 2.0 * B * L * 512, "ms_per_launch": umma_ms, "launches_per_step": n_umma, "share_of_step": share,
                 "algorithmic_flop_per_launch": flops_per_launch,
                 "note": "fp32-grade parity needs the 3-product bf16 split: tensor-pipe work is 3x the algorithmic FLOPs, "
                         "so frac <= 0.333 by construction; tensor_pipe_frac = 3*frac",
                 "tensor_pipe_frac": 3 * achieved / pk["bf16_tflops_sustained"]}
+
+    # ---- extra: BASELINE config 3 (FX chain only, B=256 random-parameter segments) on rank 0 ----
+    fx_extra = None
+    if rank == 0:
+        try:
+            import numpy as np
+            from music_mixing_style_transfer_b200.mixing_manipulator import fx_chain_forward
+            gen = torch.Generator(device=device)
+            gen.manual_seed(1234)
+            fb = 256
+            fx_x = (torch.randn(fb, 2, L, generator=gen, device=device) * 0.1).clamp_(-1, 1)
+            rng = np.random.RandomState(1234)
+            lo = np.array([-15, 30, -15, 200, .1, -15, 1000, .1, -15, 3000, .1, -15, 5000, -80, 1, 50, 4, 0, -6, 0], np.float32)
+            hi = np.array([15, 200, 15, 1000, 2, 15, 3000, 2, 15, 8000, 2, 15, 10000, -5, 20, 500, 40, 2, 9, 1], np.float32)
+            fx_p = torch.from_numpy((lo + rng.rand(fb, 20).astype(np.float32) * (hi - lo))).to(device)
+            fx_p[:, 19] = (fx_p[:, 19] >= 0.5).float()
+            fx_y = torch.empty_like(fx_x)
+            for _ in range(3):
+                fx_chain_forward(fx_x, fx_p, out=fx_y)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(10):
+                fx_chain_forward(fx_x, fx_p, out=fx_y)
+            f1.record()
+            torch.cuda.synchronize()
+            fx_ms = f0.elapsed_time(f1) / 10
+            fx_gbs = 16.0 * fb * L / (fx_ms * 1e-3) / 1e9
+            fx_extra = {"workload": "configs[2]: FX chain (EQ+comp+imager+gain), batch=256 random-param segments of 262144",
+                        "ms": fx_ms, "audio_s_per_s": fb * L / SR / (fx_ms * 1e-3),
+                        "roofline": {"bound": "hbm", "achieved": fx_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                     "frac": fx_gbs / pk["hbm_gbs"], "algorithmic_bytes": 16.0 * fb * L}}
+            del fx_x, fx_y
+        except Exception as exc:  # the headline line must survive a failure of the extra leg
+            fx_extra = {"error": repr(exc)}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -328,7 +365,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate; encoder fp32)",
+                "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operand pairs on tcgen05, fp32 accumulate; encoder blocks 0-2 fp32)",
                 "data": "synthetic",
                 "config": {"workload": "configs[1]: FXencoder+MixFXcloner full forward, batch=32 segments of 262144 "
                                        "stereo samples per GPU", "segment_length": L, "batch_per_gpu": B,
@@ -340,7 +377,7 @@ def main():
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": args.steps * (25 + 15) if rank == 0 else args.steps * 15,
                 "gpu_launches_per_step": {"encoder (24 conv + 1 pool, rank 0)": 25, "tcn (film + block0 + 13 umma)": 15},
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": {"fx_chain_config3": fx_extra},
                 "tflops_algorithmic": (TCN_FLOP_PER_SAMPLE * L * B + ENC_FLOP_PER_SEG * B) / (ms_step * 1e-3) / 1e12}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -186,7 +186,7 @@ tcn_film_kernel(const float* __restrict__ film_w, const float* __restrict__ film
 // Lane l owns channels {2l, 2l+1, 64+2l, 65+2l} so each warp store is one full 128-byte plane row.
 // =====================================================================================================================
 template <int NIN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const float4* __restrict__ film, int n_cond,
                   uint8_t* __restrict__ act, int T) {
   constexpr int ROWS = 256, HALO = 7;
@@ -198,25 +198,28 @@ tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, con
     const int t = t0 - HALO + m;  // dilation 1, zero padding 7 (architectures.py:199-206)
     xs[ci][m] = (t >= 0 && t < T) ? __ldg(x + ((size_t)b * NIN + ci) * T + t) : 0.f;
   }
-  const int ch[4] = {2 * lane, 2 * lane + 1, 64 + 2 * lane, 65 + 2 * lane};
-  float wr[4][NIN * kTaps];
-  float4 P[4];
+  // warp = (row group of 64 rows, channel half): lane owns channels {2l, 2l+1} + 64*half -> every warp store is one
+  // full 128-byte plane row; 60 weights per lane keep the kernel at 2 CTAs / SM
+  const int half = warp & 1, rgrp = warp >> 1;
+  const int ch[2] = {64 * half + 2 * lane, 64 * half + 2 * lane + 1};
+  float wr[2][NIN * kTaps];
+  float4 P[2];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 2; ++q) {
 #pragma unroll
     for (int i = 0; i < NIN * kTaps; ++i) wr[q][i] = __ldg(w0 + ch[q] * NIN * kTaps + i);
     P[q] = __ldg(film + (size_t)(n_cond > 1 ? b : 0) * kCh + ch[q]);
   }
+  // res = Conv1d(in, 128, k=1, groups=in): out channel c reads input channel c / (128/in)  (architectures.py:216-220)
+  const int res_ci = ch[0] / (kCh / NIN);
   __syncthreads();
-  // four consecutive rows per iteration share their input window: 18 broadcast reads per input channel feed 480 FMAs
+  // four consecutive rows per iteration share their input window: 18 broadcast reads per input channel feed 240 FMAs
   constexpr int RB = 4;
-  for (int r = warp * 32; r < warp * 32 + 32; r += RB) {
+  for (int r = rgrp * 64; r < rgrp * 64 + 64; r += RB) {
     if (t0 + r >= T) break;
-    float acc[RB][4];
+    float acc[RB][2];
 #pragma unroll
-    for (int u = 0; u < RB; ++u)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[u][q] = 0.f;
+    for (int u = 0; u < RB; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; }
 #pragma unroll
     for (int ci = 0; ci < NIN; ++ci) {
 #pragma unroll
@@ -226,8 +229,8 @@ tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, con
         for (int u = 0; u < RB; ++u) {
           const int j = m - u;   // tap of row r+u that touches window position m
           if (j >= 0 && j < kTaps) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[u][q] = fmaf(wr[q][ci * kTaps + j], xv, acc[u][q]);
+            acc[u][0] = fmaf(wr[0][ci * kTaps + j], xv, acc[u][0]);
+            acc[u][1] = fmaf(wr[1][ci * kTaps + j], xv, acc[u][1]);
           }
         }
       }
@@ -236,21 +239,18 @@ tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, con
     for (int u = 0; u < RB; ++u) {
       const int t = t0 + r + u;
       if (t >= T) break;
-      __nv_bfloat16 hi[4], lo[4];
+      __nv_bfloat16 hi[2], lo[2];
+      const float xin = xs[res_ci][r + u + HALO];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2; ++q) {
         float v = acc[u][q] + P[q].x;
         v = v > 0.f ? v : 0.01f * v;
-        // res = Conv1d(in, 128, k=1, groups=in): out channel c reads input channel c / (128/in)  (architectures.py:216-220)
-        const float xin = xs[ch[q] / (kCh / NIN)][r + u + HALO];
         v = fmaf(P[q].y, v, P[q].z) + P[q].w * xin;
         split_bf16(v, hi[q], lo[q]);
       }
       uint32_t* row = reinterpret_cast<uint32_t*>(act + ((size_t)b * T + t) * kRowBytes);
-      row[0 * 32 + lane] = pack_bf16(hi[0], hi[1]);
-      row[1 * 32 + lane] = pack_bf16(lo[0], lo[1]);
-      row[2 * 32 + lane] = pack_bf16(hi[2], hi[3]);
-      row[3 * 32 + lane] = pack_bf16(lo[2], lo[3]);
+      row[(2 * half) * 32 + lane] = pack_bf16(hi[0], hi[1]);
+      row[(2 * half + 1) * 32 + lane] = pack_bf16(lo[0], lo[1]);
     }
   }
 }
