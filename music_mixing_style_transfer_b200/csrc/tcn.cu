@@ -55,8 +55,19 @@ static int tcn_kchunk() {
 }
 
 struct TcnPacked {
-  size_t w0, wumma, bn_bias, res, film_w, film_b, out_w, out_b, total;
+  size_t w0, wumma, bn_bias, res, film_w, film_b, out_w, out_b, f8_scale, total;
 };
+
+// Operand-split mode of blocks >= 1: 0 = bf16 x 3 products (default), 1 = fp16 + 2 x e4m3 corrections (tcn_f8.cu).
+// Read once per process so that weight packing and launches agree.
+static int tcn_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MST_TCN_PRECISION");
+    v = (e && strcmp(e, "f16f8") == 0) ? 1 : 0;
+  }
+  return v;
+}
 
 static int tcn_layout(const mst_tcn_config* c, TcnPacked* o) {
   MST_CHECK(c, "tcn config is null");
@@ -78,6 +89,7 @@ static int tcn_layout(const mst_tcn_config* c, TcnPacked* o) {
   o->film_b = take((size_t)c->n_blocks * 2 * kCh * 4);
   o->out_w = take((size_t)c->n_outputs * kCh * 4);
   o->out_b = take((size_t)c->n_outputs * 4);
+  o->f8_scale = take((size_t)c->n_blocks * 2 * 4);   // per block: 1/(S*2^11) and a scratch word (f16f8 mode)
   o->total = off;
   return 0;
 }
@@ -617,6 +629,12 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
                              bool fuse_out, float* out, cudaStream_t st) {
   const long long d = block_dilation(cfg, n);
   MST_CHECK(7 * d + kTileRows < (1ll << 31) - T, "tcn: dilation %lld too large", d);
+  if (tcn_mode() == 1)
+    return tcn_f8_launch_block(d, packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer,
+                               reinterpret_cast<const float*>(packed + L.f8_scale) + 2 * n, act_in, act_out,
+                               film + (size_t)n * n_cond * kCh * 4, n_cond, B, T, fuse_out, cfg->n_outputs,
+                               reinterpret_cast<const float*>(packed + L.out_w),
+                               reinterpret_cast<const float*>(packed + L.out_b), out, st);
   const int kch = tcn_kchunk();
   CUtensorMap tm_x, tm_w, tm_xs, tm_y;
   if (encode_act_map(&tm_x, act_in, B, T, kch)) return 1;
@@ -649,6 +667,7 @@ static int launch_block0(const mst_tcn_config* cfg, const uint8_t* packed, const
                          const float* film, int n_cond, uint8_t* act, int B, int T, cudaStream_t st) {
   dim3 grid(cdiv(T, 256), B);
   const float* w0 = reinterpret_cast<const float*>(packed + L.w0);
+  if (tcn_mode() == 1) return tcn_f8_launch_block0(cfg->n_inputs, x, w0, film, n_cond, act, B, T, st);
   const float4* f = reinterpret_cast<const float4*>(film);
   if (cfg->n_inputs == 2) tcn_block0_kernel<2><<<grid, 256, 0, st>>>(x, w0, f, n_cond, act, T);
   else tcn_block0_kernel<1><<<grid, 256, 0, st>>>(x, w0, f, n_cond, act, T);
@@ -688,6 +707,10 @@ int mst_tcn_pack(const mst_tcn_config* cfg, const void* const* raw, void* packed
     MST_CHECK(conv_w && bn_w && bn_b && bn_m && bn_v && res_w && film_w && film_b, "tcn_pack: null weight in block %d", n);
     if (n == 0) {
       tcn_pack_block0_kernel<<<16, 256, 0, st>>>(conv_w, bn_w, bn_v, cfg->n_inputs, (float*)(packed + L.w0));
+    } else if (tcn_mode() == 1) {
+      float* sc = reinterpret_cast<float*>(packed + L.f8_scale) + 2 * n;
+      if (tcn_f8_pack_layer(conv_w, bn_w, bn_v, packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer, sc,
+                            reinterpret_cast<unsigned int*>(sc + 1), st)) return 1;
     } else {
       tcn_pack_umma_kernel<<<256, 256, 0, st>>>(
           conv_w, bn_w, bn_v, (__nv_bfloat16*)(packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer), tcn_kchunk());
@@ -789,10 +812,15 @@ int mst_tcn_block_forward(const mst_tcn_config* cfg, const void* packed_v, int b
     // film for block 0 sits at the start of the table
     if (launch_block0(cfg, packed, P, x, film, n_cond, act[1], B, L, st)) return 1;
   } else {
-    tcn_act_pack_kernel<<<grid, 256, 0, st>>>(x, act[0], L);
-    if (launch_ok("tcn_act_pack_kernel")) return 1;
+    if (tcn_mode() == 1) {
+      if (tcn_f8_act_pack(x, act[0], B, L, st)) return 1;
+    } else {
+      tcn_act_pack_kernel<<<grid, 256, 0, st>>>(x, act[0], L);
+      if (launch_ok("tcn_act_pack_kernel")) return 1;
+    }
     if (launch_umma_block(cfg, packed, P, block, act[0], act[1], film, n_cond, B, L, false, nullptr, st)) return 1;
   }
+  if (tcn_mode() == 1) return tcn_f8_act_unpack(act[1], y, B, L, st);
   tcn_act_unpack_kernel<<<grid, 256, 0, st>>>(act[1], y, L);
   return launch_ok("tcn_act_unpack_kernel");
 }

@@ -1,0 +1,580 @@
+// tcn_f8.cu -- the "2 tensor units" precision mode of the MixFXcloner TCN (MST_TCN_PRECISION=f16f8).
+//
+// Same computation, interfaces and pipeline as csrc/tcn.cu (TCNBlock.forward, architectures.py:222-234), different
+// operand split.  tcn.cu spends 3 bf16 MMAs per algorithmic MMA (Xhi*Whi + Xlo*Whi + Xhi*Wlo).  Here
+//     X*W*(S*2^11)  =  fp16(X) * fp16(W*S*2^11)                       kind::f16     (1 unit)
+//                    + e4m3((X - fp16 X)*2^11) * e4m3(W*S)            kind::f8f6f4  (1/2 unit: FP8 runs at twice the rate)
+//                    + e4m3(X) * e4m3(W*S*2^11 - fp16(W*S*2^11))      kind::f8f6f4  (1/2 unit)
+// The main weights are pre-multiplied by the exact power of two 2^11 (and a per-layer power of two S that puts
+// max|W*S| into [4,8)), so the two correction products come out at the SAME scale as the main product and all three
+// accumulate into ONE fp32 TMEM accumulator; the epilogue multiplies by 1/(S*2^11).  The corrections are 2^-11 of the
+// main term, so E4M3's 2^-4 relative rounding costs 2^-15 overall -- CPU emulation of the 14-block TCN: 6.2e-6 RMS against
+// fp32 (bf16 x 3: 2.6e-6; single-pass fp16: 1.8e-4; budget 1e-4).
+//
+// Activation row (512 B per time step, same bytes as fp32):
+//   [ fp16 hi, ch 0-63 | fp16 hi, ch 64-127 | e4m3 (x - hi)*2^11, ch 0-127 | e4m3 x, ch 0-127 ]      4 planes x 128 B
+// Weights per tap (64 KB):  [ fp16 W*S*2^11 [co][ci 0-63] | same, ci 64-127 | e4m3 W*S [co][ci 0-127] | e4m3 lo [co][ci 0-127] ]
+// Every plane / weight tile is 128 rows x 128 B -> one TMA box, one SWIZZLE_128B K-major UMMA operand tile.
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace mst {
+namespace f8 {
+
+constexpr int kCh = MST_TCN_CH;
+constexpr int kTaps = MST_TCN_K;
+constexpr int kRowBytes = 512;
+constexpr int kSubRows = 128;
+constexpr int kTileRows = 256;
+constexpr int kSlotBytes = 32768;
+constexpr int kNumSlots = 6;
+constexpr int kStageBytes = 32768;   // epilogue: [fp16 tile 16 KB | e4m3 lo 8 KB | e4m3 hi 8 KB]
+constexpr float kLoScale = 2048.f;   // 2^11
+
+__device__ __forceinline__ float fp8_to_float(uint8_t v) {
+  const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)v, __NV_E4M3);
+  return __half2float(__half(h));
+}
+__device__ __forceinline__ uint8_t float_to_fp8(float v) {
+  return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+}
+// v -> (fp16 hi, e4m3 of the scaled remainder, e4m3 of v)
+__device__ __forceinline__ void encode3(float v, __half& hi, uint8_t& l8, uint8_t& h8) {
+  hi = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  l8 = float_to_fp8((v - __half2float(hi)) * kLoScale);
+  h8 = float_to_fp8(v);
+}
+__device__ __forceinline__ float decode2(__half hi, uint8_t l8) {
+  return __half2float(hi) + fp8_to_float(l8) * (1.f / kLoScale);
+}
+
+// =====================================================================================================================
+// weight packing
+// =====================================================================================================================
+__global__ void wmax_kernel(const float* __restrict__ w, const float* __restrict__ bn_w, const float* __restrict__ bn_var,
+                            unsigned int* __restrict__ max_bits) {
+  float m = 0.f;
+  const int n = kCh * kCh * kTaps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int co = i / (kCh * kTaps);
+    m = fmaxf(m, fabsf(w[i] * (bn_w[co] / sqrtf(bn_var[co] + 1e-5f))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(max_bits, __float_as_uint(m));
+}
+
+__device__ __forceinline__ float layer_scale(unsigned int max_bits) {
+  const float m = __uint_as_float(max_bits);
+  if (!(m > 0.f)) return 1.f;
+  return exp2f(floorf(log2f(8.f / m)));   // max|W*S| in [4, 8)
+}
+
+// out (bytes): [tap][4 tiles][co 128][128 B];  inv_scale[0] = 1 / (S * 2^11)
+__global__ void pack_kernel(const float* __restrict__ w, const float* __restrict__ bn_w, const float* __restrict__ bn_var,
+                            const unsigned int* __restrict__ max_bits, uint8_t* __restrict__ out,
+                            float* __restrict__ inv_scale) {
+  const float S = layer_scale(*max_bits);
+  const int n = kTaps * kCh * kCh;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int ci = i % kCh;
+    const int co = (i / kCh) % kCh;
+    const int tap = i / (kCh * kCh);
+    const float s = bn_w[co] / sqrtf(bn_var[co] + 1e-5f);
+    const float v = w[((size_t)co * kCh + ci) * kTaps + tap] * s * S;
+    const float vm = v * kLoScale;
+    const __half wm = __float2half_rn(vm);
+    uint8_t* tap_base = out + (size_t)tap * 4 * kCh * 128;
+    reinterpret_cast<__half*>(tap_base + (size_t)(ci >> 6) * kCh * 128 + (size_t)co * 128)[ci & 63] = wm;
+    tap_base[(size_t)2 * kCh * 128 + (size_t)co * 128 + ci] = float_to_fp8(v);
+    tap_base[(size_t)3 * kCh * 128 + (size_t)co * 128 + ci] = float_to_fp8(vm - __half2float(wm));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[0] = 1.f / (S * kLoScale);
+}
+
+// =====================================================================================================================
+// block 0 and format converters
+// =====================================================================================================================
+template <int NIN>
+__global__ void __launch_bounds__(256, 2)
+block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const float4* __restrict__ film, int n_cond,
+              uint8_t* __restrict__ act, int T) {
+  constexpr int ROWS = 256, HALO = 7, RB = 4;
+  __shared__ float xs[NIN][ROWS + 2 * HALO + 4];
+  const int b = blockIdx.y, t0 = blockIdx.x * ROWS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < NIN * (ROWS + 2 * HALO); i += 256) {
+    const int ci = i / (ROWS + 2 * HALO), m = i % (ROWS + 2 * HALO);
+    const int t = t0 - HALO + m;
+    xs[ci][m] = (t >= 0 && t < T) ? __ldg(x + ((size_t)b * NIN + ci) * T + t) : 0.f;
+  }
+  const int half = warp & 1, rgrp = warp >> 1;
+  const int ch[2] = {64 * half + 2 * lane, 64 * half + 2 * lane + 1};
+  float wr[2][NIN * kTaps];
+  float4 P[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+#pragma unroll
+    for (int i = 0; i < NIN * kTaps; ++i) wr[q][i] = __ldg(w0 + ch[q] * NIN * kTaps + i);
+    P[q] = __ldg(film + (size_t)(n_cond > 1 ? b : 0) * kCh + ch[q]);
+  }
+  const int res_ci = ch[0] / (kCh / NIN);
+  __syncthreads();
+  for (int r = rgrp * 64; r < rgrp * 64 + 64; r += RB) {
+    if (t0 + r >= T) break;
+    float acc[RB][2];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; }
+#pragma unroll
+    for (int ci = 0; ci < NIN; ++ci) {
+#pragma unroll
+      for (int m = 0; m < kTaps + RB - 1; ++m) {
+        const float xv = xs[ci][r + m];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int j = m - u;
+          if (j >= 0 && j < kTaps) {
+            acc[u][0] = fmaf(wr[0][ci * kTaps + j], xv, acc[u][0]);
+            acc[u][1] = fmaf(wr[1][ci * kTaps + j], xv, acc[u][1]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      const int t = t0 + r + u;
+      if (t >= T) break;
+      const float xin = xs[res_ci][r + u + HALO];
+      __half hi[2];
+      uint8_t l8[2], h8[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float v = acc[u][q] + P[q].x;
+        v = v > 0.f ? v : 0.01f * v;
+        v = fmaf(P[q].y, v, P[q].z) + P[q].w * xin;
+        encode3(v, hi[q], l8[q], h8[q]);
+      }
+      uint8_t* row = act + ((size_t)b * T + t) * kRowBytes;
+      reinterpret_cast<__half2*>(row + half * 128)[lane] = __halves2half2(hi[0], hi[1]);
+      reinterpret_cast<uint16_t*>(row + 256 + half * 64)[lane] = (uint16_t)l8[0] | ((uint16_t)l8[1] << 8);
+      reinterpret_cast<uint16_t*>(row + 384 + half * 64)[lane] = (uint16_t)h8[0] | ((uint16_t)h8[1] << 8);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) act_pack_kernel(const float* __restrict__ x, uint8_t* __restrict__ act, int T) {
+  __shared__ float tile[kCh][33];
+  const int b = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int c = warp; c < kCh; c += 8) {
+    const int t = t0 + lane;
+    tile[c][lane] = t < T ? x[((size_t)b * kCh + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int r = warp; r < 32; r += 8) {
+    const int t = t0 + r;
+    if (t >= T) continue;
+    uint8_t* row = act + ((size_t)b * T + t) * kRowBytes;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      __half hi[2];
+      uint8_t l8[2], h8[2];
+      encode3(tile[64 * half + 2 * lane][r], hi[0], l8[0], h8[0]);
+      encode3(tile[64 * half + 2 * lane + 1][r], hi[1], l8[1], h8[1]);
+      reinterpret_cast<__half2*>(row + half * 128)[lane] = __halves2half2(hi[0], hi[1]);
+      reinterpret_cast<uint16_t*>(row + 256 + half * 64)[lane] = (uint16_t)l8[0] | ((uint16_t)l8[1] << 8);
+      reinterpret_cast<uint16_t*>(row + 384 + half * 64)[lane] = (uint16_t)h8[0] | ((uint16_t)h8[1] << 8);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) act_unpack_kernel(const uint8_t* __restrict__ act, float* __restrict__ y, int T) {
+  __shared__ float tile[kCh][33];
+  const int b = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int r = warp; r < 32; r += 8) {
+    const int t = t0 + r;
+    if (t >= T) continue;
+    const uint8_t* row = act + ((size_t)b * T + t) * kRowBytes;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const __half2 h2 = reinterpret_cast<const __half2*>(row + half * 128)[lane];
+      const uint16_t l2 = reinterpret_cast<const uint16_t*>(row + 256 + half * 64)[lane];
+      tile[64 * half + 2 * lane][r] = decode2(__low2half(h2), (uint8_t)(l2 & 0xFF));
+      tile[64 * half + 2 * lane + 1][r] = decode2(__high2half(h2), (uint8_t)(l2 >> 8));
+    }
+  }
+  __syncthreads();
+  for (int c = warp; c < kCh; c += 8) {
+    const int t = t0 + lane;
+    if (t < T) y[((size_t)b * kCh + c) * T + t] = tile[c][lane];
+  }
+}
+
+// =====================================================================================================================
+// the tcgen05 kernel
+// =====================================================================================================================
+struct LayerArgs {
+  int B, T, dilation, tiles_per_seg, n_tiles, n_cond;
+  const float4* film;
+  const float* inv_scale;    // 1 / (S * 2^11) of this layer's packed weights
+  const uint8_t* act_in;     // residual rows are read straight from global memory (L2-hot centre tap)
+  int fuse_out, n_out;
+  const float* out_w;
+  const float* out_b;
+  float* out;
+};
+
+struct __align__(8) Barriers {
+  uint64_t full[kNumSlots], empty[kNumSlots];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+constexpr size_t kSmemBytes = 1024 + (size_t)kNumSlots * kSlotBytes + kStageBytes + 256;
+
+__device__ __forceinline__ bool tap_live(long long ts, int T) { return ts < (long long)T && ts + kSubRows > 0; }
+
+__device__ __forceinline__ void mma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// tm_x / tm_w: byte tensors, box {128 B, 128 rows}, SWIZZLE_128B.  tm_yh: same box on the output (fp16 planes);
+// tm_yb: box {64 B, 128 rows}, no swizzle, for the two e4m3 planes.
+__global__ void __launch_bounds__(256, 1)
+block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+             const __grid_constant__ CUtensorMap tm_yh, const __grid_constant__ CUtensorMap tm_yb, const LayerArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem;
+  uint8_t* staging = smem + (size_t)kNumSlots * kSlotBytes;
+  Barriers* bars = reinterpret_cast<Barriers*>(staging + kStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_x);
+    ptx::prefetch_tensormap(&tm_w);
+    ptx::prefetch_tensormap(&tm_yh);
+    ptx::prefetch_tensormap(&tm_yb);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kNumSlots; ++i) {
+      ptx::mbar_init(&bars->full[i], 1);
+      ptx::mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars->tmem_full[i], 1);
+      ptx::mbar_init(&bars->tmem_empty[i], 128);
+    }
+    ptx::mbar_fence_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&bars->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const long long d = a.dilation;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
+      auto load_pair = [&](const CUtensorMap* tm, bool is_w, int c0a, int c0b, int r, int b) {
+        ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
+        ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
+        uint8_t* dst = ring + (size_t)slot * kSlotBytes;
+        if (is_w) {
+          ptx::tma_load_2d(tm, &bars->full[slot], dst, 0, c0a);
+          ptx::tma_load_2d(tm, &bars->full[slot], dst + 16384, 0, c0b);
+        } else {
+          ptx::tma_load_3d(tm, &bars->full[slot], dst, c0a, r, b);
+          ptx::tma_load_3d(tm, &bars->full[slot], dst + 16384, c0b, r, b);
+        }
+        next();
+      };
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int b = tile / a.tiles_per_seg;
+        const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
+        const bool sub1 = t0 + kSubRows < a.T;
+        for (int j = 0; j < kTaps; ++j) {
+          const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
+          const bool live0 = tap_live(ts0, a.T), live1 = sub1 && tap_live(ts1, a.T);
+          if (!live0 && !live1) continue;
+          for (int grp = 0; grp < 2; ++grp) {   // 0: fp16 main tiles, 1: e4m3 correction tiles
+            const int wrow = (j * 4 + 2 * grp) * kCh;
+            load_pair(&tm_w, true, wrow, wrow + kCh, 0, 0);
+            if (live0) load_pair(&tm_x, false, 256 * grp, 256 * grp + 128, (int)ts0, b);
+            if (live1) load_pair(&tm_x, false, 256 * grp, 256 * grp + 128, (int)ts1, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(kSubRows, kCh);   // A/B format code 0 = F16 (kind::f16) = E4M3 (kind::f8f6f4)
+      uint32_t slot = 0, phase = 0;
+      auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
+      // one slot pair = two 16 KB operand tiles per side; tile i of X multiplies tile i of W; 4 K-steps of 32 bytes each
+      auto issue_group = [&](uint32_t x_addr, uint32_t w_addr, uint32_t d_tmem, bool first, bool f8) {
+#pragma unroll
+        for (int tl = 0; tl < 2; ++tl) {
+          const uint64_t xd = ptx::umma_desc_kmajor<128>(x_addr + tl * 16384), wd = ptx::umma_desc_kmajor<128>(w_addr + tl * 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            const uint32_t accum = (first && tl == 0 && k == 0) ? 0u : 1u;
+            if (f8) mma_f8(d_tmem, xd + adv, wd + adv, idesc, accum);
+            else ptx::umma_mma_f16kind(d_tmem, xd + adv, wd + adv, idesc, accum);
+          }
+        }
+      };
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const int b = tile / a.tiles_per_seg;
+        const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
+        const bool sub1 = t0 + kSubRows < a.T;
+        const int buf = it & 1;
+        ptx::mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 + 0) * kCh, acc1 = tmem_base + (uint32_t)(buf * 2 + 1) * kCh;
+        bool first0 = true, first1 = true;
+        for (int j = 0; j < kTaps; ++j) {
+          const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
+          const bool live0 = tap_live(ts0, a.T), live1 = sub1 && tap_live(ts1, a.T);
+          if (!live0 && !live1) continue;
+          for (int grp = 0; grp < 2; ++grp) {
+            const uint32_t wslot = slot;
+            ptx::mbar_wait(&bars->full[wslot], phase);
+            const uint32_t w_addr = ptx::smem_u32(ring + (size_t)wslot * kSlotBytes);
+            next();
+            if (live0) {
+              ptx::mbar_wait(&bars->full[slot], phase);
+              ptx::tc_fence_after();
+              issue_group(ptx::smem_u32(ring + (size_t)slot * kSlotBytes), w_addr, acc0, first0, grp == 1);
+              first0 = false;
+              ptx::umma_commit(&bars->empty[slot]);
+              next();
+            }
+            if (live1) {
+              ptx::mbar_wait(&bars->full[slot], phase);
+              ptx::tc_fence_after();
+              issue_group(ptx::smem_u32(ring + (size_t)slot * kSlotBytes), w_addr, acc1, first1, grp == 1);
+              first1 = false;
+              ptx::umma_commit(&bars->empty[slot]);
+              next();
+            }
+            ptx::umma_commit(&bars->empty[wslot]);
+          }
+        }
+        ptx::umma_commit(&bars->tmem_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue (128 threads, thread <-> one time row) ==============================
+    const int q = warp & 3;
+    const int et = threadIdx.x - 128;
+    const int rl = q * 32 + lane;
+    const float inv_scale = __ldg(a.inv_scale);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / a.tiles_per_seg;
+      const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
+      const int buf = it & 1;
+      const float4* film = a.film + (size_t)(a.n_cond > 1 ? b : 0) * kCh;
+      ptx::mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      for (int sub = 0; sub < 2; ++sub) {
+        const int ts = t0 + sub * kSubRows;
+        if (ts >= a.T) break;
+        const int t = ts + rl;
+        const bool row_ok = t < a.T;
+        const uint8_t* xrow = a.act_in + ((size_t)b * a.T + (row_ok ? t : 0)) * kRowBytes;
+        float o0 = 0.f, o1 = 0.f;
+        for (int h = 0; h < 2; ++h) {
+          // residual x_in of this row and channel half: 8 x 16 B of fp16 hi + 8 x 8 B of e4m3 lo, all requested up front
+          // so the L2 round trips overlap each other and the TMEM read
+          uint4 xh[8];
+          uint2 xl[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            xh[c] = make_uint4(0, 0, 0, 0);
+            xl[c] = make_uint2(0, 0);
+            if (row_ok) {
+              xh[c] = __ldg(reinterpret_cast<const uint4*>(xrow + h * 128 + c * 16));
+              xl[c] = __ldg(reinterpret_cast<const uint2*>(xrow + 256 + h * 64 + c * 8));
+            }
+          }
+          uint32_t acc[64];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * kCh + h * 64);
+          ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+          ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+          ptx::tmem_ld_wait();
+          // the staging tile is free once the previous TMA stores have read it
+          if (!a.fuse_out) {
+            if (et == 0) ptx::tma_store_wait_read0();
+            ptx::named_bar_sync(1, 128);
+          }
+          uint8_t* srow = staging + rl * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {     // 8 channels per iteration, processed as 4 pairs
+            const uint32_t xhw[4] = {xh[c].x, xh[c].y, xh[c].z, xh[c].w};
+            const uint32_t xlw[2] = {xl[c].x, xl[c].y};
+            uint32_t oh[4];
+            uint32_t ol[2] = {0, 0}, oh8[2] = {0, 0};
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr) {
+              const int cl = c * 8 + 2 * pr;
+              const int ch = h * 64 + cl;
+              const float4 P0 = __ldg(film + ch), P1 = __ldg(film + ch + 1);
+              // x_in = fp16 hi + e4m3 lo * 2^-11  (two channels at once)
+              const float2 hif = __half22float2(*reinterpret_cast<const __half2*>(&xhw[pr]));
+              const unsigned short l8pair = (unsigned short)((xlw[pr >> 1] >> (16 * (pr & 1))) & 0xFFFFu);
+              const __half2_raw lraw = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)l8pair, __NV_E4M3);
+              const float2 lof = __half22float2(__half2(lraw));
+              const float xin0 = fmaf(lof.x, 1.f / kLoScale, hif.x), xin1 = fmaf(lof.y, 1.f / kLoScale, hif.y);
+              float u0 = fmaf(__uint_as_float(acc[cl]), inv_scale, P0.x);
+              float u1 = fmaf(__uint_as_float(acc[cl + 1]), inv_scale, P1.x);
+              u0 = u0 > 0.f ? u0 : 0.01f * u0;
+              u1 = u1 > 0.f ? u1 : 0.01f * u1;
+              u0 = fmaf(P0.y, u0, P0.z) + P0.w * xin0;
+              u1 = fmaf(P1.y, u1, P1.z) + P1.w * xin1;
+              if (a.fuse_out) {
+                o0 = fmaf(u0, __ldg(a.out_w + ch), o0);
+                o0 = fmaf(u1, __ldg(a.out_w + ch + 1), o0);
+                if (a.n_out > 1) {
+                  o1 = fmaf(u0, __ldg(a.out_w + kCh + ch), o1);
+                  o1 = fmaf(u1, __ldg(a.out_w + kCh + ch + 1), o1);
+                }
+              } else {
+                const __half2 hi2 = __floats2half2_rn(fminf(fmaxf(u0, -65504.f), 65504.f), fminf(fmaxf(u1, -65504.f), 65504.f));
+                const float2 hb = __half22float2(hi2);
+                oh[pr] = *reinterpret_cast<const uint32_t*>(&hi2);
+                const uint32_t l2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((u0 - hb.x) * kLoScale, (u1 - hb.y) * kLoScale),
+                                                                      __NV_SATFINITE, __NV_E4M3);
+                const uint32_t h2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(u0, u1), __NV_SATFINITE, __NV_E4M3);
+                ol[pr >> 1] |= l2 << (16 * (pr & 1));
+                oh8[pr >> 1] |= h2 << (16 * (pr & 1));
+              }
+            }
+            if (!a.fuse_out) {
+              *reinterpret_cast<uint4*>(srow + ((c ^ (rl & 7)) << 4)) = make_uint4(oh[0], oh[1], oh[2], oh[3]);   // SWIZZLE_128B tile
+              *reinterpret_cast<uint2*>(staging + 16384 + rl * 64 + c * 8) = make_uint2(ol[0], ol[1]);           // plain [128][64 B]
+              *reinterpret_cast<uint2*>(staging + 24576 + rl * 64 + c * 8) = make_uint2(oh8[0], oh8[1]);
+            }
+          }
+          if (!a.fuse_out) {
+            ptx::fence_proxy_async_smem();
+            ptx::named_bar_sync(2, 128);
+            if (et == 0) {
+              ptx::tma_store_3d(&tm_yh, staging, h * 128, ts, b);
+              ptx::tma_store_3d(&tm_yb, staging + 16384, 256 + h * 64, ts, b);
+              ptx::tma_store_3d(&tm_yb, staging + 24576, 384 + h * 64, ts, b);
+              ptx::tma_store_commit();
+            }
+          }
+        }
+        if (a.fuse_out && row_ok) {
+          a.out[((size_t)b * a.n_out + 0) * a.T + t] = fminf(fmaxf(o0 + __ldg(a.out_b), -1.f), 1.f);
+          if (a.n_out > 1) a.out[((size_t)b * a.n_out + 1) * a.T + t] = fminf(fmaxf(o1 + __ldg(a.out_b + 1), -1.f), 1.f);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&bars->tmem_empty[buf]);
+    }
+    if (et == 0) ptx::tma_store_wait_all();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+static int encode_bytes_map(CUtensorMap* m, const void* base, int rank, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2,
+                            cuuint32_t box0, cuuint32_t box1, bool swizzle) {
+  PFN_encodeTiled enc = tensor_map_encoder();
+  if (!enc) return 1;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0, d0 * d1};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, rank, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f16f8, rank %d, box %u x %u) failed: CUresult %d", rank, box0, box1, (int)r);
+  return 0;
+}
+
+}  // namespace f8
+
+// ---- entry points used by tcn.cu ----
+size_t tcn_f8_weight_bytes() { return (size_t)f8::kTaps * 4 * f8::kCh * 128; }   // 983,040 B per layer (same as bf16 x 2)
+
+int tcn_f8_pack_layer(const float* conv_w, const float* bn_w, const float* bn_var, void* w_out, float* inv_scale,
+                      unsigned int* scratch, cudaStream_t st) {
+  MST_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(unsigned int), st));
+  f8::wmax_kernel<<<128, 256, 0, st>>>(conv_w, bn_w, bn_var, scratch);
+  if (launch_ok("tcn f8 wmax_kernel")) return 1;
+  f8::pack_kernel<<<256, 256, 0, st>>>(conv_w, bn_w, bn_var, scratch, (uint8_t*)w_out, inv_scale);
+  return launch_ok("tcn f8 pack_kernel");
+}
+
+int tcn_f8_launch_block0(int n_inputs, const float* x, const float* w0, const float* film, int n_cond, void* act, int B, int T,
+                         cudaStream_t st) {
+  dim3 grid(cdiv(T, 256), B);
+  const float4* f = reinterpret_cast<const float4*>(film);
+  if (n_inputs == 2) f8::block0_kernel<2><<<grid, 256, 0, st>>>(x, w0, f, n_cond, (uint8_t*)act, T);
+  else f8::block0_kernel<1><<<grid, 256, 0, st>>>(x, w0, f, n_cond, (uint8_t*)act, T);
+  return launch_ok("tcn f8 block0_kernel");
+}
+
+int tcn_f8_act_pack(const float* x, void* act, int B, int T, cudaStream_t st) {
+  f8::act_pack_kernel<<<dim3(cdiv(T, 32), B), 256, 0, st>>>(x, (uint8_t*)act, T);
+  return launch_ok("tcn f8 act_pack_kernel");
+}
+int tcn_f8_act_unpack(const void* act, float* y, int B, int T, cudaStream_t st) {
+  f8::act_unpack_kernel<<<dim3(cdiv(T, 32), B), 256, 0, st>>>((const uint8_t*)act, y, T);
+  return launch_ok("tcn f8 act_unpack_kernel");
+}
+
+int tcn_f8_launch_block(long long dilation, const void* w_layer, const float* inv_scale, const void* act_in, void* act_out,
+                        const float* film_layer, int n_cond, int B, int T, bool fuse_out, int n_out, const float* out_w,
+                        const float* out_b, float* out, cudaStream_t st) {
+  CUtensorMap tm_x, tm_w, tm_yh, tm_yb;
+  if (f8::encode_bytes_map(&tm_x, act_in, 3, f8::kRowBytes, T, B, 128, f8::kSubRows, true)) return 1;
+  if (f8::encode_bytes_map(&tm_w, w_layer, 2, 128, (cuuint64_t)f8::kTaps * 4 * f8::kCh, 1, 128, f8::kCh, true)) return 1;
+  const void* ybase = fuse_out ? act_in : act_out;
+  if (f8::encode_bytes_map(&tm_yh, ybase, 3, f8::kRowBytes, T, B, 128, f8::kSubRows, true)) return 1;
+  if (f8::encode_bytes_map(&tm_yb, ybase, 3, f8::kRowBytes, T, B, 64, f8::kSubRows, false)) return 1;
+  f8::LayerArgs a;
+  a.B = B; a.T = T; a.dilation = (int)dilation;
+  a.tiles_per_seg = cdiv(T, f8::kTileRows);
+  a.n_tiles = B * a.tiles_per_seg;
+  a.n_cond = n_cond;
+  a.film = reinterpret_cast<const float4*>(film_layer);
+  a.inv_scale = inv_scale;
+  a.act_in = (const uint8_t*)act_in;
+  a.fuse_out = fuse_out ? 1 : 0;
+  a.n_out = n_out; a.out_w = out_w; a.out_b = out_b; a.out = out;
+  MST_CUDA_OK(cudaFuncSetAttribute(f8::block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f8::kSmemBytes));
+  const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
+  f8::block_kernel<<<grid, 256, f8::kSmemBytes, st>>>(tm_x, tm_w, tm_yh, tm_yb, a);
+  return launch_ok("tcn f8 block_kernel");
+}
+
+}  // namespace mst
