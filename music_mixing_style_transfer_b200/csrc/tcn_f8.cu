@@ -30,8 +30,8 @@ constexpr int kRowBytes = 512;
 constexpr int kSubRows = 128;
 constexpr int kTileRows = 256;
 constexpr int kSlotBytes = 32768;
-constexpr int kNumSlots = 6;
-constexpr int kStageBytes = 32768;   // epilogue: [fp16 tile 16 KB | e4m3 lo 8 KB | e4m3 hi 8 KB]
+constexpr int kWSlots = 3;           // weight ring  (released only after both sub-tiles consumed a slot -> its own ring)
+constexpr int kXSlots = 4;           // activation ring
 constexpr float kLoScale = 2048.f;   // 2^11
 
 __device__ __forceinline__ float fp8_to_float(uint8_t v) {
@@ -220,6 +220,7 @@ struct LayerArgs {
   const float4* film;
   const float* inv_scale;    // 1 / (S * 2^11) of this layer's packed weights
   const uint8_t* act_in;     // residual rows are read straight from global memory (L2-hot centre tap)
+  uint8_t* act_out;          // output rows are written straight from registers (all shared memory goes to the rings)
   int fuse_out, n_out;
   const float* out_w;
   const float* out_b;
@@ -227,12 +228,14 @@ struct LayerArgs {
 };
 
 struct __align__(8) Barriers {
-  uint64_t full[kNumSlots], empty[kNumSlots];
+  uint64_t w_full[kWSlots], w_empty[kWSlots];
+  uint64_t x_full[kXSlots], x_empty[kXSlots];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
 };
+constexpr int kThreads = 384;        // 4 control warps + 8 epilogue warps (two per TMEM lane quarter, one per channel half)
 
-constexpr size_t kSmemBytes = 1024 + (size_t)kNumSlots * kSlotBytes + kStageBytes + 256;
+constexpr size_t kSmemBytes = 1024 + (size_t)(kWSlots + kXSlots) * kSlotBytes + 256 + 1024;   // + fused-output partials
 
 __device__ __forceinline__ bool tap_live(long long ts, int T) { return ts < (long long)T && ts + kSubRows > 0; }
 
@@ -246,32 +249,33 @@ __device__ __forceinline__ void mma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_
       : "memory");
 }
 
-// tm_x / tm_w: byte tensors, box {128 B, 128 rows}, SWIZZLE_128B.  tm_yh: same box on the output (fp16 planes);
-// tm_yb: box {64 B, 128 rows}, no swizzle, for the two e4m3 planes.
-__global__ void __launch_bounds__(256, 1)
-block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-             const __grid_constant__ CUtensorMap tm_yh, const __grid_constant__ CUtensorMap tm_yb, const LayerArgs a) {
+// Pipeline: the L2 -> shared-memory round trip of a TMA box is ~1.3 us under load; a slot that is released at time t is
+// useful again at t + 1.3 us.  One MMA group (a weight slot + its one or two activation slots) lasts only ~0.7 us in this
+// mode, so (a) weights and activations get SEPARATE rings with separate producer lanes -- the weight slot is released
+// last and needed first, in a shared ring it would stall every activation load behind it -- and (b) all 224 KB of shared
+// memory are ring slots (3 x 32 KB weights, 4 x 32 KB activations): the epilogue reads the residual and writes the output
+// rows directly from / to global memory instead of staging them for TMA.
+// tm_x / tm_w: byte tensors, box {128 B, 128 rows}, SWIZZLE_128B.
+__global__ void __launch_bounds__(kThreads, 1)
+block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const LayerArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* ring = smem;
-  uint8_t* staging = smem + (size_t)kNumSlots * kSlotBytes;
-  Barriers* bars = reinterpret_cast<Barriers*>(staging + kStageBytes);
+  uint8_t* wring = smem;
+  uint8_t* xring = smem + (size_t)kWSlots * kSlotBytes;
+  Barriers* bars = reinterpret_cast<Barriers*>(xring + (size_t)kXSlots * kSlotBytes);
+  float2* opart = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [128 rows] partial outputs of half 1
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_x);
     ptx::prefetch_tensormap(&tm_w);
-    ptx::prefetch_tensormap(&tm_yh);
-    ptx::prefetch_tensormap(&tm_yb);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kNumSlots; ++i) {
-      ptx::mbar_init(&bars->full[i], 1);
-      ptx::mbar_init(&bars->empty[i], 1);
-    }
+    for (int i = 0; i < kWSlots; ++i) { ptx::mbar_init(&bars->w_full[i], 1); ptx::mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < kXSlots; ++i) { ptx::mbar_init(&bars->x_full[i], 1); ptx::mbar_init(&bars->x_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->tmem_full[i], 1);
-      ptx::mbar_init(&bars->tmem_empty[i], 128);
+      ptx::mbar_init(&bars->tmem_empty[i], 256);
     }
     ptx::mbar_fence_init();
   }
@@ -286,22 +290,16 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   const long long d = a.dilation;
 
   if (warp == 0) {
-    // ============================== TMA producer ==============================
+    // ============================== TMA producer: activations ==============================
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
-      auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
-      auto load_pair = [&](const CUtensorMap* tm, bool is_w, int c0a, int c0b, int r, int b) {
-        ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
-        ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
-        uint8_t* dst = ring + (size_t)slot * kSlotBytes;
-        if (is_w) {
-          ptx::tma_load_2d(tm, &bars->full[slot], dst, 0, c0a);
-          ptx::tma_load_2d(tm, &bars->full[slot], dst + 16384, 0, c0b);
-        } else {
-          ptx::tma_load_3d(tm, &bars->full[slot], dst, c0a, r, b);
-          ptx::tma_load_3d(tm, &bars->full[slot], dst + 16384, c0b, r, b);
-        }
-        next();
+      auto load_x = [&](int c0, int r, int b) {
+        ptx::mbar_wait(&bars->x_empty[slot], phase ^ 1);
+        ptx::mbar_expect_tx(&bars->x_full[slot], kSlotBytes);
+        uint8_t* dst = xring + (size_t)slot * kSlotBytes;
+        ptx::tma_load_3d(&tm_x, &bars->x_full[slot], dst, c0, r, b);
+        ptx::tma_load_3d(&tm_x, &bars->x_full[slot], dst + 16384, c0 + 128, r, b);
+        if (++slot == kXSlots) { slot = 0; phase ^= 1; }
       };
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int b = tile / a.tiles_per_seg;
@@ -310,12 +308,32 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         for (int j = 0; j < kTaps; ++j) {
           const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
           const bool live0 = tap_live(ts0, a.T), live1 = sub1 && tap_live(ts1, a.T);
-          if (!live0 && !live1) continue;
-          for (int grp = 0; grp < 2; ++grp) {   // 0: fp16 main tiles, 1: e4m3 correction tiles
+          for (int grp = 0; grp < 2; ++grp) {   // 0: fp16 planes, 1: e4m3 planes
+            if (live0) load_x(256 * grp, (int)ts0, b);
+            if (live1) load_x(256 * grp, (int)ts1, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ============================== TMA producer: weights ==============================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int b = tile / a.tiles_per_seg;
+        const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
+        const bool sub1 = t0 + kSubRows < a.T;
+        for (int j = 0; j < kTaps; ++j) {
+          const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
+          if (!tap_live(ts0, a.T) && !(sub1 && tap_live(ts1, a.T))) continue;
+          for (int grp = 0; grp < 2; ++grp) {
             const int wrow = (j * 4 + 2 * grp) * kCh;
-            load_pair(&tm_w, true, wrow, wrow + kCh, 0, 0);
-            if (live0) load_pair(&tm_x, false, 256 * grp, 256 * grp + 128, (int)ts0, b);
-            if (live1) load_pair(&tm_x, false, 256 * grp, 256 * grp + 128, (int)ts1, b);
+            ptx::mbar_wait(&bars->w_empty[slot], phase ^ 1);
+            ptx::mbar_expect_tx(&bars->w_full[slot], kSlotBytes);
+            uint8_t* dst = wring + (size_t)slot * kSlotBytes;
+            ptx::tma_load_2d(&tm_w, &bars->w_full[slot], dst, 0, wrow);
+            ptx::tma_load_2d(&tm_w, &bars->w_full[slot], dst + 16384, 0, wrow + kCh);
+            if (++slot == kWSlots) { slot = 0; phase ^= 1; }
           }
         }
       }
@@ -324,8 +342,7 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     // ============================== MMA issuer ==============================
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(kSubRows, kCh);   // A/B format code 0 = F16 (kind::f16) = E4M3 (kind::f8f6f4)
-      uint32_t slot = 0, phase = 0;
-      auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
+      uint32_t ws = 0, wph = 0, xs = 0, xph = 0;
       // one slot pair = two 16 KB operand tiles per side; tile i of X multiplies tile i of W; 4 K-steps of 32 bytes each
       auto issue_group = [&](uint32_t x_addr, uint32_t w_addr, uint32_t d_tmem, bool first, bool f8) {
 #pragma unroll
@@ -355,36 +372,36 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           const bool live0 = tap_live(ts0, a.T), live1 = sub1 && tap_live(ts1, a.T);
           if (!live0 && !live1) continue;
           for (int grp = 0; grp < 2; ++grp) {
-            const uint32_t wslot = slot;
-            ptx::mbar_wait(&bars->full[wslot], phase);
-            const uint32_t w_addr = ptx::smem_u32(ring + (size_t)wslot * kSlotBytes);
-            next();
+            ptx::mbar_wait(&bars->w_full[ws], wph);
+            const uint32_t w_addr = ptx::smem_u32(wring + (size_t)ws * kSlotBytes);
             if (live0) {
-              ptx::mbar_wait(&bars->full[slot], phase);
+              ptx::mbar_wait(&bars->x_full[xs], xph);
               ptx::tc_fence_after();
-              issue_group(ptx::smem_u32(ring + (size_t)slot * kSlotBytes), w_addr, acc0, first0, grp == 1);
+              issue_group(ptx::smem_u32(xring + (size_t)xs * kSlotBytes), w_addr, acc0, first0, grp == 1);
               first0 = false;
-              ptx::umma_commit(&bars->empty[slot]);
-              next();
+              ptx::umma_commit(&bars->x_empty[xs]);
+              if (++xs == kXSlots) { xs = 0; xph ^= 1; }
             }
             if (live1) {
-              ptx::mbar_wait(&bars->full[slot], phase);
+              ptx::mbar_wait(&bars->x_full[xs], xph);
               ptx::tc_fence_after();
-              issue_group(ptx::smem_u32(ring + (size_t)slot * kSlotBytes), w_addr, acc1, first1, grp == 1);
+              issue_group(ptx::smem_u32(xring + (size_t)xs * kSlotBytes), w_addr, acc1, first1, grp == 1);
               first1 = false;
-              ptx::umma_commit(&bars->empty[slot]);
-              next();
+              ptx::umma_commit(&bars->x_empty[xs]);
+              if (++xs == kXSlots) { xs = 0; xph ^= 1; }
             }
-            ptx::umma_commit(&bars->empty[wslot]);
+            ptx::umma_commit(&bars->w_empty[ws]);
+            if (++ws == kWSlots) { ws = 0; wph ^= 1; }
           }
         }
         ptx::umma_commit(&bars->tmem_full[buf]);
       }
     }
   } else if (warp >= 4) {
-    // ============================== epilogue (128 threads, thread <-> one time row) ==============================
+    // ============================== epilogue (256 threads: thread <-> one time row x one 64-channel half) ==============
+    // A warp may only read the TMEM lane quarter (warp % 4); warps 4-7 take channels 0-63, warps 8-11 channels 64-127.
     const int q = warp & 3;
-    const int et = threadIdx.x - 128;
+    const int h = (warp - 4) >> 2;
     const int rl = q * 32 + lane;
     const float inv_scale = __ldg(a.inv_scale);
     int it = 0;
@@ -400,9 +417,11 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         if (ts >= a.T) break;
         const int t = ts + rl;
         const bool row_ok = t < a.T;
-        const uint8_t* xrow = a.act_in + ((size_t)b * a.T + (row_ok ? t : 0)) * kRowBytes;
+        const size_t row_off = ((size_t)b * a.T + (row_ok ? t : 0)) * kRowBytes;
+        const uint8_t* xrow = a.act_in + row_off;
+        uint8_t* yrow = a.act_out + row_off;
         float o0 = 0.f, o1 = 0.f;
-        for (int h = 0; h < 2; ++h) {
+        {
           // residual x_in of this row and channel half: 8 x 16 B of fp16 hi + 8 x 8 B of e4m3 lo, all requested up front
           // so the L2 round trips overlap each other and the TMEM read
           uint4 xh[8];
@@ -421,12 +440,6 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
           ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
           ptx::tmem_ld_wait();
-          // the staging tile is free once the previous TMA stores have read it
-          if (!a.fuse_out) {
-            if (et == 0) ptx::tma_store_wait_read0();
-            ptx::named_bar_sync(1, 128);
-          }
-          uint8_t* srow = staging + rl * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {     // 8 channels per iteration, processed as 4 pairs
             const uint32_t xhw[4] = {xh[c].x, xh[c].y, xh[c].z, xh[c].w};
@@ -468,32 +481,30 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
                 oh8[pr >> 1] |= h2 << (16 * (pr & 1));
               }
             }
-            if (!a.fuse_out) {
-              *reinterpret_cast<uint4*>(srow + ((c ^ (rl & 7)) << 4)) = make_uint4(oh[0], oh[1], oh[2], oh[3]);   // SWIZZLE_128B tile
-              *reinterpret_cast<uint2*>(staging + 16384 + rl * 64 + c * 8) = make_uint2(ol[0], ol[1]);           // plain [128][64 B]
-              *reinterpret_cast<uint2*>(staging + 24576 + rl * 64 + c * 8) = make_uint2(oh8[0], oh8[1]);
-            }
-          }
-          if (!a.fuse_out) {
-            ptx::fence_proxy_async_smem();
-            ptx::named_bar_sync(2, 128);
-            if (et == 0) {
-              ptx::tma_store_3d(&tm_yh, staging, h * 128, ts, b);
-              ptx::tma_store_3d(&tm_yb, staging + 16384, 256 + h * 64, ts, b);
-              ptx::tma_store_3d(&tm_yb, staging + 24576, 384 + h * 64, ts, b);
-              ptx::tma_store_commit();
+            if (!a.fuse_out && row_ok) {
+              // the thread owns its row: every 32-byte sector it touches it fills; streaming stores (evict-first) keep
+              // the write-once output from displacing the tap tiles that 14 other taps still want from L2
+              __stcs(reinterpret_cast<uint4*>(yrow + h * 128 + c * 16), make_uint4(oh[0], oh[1], oh[2], oh[3]));
+              __stcs(reinterpret_cast<uint2*>(yrow + 256 + h * 64 + c * 8), make_uint2(ol[0], ol[1]));
+              __stcs(reinterpret_cast<uint2*>(yrow + 384 + h * 64 + c * 8), make_uint2(oh8[0], oh8[1]));
             }
           }
         }
-        if (a.fuse_out && row_ok) {
-          a.out[((size_t)b * a.n_out + 0) * a.T + t] = fminf(fmaxf(o0 + __ldg(a.out_b), -1.f), 1.f);
-          if (a.n_out > 1) a.out[((size_t)b * a.n_out + 1) * a.T + t] = fminf(fmaxf(o1 + __ldg(a.out_b + 1), -1.f), 1.f);
+        if (a.fuse_out) {
+          // the two channel halves of a row live in different warps: half 1 hands its partial sums over in shared memory
+          if (h == 1) opart[rl] = make_float2(o0, o1);
+          ptx::named_bar_sync(1, 256);
+          if (h == 0 && row_ok) {
+            const float2 pp = opart[rl];
+            a.out[((size_t)b * a.n_out + 0) * a.T + t] = fminf(fmaxf(o0 + pp.x + __ldg(a.out_b), -1.f), 1.f);
+            if (a.n_out > 1) a.out[((size_t)b * a.n_out + 1) * a.T + t] = fminf(fmaxf(o1 + pp.y + __ldg(a.out_b + 1), -1.f), 1.f);
+          }
+          ptx::named_bar_sync(2, 256);   // opart is reused by the next sub-tile
         }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars->tmem_empty[buf]);
     }
-    if (et == 0) ptx::tma_store_wait_all();
   }
 
   ptx::tc_fence_before();
@@ -555,12 +566,9 @@ int tcn_f8_act_unpack(const void* act, float* y, int B, int T, cudaStream_t st) 
 int tcn_f8_launch_block(long long dilation, const void* w_layer, const float* inv_scale, const void* act_in, void* act_out,
                         const float* film_layer, int n_cond, int B, int T, bool fuse_out, int n_out, const float* out_w,
                         const float* out_b, float* out, cudaStream_t st) {
-  CUtensorMap tm_x, tm_w, tm_yh, tm_yb;
+  CUtensorMap tm_x, tm_w;
   if (f8::encode_bytes_map(&tm_x, act_in, 3, f8::kRowBytes, T, B, 128, f8::kSubRows, true)) return 1;
   if (f8::encode_bytes_map(&tm_w, w_layer, 2, 128, (cuuint64_t)f8::kTaps * 4 * f8::kCh, 1, 128, f8::kCh, true)) return 1;
-  const void* ybase = fuse_out ? act_in : act_out;
-  if (f8::encode_bytes_map(&tm_yh, ybase, 3, f8::kRowBytes, T, B, 128, f8::kSubRows, true)) return 1;
-  if (f8::encode_bytes_map(&tm_yb, ybase, 3, f8::kRowBytes, T, B, 64, f8::kSubRows, false)) return 1;
   f8::LayerArgs a;
   a.B = B; a.T = T; a.dilation = (int)dilation;
   a.tiles_per_seg = cdiv(T, f8::kTileRows);
@@ -569,11 +577,12 @@ int tcn_f8_launch_block(long long dilation, const void* w_layer, const float* in
   a.film = reinterpret_cast<const float4*>(film_layer);
   a.inv_scale = inv_scale;
   a.act_in = (const uint8_t*)act_in;
+  a.act_out = (uint8_t*)act_out;
   a.fuse_out = fuse_out ? 1 : 0;
   a.n_out = n_out; a.out_w = out_w; a.out_b = out_b; a.out = out;
   MST_CUDA_OK(cudaFuncSetAttribute(f8::block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f8::kSmemBytes));
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-  f8::block_kernel<<<grid, 256, f8::kSmemBytes, st>>>(tm_x, tm_w, tm_yh, tm_yb, a);
+  f8::block_kernel<<<grid, f8::kThreads, f8::kSmemBytes, st>>>(tm_x, tm_w, a);
   return launch_ok("tcn f8 block_kernel");
 }
 
