@@ -225,6 +225,7 @@ struct LayerArgs {
   const float* out_w;
   const float* out_b;
   float* out;
+  int dbg;                   // diagnostics only (MST_TCN_DBG): 1 = skip the MMAs, 2 = skip the TMA loads, 4 = skip epilogue math/stores
 };
 
 struct __align__(8) Barriers {
@@ -249,6 +250,30 @@ __device__ __forceinline__ void mma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_
       : "memory");
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose box lands at the same shared-memory offset of EVERY CTA in `mask` and completes bytes on the mbarrier
+// at the same offset of each of them
+__device__ __forceinline__ void tma_load_2d_multicast(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(ptx::smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+
 // Pipeline: the L2 -> shared-memory round trip of a TMA box is ~1.3 us under load; a slot that is released at time t is
 // useful again at t + 1.3 us.  One MMA group (a weight slot + its one or two activation slots) lasts only ~0.7 us in this
 // mode, so (a) weights and activations get SEPARATE rings with separate producer lanes -- the weight slot is released
@@ -256,6 +281,12 @@ __device__ __forceinline__ void mma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_
 // memory are ring slots (3 x 32 KB weights, 4 x 32 KB activations): the epilogue reads the residual and writes the output
 // rows directly from / to global memory instead of staging them for TMA.
 // tm_x / tm_w: byte tensors, box {128 B, 128 rows}, SWIZZLE_128B.
+//
+// MC2 = 1: launched as clusters of two CTAs that work on time-adjacent tiles in lockstep.  Each CTA fetches HALF of every
+// weight slot and TMA-multicasts it into both CTAs' shared memory, so the weight bytes cross the L2 -> SM fabric once per
+// pair (the kernel is bound by that fabric: ~11 TB/s, 100 GB per launch, one third of it weights).  A weight slot may be
+// overwritten only when BOTH consumers have released it: w_empty counts 2 and every release is a multicast commit.
+template <int MC2>
 __global__ void __launch_bounds__(kThreads, 1)
 block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const LayerArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -271,7 +302,7 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     ptx::prefetch_tensormap(&tm_w);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kWSlots; ++i) { ptx::mbar_init(&bars->w_full[i], 1); ptx::mbar_init(&bars->w_empty[i], 1); }
+    for (int i = 0; i < kWSlots; ++i) { ptx::mbar_init(&bars->w_full[i], 1); ptx::mbar_init(&bars->w_empty[i], MC2 ? 2 : 1); }
     for (int i = 0; i < kXSlots; ++i) { ptx::mbar_init(&bars->x_full[i], 1); ptx::mbar_init(&bars->x_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->tmem_full[i], 1);
@@ -286,8 +317,28 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  if (MC2) cluster_sync_all();     // the peer's barriers are initialised before anything remote can touch them
   const uint32_t tmem_base = bars->tmem_base;
   const long long d = a.dilation;
+  // work assignment: CTA `rank` of cluster `cid` takes tile 2*pair + rank of every pair it visits (MC2), else tile = pair
+  const int rank = MC2 ? (int)cluster_ctarank() : 0;
+  const int cid = MC2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ncl = MC2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_pairs = MC2 ? (a.n_tiles + 1) / 2 : a.n_tiles;
+  struct TileInfo { int b, t0; bool valid, sub1; };
+  auto tile_info = [&](int tile) {
+    TileInfo ti;
+    ti.valid = tile < a.n_tiles;
+    ti.b = ti.valid ? tile / a.tiles_per_seg : 0;
+    ti.t0 = ti.valid ? (tile - ti.b * a.tiles_per_seg) * kTileRows : 0;
+    ti.sub1 = ti.valid && ti.t0 + kSubRows < a.T;
+    return ti;
+  };
+  auto tap_need = [&](const TileInfo& ti, int j, bool& live0, bool& live1) {
+    const long long ts0 = ti.t0 + (long long)(j - 7) * d;
+    live0 = ti.valid && tap_live(ts0, a.T);
+    live1 = ti.sub1 && tap_live(ts0 + kSubRows, a.T);
+  };
 
   if (warp == 0) {
     // ============================== TMA producer: activations ==============================
@@ -295,22 +346,24 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
       uint32_t slot = 0, phase = 0;
       auto load_x = [&](int c0, int r, int b) {
         ptx::mbar_wait(&bars->x_empty[slot], phase ^ 1);
+        if (a.dbg & 2) { ptx::mbar_arrive(&bars->x_full[slot]); if (++slot == kXSlots) { slot = 0; phase ^= 1; } return; }
         ptx::mbar_expect_tx(&bars->x_full[slot], kSlotBytes);
         uint8_t* dst = xring + (size_t)slot * kSlotBytes;
         ptx::tma_load_3d(&tm_x, &bars->x_full[slot], dst, c0, r, b);
         ptx::tma_load_3d(&tm_x, &bars->x_full[slot], dst + 16384, c0 + 128, r, b);
         if (++slot == kXSlots) { slot = 0; phase ^= 1; }
       };
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int b = tile / a.tiles_per_seg;
-        const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
-        const bool sub1 = t0 + kSubRows < a.T;
-        for (int j = 0; j < kTaps; ++j) {
-          const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
-          const bool live0 = tap_live(ts0, a.T), live1 = sub1 && tap_live(ts1, a.T);
-          for (int grp = 0; grp < 2; ++grp) {   // 0: fp16 planes, 1: e4m3 planes
-            if (live0) load_x(256 * grp, (int)ts0, b);
-            if (live1) load_x(256 * grp, (int)ts1, b);
+      for (int pair = cid; pair < n_pairs; pair += ncl) {
+        const TileInfo me = tile_info(MC2 ? 2 * pair + rank : pair);
+        // all fp16 (kind::f16) tap groups of the tile first, then all e4m3 (kind::f8f6f4) ones: the tensor pipe pays for
+        // every change of MMA kind, so the kinds are switched twice per tile instead of 30 times
+        for (int grp = 0; grp < 2; ++grp) {
+          for (int j = 0; j < kTaps; ++j) {
+            bool live0, live1;
+            tap_need(me, j, live0, live1);
+            const long long ts0 = me.t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
+            if (live0) load_x(256 * grp, (int)ts0, me.b);
+            if (live1) load_x(256 * grp, (int)ts1, me.b);
           }
         }
       }
@@ -319,20 +372,25 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     // ============================== TMA producer: weights ==============================
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int b = tile / a.tiles_per_seg;
-        const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
-        const bool sub1 = t0 + kSubRows < a.T;
-        for (int j = 0; j < kTaps; ++j) {
-          const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
-          if (!tap_live(ts0, a.T) && !(sub1 && tap_live(ts1, a.T))) continue;
-          for (int grp = 0; grp < 2; ++grp) {
+      for (int pair = cid; pair < n_pairs; pair += ncl) {
+        const TileInfo me = tile_info(MC2 ? 2 * pair + rank : pair), peer = tile_info(MC2 ? 2 * pair + (rank ^ 1) : a.n_tiles);
+        for (int grp = 0; grp < 2; ++grp) {
+          for (int j = 0; j < kTaps; ++j) {
+            bool l0, l1, p0 = false, p1 = false;
+            tap_need(me, j, l0, l1);
+            if (MC2) tap_need(peer, j, p0, p1);
+            if (!(l0 || l1 || p0 || p1)) continue;     // neither CTA of the pair touches this tap
             const int wrow = (j * 4 + 2 * grp) * kCh;
             ptx::mbar_wait(&bars->w_empty[slot], phase ^ 1);
+            if (!MC2 && (a.dbg & 2)) { ptx::mbar_arrive(&bars->w_full[slot]); if (++slot == kWSlots) { slot = 0; phase ^= 1; } continue; }
             ptx::mbar_expect_tx(&bars->w_full[slot], kSlotBytes);
             uint8_t* dst = wring + (size_t)slot * kSlotBytes;
-            ptx::tma_load_2d(&tm_w, &bars->w_full[slot], dst, 0, wrow);
-            ptx::tma_load_2d(&tm_w, &bars->w_full[slot], dst + 16384, 0, wrow + kCh);
+            if (MC2) {   // my half of the slot, delivered to both CTAs; the peer delivers the other half
+              tma_load_2d_multicast(&tm_w, &bars->w_full[slot], dst + rank * 16384, 0, wrow + rank * kCh, (uint16_t)0x3);
+            } else {
+              ptx::tma_load_2d(&tm_w, &bars->w_full[slot], dst, 0, wrow);
+              ptx::tma_load_2d(&tm_w, &bars->w_full[slot], dst + 16384, 0, wrow + kCh);
+            }
             if (++slot == kWSlots) { slot = 0; phase ^= 1; }
           }
         }
@@ -352,27 +410,27 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
           for (int k = 0; k < 4; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
             const uint32_t accum = (first && tl == 0 && k == 0) ? 0u : 1u;
+            if ((a.dbg & 1) || (f8 && (a.dbg & 8)) || (!f8 && (a.dbg & 16))) continue;
             if (f8) mma_f8(d_tmem, xd + adv, wd + adv, idesc, accum);
             else ptx::umma_mma_f16kind(d_tmem, xd + adv, wd + adv, idesc, accum);
           }
         }
       };
       int it = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        const int b = tile / a.tiles_per_seg;
-        const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
-        const bool sub1 = t0 + kSubRows < a.T;
+      for (int pair = cid; pair < n_pairs; pair += ncl, ++it) {
+        const TileInfo me = tile_info(MC2 ? 2 * pair + rank : pair), peer = tile_info(MC2 ? 2 * pair + (rank ^ 1) : a.n_tiles);
         const int buf = it & 1;
         ptx::mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 + 0) * kCh, acc1 = tmem_base + (uint32_t)(buf * 2 + 1) * kCh;
         bool first0 = true, first1 = true;
-        for (int j = 0; j < kTaps; ++j) {
-          const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
-          const bool live0 = tap_live(ts0, a.T), live1 = sub1 && tap_live(ts1, a.T);
-          if (!live0 && !live1) continue;
-          for (int grp = 0; grp < 2; ++grp) {
-            ptx::mbar_wait(&bars->w_full[ws], wph);
+        for (int grp = 0; grp < 2; ++grp) {
+          for (int j = 0; j < kTaps; ++j) {
+            bool live0, live1, p0 = false, p1 = false;
+            tap_need(me, j, live0, live1);
+            if (MC2) tap_need(peer, j, p0, p1);
+            if (!(live0 || live1 || p0 || p1)) continue;
+            ptx::mbar_wait(&bars->w_full[ws], wph);     // also when only the peer needs it: a slot is released only after it landed
             const uint32_t w_addr = ptx::smem_u32(wring + (size_t)ws * kSlotBytes);
             if (live0) {
               ptx::mbar_wait(&bars->x_full[xs], xph);
@@ -390,7 +448,8 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
               ptx::umma_commit(&bars->x_empty[xs]);
               if (++xs == kXSlots) { xs = 0; xph ^= 1; }
             }
-            ptx::umma_commit(&bars->w_empty[ws]);
+            if (MC2) umma_commit_multicast(&bars->w_empty[ws], (uint16_t)0x3);
+            else ptx::umma_commit(&bars->w_empty[ws]);
             if (++ws == kWSlots) { ws = 0; wph ^= 1; }
           }
         }
@@ -405,16 +464,16 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     const int rl = q * 32 + lane;
     const float inv_scale = __ldg(a.inv_scale);
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-      const int b = tile / a.tiles_per_seg;
-      const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
+    for (int pair = cid; pair < n_pairs; pair += ncl, ++it) {
+      const TileInfo me = tile_info(MC2 ? 2 * pair + rank : pair);
+      const int b = me.b, t0 = me.t0;
       const int buf = it & 1;
       const float4* film = a.film + (size_t)(a.n_cond > 1 ? b : 0) * kCh;
       ptx::mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();
       for (int sub = 0; sub < 2; ++sub) {
         const int ts = t0 + sub * kSubRows;
-        if (ts >= a.T) break;
+        if (!me.valid || ts >= a.T || (a.dbg & 4)) break;
         const int t = ts + rl;
         const bool row_ok = t < a.T;
         const size_t row_off = ((size_t)b * a.T + (row_ok ? t : 0)) * kRowBytes;
@@ -509,6 +568,7 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (MC2) cluster_sync_all();     // nobody leaves while the peer may still multicast into it or arrive on its barriers
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -580,9 +640,28 @@ int tcn_f8_launch_block(long long dilation, const void* w_layer, const float* in
   a.act_out = (uint8_t*)act_out;
   a.fuse_out = fuse_out ? 1 : 0;
   a.n_out = n_out; a.out_w = out_w; a.out_b = out_b; a.out = out;
-  MST_CUDA_OK(cudaFuncSetAttribute(f8::block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f8::kSmemBytes));
+  { const char* e = getenv("MST_TCN_DBG"); a.dbg = e ? atoi(e) : 0; }
+  static int mc2 = -1;
+  if (mc2 < 0) { const char* e = getenv("MST_TCN_MULTICAST"); mc2 = (e && atoi(e) == 0) ? 0 : 1; }
+  if (mc2) {
+    MST_CUDA_OK(cudaFuncSetAttribute(f8::block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f8::kSmemBytes));
+    const int n_pairs = (a.n_tiles + 1) / 2;
+    const int clusters = n_pairs < sm_count() / 2 ? n_pairs : sm_count() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(f8::kThreads);
+    cfg.dynamicSmemBytes = f8::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MST_CUDA_OK(cudaLaunchKernelEx(&cfg, f8::block_kernel<1>, tm_x, tm_w, a));
+    return launch_ok("tcn f8 block_kernel<mc2>");
+  }
+  MST_CUDA_OK(cudaFuncSetAttribute(f8::block_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f8::kSmemBytes));
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-  f8::block_kernel<<<grid, f8::kThreads, f8::kSmemBytes, st>>>(tm_x, tm_w, a);
+  f8::block_kernel<0><<<grid, f8::kThreads, f8::kSmemBytes, st>>>(tm_x, tm_w, a);
   return launch_ok("tcn f8 block_kernel");
 }
 
