@@ -67,5 +67,8 @@ int tcn_f8_act_unpack(const void* act, float* y, int B, int T, cudaStream_t st);
 int tcn_f8_launch_block(long long dilation, const void* w_layer, const float* inv_scale, const void* act_in, void* act_out,
                         const float* film_layer, int n_cond, int B, int T, bool fuse_out, int n_out, const float* out_w,
                         const float* out_b, float* out, cudaStream_t st);
+int tcn_pipe2_launch_block(long long dilation, const void* w_layer, const void* act_in, void* act_out, const float* film_layer,
+                           int n_cond, int B, int T, bool fuse_out, int n_out, const float* out_w, const float* out_b,
+                           float* out, cudaStream_t st);
 
 }  // namespace mst

@@ -69,6 +69,17 @@ static int tcn_mode() {
   return v;
 }
 
+// Pipeline of blocks >= 1 in bf16 mode: 1 = one shared operand ring + TMA-staged epilogue (tcn_block_umma_kernel),
+// 2 = separate weight / activation rings + direct epilogue (block_kernel<*, 1> in tcn_f8.cu).  MST_TCN_PIPE overrides.
+static int tcn_pipe() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MST_TCN_PIPE");
+    v = (e && atoi(e) == 2) ? 2 : 1;
+  }
+  return v;
+}
+
 static int tcn_layout(const mst_tcn_config* c, TcnPacked* o) {
   MST_CHECK(c, "tcn config is null");
   MST_CHECK(c->channels == kCh && c->kernel_size == kTaps,
@@ -636,6 +647,11 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
                                reinterpret_cast<const float*>(packed + L.out_w),
                                reinterpret_cast<const float*>(packed + L.out_b), out, st);
   const int kch = tcn_kchunk();
+  if (tcn_pipe() == 2 && kch == 64)
+    return tcn_pipe2_launch_block(d, packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer, act_in, act_out,
+                                  film + (size_t)n * n_cond * kCh * 4, n_cond, B, T, fuse_out, cfg->n_outputs,
+                                  reinterpret_cast<const float*>(packed + L.out_w),
+                                  reinterpret_cast<const float*>(packed + L.out_b), out, st);
   CUtensorMap tm_x, tm_w, tm_xs, tm_y;
   if (encode_act_map(&tm_x, act_in, B, T, kch)) return 1;
   if (encode_act_map(&tm_xs, act_in, B, T, 64)) return 1;

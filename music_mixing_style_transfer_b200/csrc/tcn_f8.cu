@@ -286,7 +286,11 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ma
 // weight slot and TMA-multicasts it into both CTAs' shared memory, so the weight bytes cross the L2 -> SM fabric once per
 // pair (the kernel is bound by that fabric: ~11 TB/s, 100 GB per launch, one third of it weights).  A weight slot may be
 // overwritten only when BOTH consumers have released it: w_empty counts 2 and every release is a multicast commit.
-template <int MC2>
+//
+// FMT = 0: fp16 + 2 x e4m3 operands (the f16f8 mode).  FMT = 1: the default bf16 hi/lo operands of tcn.cu (three products
+// per K-step) run through THIS pipeline; rows are [hi ch0-63 | lo ch0-63 | hi ch64-127 | lo ch64-127], so the slot
+// addressing (column 256*grp and +128, weight rows (4*tap + 2*grp) * 128 and +128) is the same in both formats.
+template <int MC2, int FMT>
 __global__ void __launch_bounds__(kThreads, 1)
 block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const LayerArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -399,10 +403,26 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(kSubRows, kCh);   // A/B format code 0 = F16 (kind::f16) = E4M3 (kind::f8f6f4)
+      constexpr uint32_t idesc = FMT == 1 ? ptx::umma_idesc_bf16_f32(kSubRows, kCh)
+                                          : ptx::umma_idesc_f16_f32(kSubRows, kCh);   // code 0 = F16 (kind::f16) = E4M3 (kind::f8f6f4)
       uint32_t ws = 0, wph = 0, xs = 0, xph = 0;
-      // one slot pair = two 16 KB operand tiles per side; tile i of X multiplies tile i of W; 4 K-steps of 32 bytes each
+      // one slot pair = two 16 KB operand tiles per side, 4 K-steps of 32 bytes each.
+      // FMT 0: tile i of X multiplies tile i of W.   FMT 1: X = [hi | lo], W = [hi | lo]: hi*hi + lo*hi + hi*lo.
       auto issue_group = [&](uint32_t x_addr, uint32_t w_addr, uint32_t d_tmem, bool first, bool f8) {
+        if (FMT == 1) {
+          const uint64_t xh = ptx::umma_desc_kmajor<128>(x_addr), xl = ptx::umma_desc_kmajor<128>(x_addr + 16384);
+          const uint64_t wh = ptx::umma_desc_kmajor<128>(w_addr), wl = ptx::umma_desc_kmajor<128>(w_addr + 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            if (a.dbg & 1) continue;
+            ptx::umma_mma_f16kind(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u);
+            if (a.dbg & 32) continue;     // ablation: leading product only
+            ptx::umma_mma_f16kind(d_tmem, xl + adv, wh + adv, idesc, 1u);
+            ptx::umma_mma_f16kind(d_tmem, xh + adv, wl + adv, idesc, 1u);
+          }
+          return;
+        }
 #pragma unroll
         for (int tl = 0; tl < 2; ++tl) {
           const uint64_t xd = ptx::umma_desc_kmajor<128>(x_addr + tl * 16384), wd = ptx::umma_desc_kmajor<128>(w_addr + tl * 16384);
@@ -422,7 +442,8 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         const int buf = it & 1;
         ptx::mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
-        const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 + 0) * kCh, acc1 = tmem_base + (uint32_t)(buf * 2 + 1) * kCh;
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 + 0) * kCh;
+        const uint32_t acc1 = (a.dbg & 128) ? acc0 : tmem_base + (uint32_t)(buf * 2 + 1) * kCh;   // ablation: one accumulator
         bool first0 = true, first1 = true;
         for (int grp = 0; grp < 2; ++grp) {
           for (int j = 0; j < kTaps; ++j) {
@@ -434,21 +455,22 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
             const uint32_t w_addr = ptx::smem_u32(wring + (size_t)ws * kSlotBytes);
             if (live0) {
               ptx::mbar_wait(&bars->x_full[xs], xph);
-              ptx::tc_fence_after();
+              if (!(a.dbg & 256)) ptx::tc_fence_after();
               issue_group(ptx::smem_u32(xring + (size_t)xs * kSlotBytes), w_addr, acc0, first0, grp == 1);
               first0 = false;
-              ptx::umma_commit(&bars->x_empty[xs]);
+              if (a.dbg & 64) ptx::mbar_arrive(&bars->x_empty[xs]); else ptx::umma_commit(&bars->x_empty[xs]);
               if (++xs == kXSlots) { xs = 0; xph ^= 1; }
             }
             if (live1) {
               ptx::mbar_wait(&bars->x_full[xs], xph);
-              ptx::tc_fence_after();
+              if (!(a.dbg & 256)) ptx::tc_fence_after();
               issue_group(ptx::smem_u32(xring + (size_t)xs * kSlotBytes), w_addr, acc1, first1, grp == 1);
               first1 = false;
-              ptx::umma_commit(&bars->x_empty[xs]);
+              if (a.dbg & 64) ptx::mbar_arrive(&bars->x_empty[xs]); else ptx::umma_commit(&bars->x_empty[xs]);
               if (++xs == kXSlots) { xs = 0; xph ^= 1; }
             }
             if (MC2) umma_commit_multicast(&bars->w_empty[ws], (uint16_t)0x3);
+            else if (a.dbg & 64) ptx::mbar_arrive(&bars->w_empty[ws]);     // ablation (with bit 2 only): no commit per slot
             else ptx::umma_commit(&bars->w_empty[ws]);
             if (++ws == kWSlots) { ws = 0; wph ^= 1; }
           }
@@ -462,7 +484,7 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
     const int q = warp & 3;
     const int h = (warp - 4) >> 2;
     const int rl = q * 32 + lane;
-    const float inv_scale = __ldg(a.inv_scale);
+    const float inv_scale = FMT == 0 ? __ldg(a.inv_scale) : 1.f;
     int it = 0;
     for (int pair = cid; pair < n_pairs; pair += ncl, ++it) {
       const TileInfo me = tile_info(MC2 ? 2 * pair + rank : pair);
@@ -480,7 +502,7 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
         const uint8_t* xrow = a.act_in + row_off;
         uint8_t* yrow = a.act_out + row_off;
         float o0 = 0.f, o1 = 0.f;
-        {
+        if constexpr (FMT == 0) {
           // residual x_in of this row and channel half: 8 x 16 B of fp16 hi + 8 x 8 B of e4m3 lo, all requested up front
           // so the L2 round trips overlap each other and the TMEM read
           uint4 xh[8];
@@ -546,6 +568,65 @@ block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ C
               __stcs(reinterpret_cast<uint4*>(yrow + h * 128 + c * 16), make_uint4(oh[0], oh[1], oh[2], oh[3]));
               __stcs(reinterpret_cast<uint2*>(yrow + 256 + h * 64 + c * 8), make_uint2(ol[0], ol[1]));
               __stcs(reinterpret_cast<uint2*>(yrow + 384 + h * 64 + c * 8), make_uint2(oh8[0], oh8[1]));
+            }
+          }
+        }
+        else {
+          // residual x_in of this row and channel half: 8 x 16 B of bf16 hi and 8 x 16 B of bf16 lo, requested up front
+          uint4 xh[8], xl[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            xh[c] = make_uint4(0, 0, 0, 0);
+            xl[c] = make_uint4(0, 0, 0, 0);
+            if (row_ok) {
+              xh[c] = __ldg(reinterpret_cast<const uint4*>(xrow + h * 256 + c * 16));
+              xl[c] = __ldg(reinterpret_cast<const uint4*>(xrow + h * 256 + 128 + c * 16));
+            }
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t acc[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * kCh + h * 64 + half * 32);
+            ptx::tmem_ld_32x32(taddr, acc);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int c = half * 4 + c4;
+              const uint32_t xhw[4] = {xh[c].x, xh[c].y, xh[c].z, xh[c].w};
+              const uint32_t xlw[4] = {xl[c].x, xl[c].y, xl[c].z, xl[c].w};
+              uint32_t oh[4], ol[4];
+#pragma unroll
+              for (int pr = 0; pr < 4; ++pr) {
+                const int cl = c4 * 8 + 2 * pr;            // column inside this 32-column half
+                const int ch = h * 64 + half * 32 + cl;
+                const float4 P0 = __ldg(film + ch), P1 = __ldg(film + ch + 1);
+                const float xin0 = __uint_as_float(xhw[pr] << 16) + __uint_as_float(xlw[pr] << 16);
+                const float xin1 = __uint_as_float(xhw[pr] & 0xFFFF0000u) + __uint_as_float(xlw[pr] & 0xFFFF0000u);
+                float u0 = __uint_as_float(acc[cl]) + P0.x;
+                float u1 = __uint_as_float(acc[cl + 1]) + P1.x;
+                u0 = u0 > 0.f ? u0 : 0.01f * u0;
+                u1 = u1 > 0.f ? u1 : 0.01f * u1;
+                u0 = fmaf(P0.y, u0, P0.z) + P0.w * xin0;
+                u1 = fmaf(P1.y, u1, P1.z) + P1.w * xin1;
+                if (a.fuse_out) {
+                  o0 = fmaf(u0, __ldg(a.out_w + ch), o0);
+                  o0 = fmaf(u1, __ldg(a.out_w + ch + 1), o0);
+                  if (a.n_out > 1) {
+                    o1 = fmaf(u0, __ldg(a.out_w + kCh + ch), o1);
+                    o1 = fmaf(u1, __ldg(a.out_w + kCh + ch + 1), o1);
+                  }
+                } else {
+                  const __nv_bfloat16 h0 = __float2bfloat16_rn(u0), h1 = __float2bfloat16_rn(u1);
+                  const __nv_bfloat16 l0 = __float2bfloat16_rn(u0 - __bfloat162float(h0));
+                  const __nv_bfloat16 l1 = __float2bfloat16_rn(u1 - __bfloat162float(h1));
+                  oh[pr] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                  ol[pr] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+              }
+              if (!a.fuse_out && row_ok) {
+                __stcs(reinterpret_cast<uint4*>(yrow + h * 256 + c * 16), make_uint4(oh[0], oh[1], oh[2], oh[3]));
+                __stcs(reinterpret_cast<uint4*>(yrow + h * 256 + 128 + c * 16), make_uint4(ol[0], ol[1], ol[2], ol[3]));
+              }
             }
           }
         }
@@ -623,9 +704,10 @@ int tcn_f8_act_unpack(const void* act, float* y, int B, int T, cudaStream_t st) 
   return launch_ok("tcn f8 act_unpack_kernel");
 }
 
-int tcn_f8_launch_block(long long dilation, const void* w_layer, const float* inv_scale, const void* act_in, void* act_out,
-                        const float* film_layer, int n_cond, int B, int T, bool fuse_out, int n_out, const float* out_w,
-                        const float* out_b, float* out, cudaStream_t st) {
+template <int FMT>
+static int launch_block_impl(long long dilation, const void* w_layer, const float* inv_scale, const void* act_in, void* act_out,
+                             const float* film_layer, int n_cond, int B, int T, bool fuse_out, int n_out, const float* out_w,
+                             const float* out_b, float* out, cudaStream_t st) {
   CUtensorMap tm_x, tm_w;
   if (f8::encode_bytes_map(&tm_x, act_in, 3, f8::kRowBytes, T, B, 128, f8::kSubRows, true)) return 1;
   if (f8::encode_bytes_map(&tm_w, w_layer, 2, 128, (cuuint64_t)f8::kTaps * 4 * f8::kCh, 1, 128, f8::kCh, true)) return 1;
@@ -642,9 +724,9 @@ int tcn_f8_launch_block(long long dilation, const void* w_layer, const float* in
   a.n_out = n_out; a.out_w = out_w; a.out_b = out_b; a.out = out;
   { const char* e = getenv("MST_TCN_DBG"); a.dbg = e ? atoi(e) : 0; }
   static int mc2 = -1;
-  if (mc2 < 0) { const char* e = getenv("MST_TCN_MULTICAST"); mc2 = (e && atoi(e) == 0) ? 0 : 1; }
+  if (mc2 < 0) { const char* e = getenv("MST_TCN_MULTICAST"); mc2 = (e && atoi(e) == 1) ? 1 : 0; }   // measured slower: off by default
   if (mc2) {
-    MST_CUDA_OK(cudaFuncSetAttribute(f8::block_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f8::kSmemBytes));
+    MST_CUDA_OK(cudaFuncSetAttribute(f8::block_kernel<1, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f8::kSmemBytes));
     const int n_pairs = (a.n_tiles + 1) / 2;
     const int clusters = n_pairs < sm_count() / 2 ? n_pairs : sm_count() / 2;
     cudaLaunchConfig_t cfg = {};
@@ -656,13 +738,28 @@ int tcn_f8_launch_block(long long dilation, const void* w_layer, const float* in
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    MST_CUDA_OK(cudaLaunchKernelEx(&cfg, f8::block_kernel<1>, tm_x, tm_w, a));
-    return launch_ok("tcn f8 block_kernel<mc2>");
+    MST_CUDA_OK(cudaLaunchKernelEx(&cfg, f8::block_kernel<1, FMT>, tm_x, tm_w, a));
+    return launch_ok("tcn dual-ring block_kernel<mc2>");
   }
-  MST_CUDA_OK(cudaFuncSetAttribute(f8::block_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f8::kSmemBytes));
+  MST_CUDA_OK(cudaFuncSetAttribute(f8::block_kernel<0, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f8::kSmemBytes));
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-  f8::block_kernel<0><<<grid, f8::kThreads, f8::kSmemBytes, st>>>(tm_x, tm_w, a);
-  return launch_ok("tcn f8 block_kernel");
+  f8::block_kernel<0, FMT><<<grid, f8::kThreads, f8::kSmemBytes, st>>>(tm_x, tm_w, a);
+  return launch_ok("tcn dual-ring block_kernel");
+}
+
+int tcn_f8_launch_block(long long dilation, const void* w_layer, const float* inv_scale, const void* act_in, void* act_out,
+                        const float* film_layer, int n_cond, int B, int T, bool fuse_out, int n_out, const float* out_w,
+                        const float* out_b, float* out, cudaStream_t st) {
+  return launch_block_impl<0>(dilation, w_layer, inv_scale, act_in, act_out, film_layer, n_cond, B, T, fuse_out, n_out, out_w,
+                              out_b, out, st);
+}
+
+// bf16 hi/lo activations and weights of tcn.cu (64-channel chunks) through the dual-ring pipeline
+int tcn_pipe2_launch_block(long long dilation, const void* w_layer, const void* act_in, void* act_out, const float* film_layer,
+                           int n_cond, int B, int T, bool fuse_out, int n_out, const float* out_w, const float* out_b,
+                           float* out, cudaStream_t st) {
+  return launch_block_impl<1>(dilation, w_layer, nullptr, act_in, act_out, film_layer, n_cond, B, T, fuse_out, n_out, out_w,
+                              out_b, out, st);
 }
 
 }  // namespace mst

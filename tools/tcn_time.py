@@ -18,4 +18,4 @@ with torch.no_grad():
         tcn.forward_layers(x, c, note)
 torch.cuda.synchronize()
 d = [ev[i].elapsed_time(ev[i + 1]) for i in range(0, len(ev), 2)]
-print({k: os.environ.get(k) for k in ("MST_TCN_PRECISION", "MST_TCN_MULTICAST", "MST_TCN_DBG")}, "ms/launch mean %.3f min %.3f max %.3f" % (sum(d) / len(d), min(d), max(d)))
+print({k: os.environ.get(k) for k in ("MST_TCN_PRECISION", "MST_TCN_PIPE", "MST_TCN_MULTICAST", "MST_TCN_DBG")}, "ms/launch mean %.3f min %.3f max %.3f" % (sum(d) / len(d), min(d), max(d)))
