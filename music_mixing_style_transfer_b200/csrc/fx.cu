@@ -27,6 +27,8 @@
 // compressor-pass sums (sum L^2, sum R^2, sum L*R), so imager + gain are a single element-wise pass.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace mst {
 
 constexpr int kFxThreads = 512;
@@ -497,6 +499,21 @@ fx_final_kernel(const float* __restrict__ params, float* __restrict__ y, const d
 
 using namespace mst;
 
+namespace mst {
+int fx2_chain_forward(const float* x, const float* params, float* y, int B, int L, float sample_rate, int stages, double* stats,
+                      cudaStream_t st);   // fx2.cu
+}
+
+// MST_FX_IMPL=v1 selects the first-generation kernels of this file (kept for A/B timing); default = fx2.cu
+static bool fx_use_v1() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("MST_FX_IMPL");
+    cached = (e && strcmp(e, "v1") == 0) ? 1 : 0;
+  }
+  return cached == 1;
+}
+
 extern "C" {
 
 size_t mst_fx_workspace_bytes(int B, int L) {
@@ -512,6 +529,7 @@ int mst_fx_chain_forward(const float* x, const float* params, float* y, int B, i
   MST_CHECK(sample_rate > 0.f, "fx_chain_forward: bad sample rate");
   cudaStream_t st = (cudaStream_t)stream;
   double* stats = reinterpret_cast<double*>(workspace);
+  if (!fx_use_v1()) return fx2_chain_forward(x, params, y, B, L, sample_rate, stages, stats, st);
   const int rms = (stages & MST_FX_RMSNORM) ? 1 : 0;
   fx_eq_kernel<<<2 * B, kFxHalf, 0, st>>>(x, params, y, stats, L, sample_rate, (stages & MST_FX_EQ) ? 1 : 0);
   if (launch_ok("fx_eq_kernel")) return 1;

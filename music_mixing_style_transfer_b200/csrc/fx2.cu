@@ -1,0 +1,763 @@
+// fx2.cu -- second-generation FX chain kernels (parametric EQ -> compressor -> mid/side imager -> gain) for sm_100a.
+//
+// Replaces the same reference code as fx.cu (paths relative to /root/reference/mixing_style_transfer/mixing_manipulator/):
+//   AugmentationChain.__call__ / apply_processor   common_audioeffects.py:156-192, 115-148 (RMS re-normalisation :142-145)
+//   Equaliser.process                               :501-525 (filters :438-462)
+//   compressor_process / Compressor.process         :529-587, :624-652
+//   MidSideImager.process                           :965-992
+//   Gain.process                                    :1038-1051
+//
+// Why a second generation: ncu on fx.cu (profiles/r01_fx_v1_ncu.md) shows 124 thread-instructions per sample in each of
+// the EQ and compressor kernels, 22-25 % of the warp slots occupied and 0.7 eligible warps per scheduler cycle -- both
+// kernels are instruction- and latency-bound at ~1 TB/s.  This file keeps the time-parallel algorithms (chunked
+// recurrences + block scans, compressor pattern fixed point) and changes the arithmetic and the geometry:
+//   * One CTA (256 threads) per SEGMENT; a thread owns the SAME frames of both channels and works on (L, R) pairs with
+//     packed fma.rn.f32x2 (FFMA2: measured 1.46x the FMA rate of scalar FFMA on B200, tools/ubench/fp_pipes.cu) -- the two
+//     channels share every coefficient, and the compressor's cross-channel sum L*R becomes thread-local.
+//   * EQ biquads run in the state coordinates (u, beta) = (s1, s1 + s2) of the DF-II-transposed states:
+//         y = b0 x + u;   u' = -(1 + a1) y + (b0 + b1) x + beta;   beta' = beta + (b0+b1+b2) x - (1+a1+a2) y
+//     which is algebraically the same filter (5 FMAs per sample) but keeps the ill-conditioned "slope" direction of a
+//     low-frequency section (poles near z = 1) in its own small-magnitude state, so plain float32 is accurate to
+//     ~1e-7 RMS even for a 30 Hz shelf (numpy emulation + tests) -- no float64 in the per-sample work at all.
+//     Only the per-chunk end states, their scan and the tile carry are float64.
+//   * Every thread runs TWO independent 16-frame chunks (ILP 2) -> 32 frames x 2 channels per thread, 8192-frame tiles,
+//     so the scan and the five block barriers are amortised over 4x more samples per thread than in fx.cu.
+//   * Compressor: gain computer on MUFU lg2 (x_l = max(0, (x_g - T)(1 - 1/R)) in one FMA + max), smoother step
+//     y' = max(y + c_att (x - y), y + c_rel (x - y)) (the attack/release choice is the max of two affine maps), float32
+//     maps and scans (all-float32 smoothing is within 1e-6 relative of the float64 reference), exp2 on MUFU.
+//   * Global memory is touched only by fully coalesced 16-byte accesses: tiles are transposed through a padded,
+//     warp-private shared-memory staging buffer (conflict-free LDS.128 on both sides).
+//   * The final pass is a 2x2 matrix per frame whose coefficients are produced once per segment by the compressor CTA.
+//
+// Layout: x, y fp32 [B][2][L]; params fp32 [B][20]; stats double [B][16] (workspace).
+#include "common.cuh"
+
+namespace mst {
+namespace fx2 {
+
+typedef unsigned long long u64;
+
+constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+constexpr int kChunk = 16;                    // frames per recurrence chunk
+constexpr int kEqLane = 32;                   // frames per thread per tile in the EQ kernel (two chunks)
+constexpr int kEqTile = kThreads * kEqLane;   // 8192 frames
+constexpr int kEqRow = kEqLane + 4;           // padded staging row (floats): 36 -> lanes 0..7 start in distinct 4-bank groups
+constexpr int kCpLane = 16;                   // frames per thread per tile in the compressor kernel
+constexpr int kCpTile = kThreads * kCpLane;   // 4096 frames
+constexpr int kCpRow = kCpLane + 4;           // 20
+constexpr int kFxStats = 16;
+
+// stats slots (doubles per segment); 10..13 = final-pass matrix (out_L = m0 l + m1 r, out_R = m2 l + m3 r)
+enum { S_X2_0 = 0, S_X2_1, S_Y1_0, S_Y1_1, S_U2_0, S_U2_1, S_Y2_0, S_Y2_1, S_LR, S_ROUNDS, S_M0, S_M1, S_M2, S_M3 };
+
+// ---- packed float32 x 2 helpers (lo = left channel, hi = right channel) ----
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float lo_of(u64 v) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return a;
+}
+__device__ __forceinline__ float hi_of(u64 v) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return b;
+}
+__device__ __forceinline__ u64 dup(float v) { return pk(v, v); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// n = d > 0 ? a : r;  mask |= d > 0 ? bit : 0   (FSETP + FSEL + predicated LOP3)
+__device__ __forceinline__ void step_select(float& n, unsigned& mask, float d, float a, float r, unsigned bit) {
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %2, 0f00000000;\n\tselp.f32 %0, %3, %4, p;\n\t@p or.b32 %1, %1, %5;\n\t}"
+      : "=f"(n), "+r"(mask)
+      : "f"(d), "f"(a), "f"(r), "r"(bit));
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct Biquad { double b0, b1, b2, a1, a2; };
+
+__device__ Biquad rbj(double G, double Q, double fc, double rate, int type) {  // 0 low shelf, 1 peaking, 2 high shelf
+  const double A = pow(10.0, G / 40.0);
+  const double w0 = 2.0 * 3.14159265358979323846 * (fc / rate);
+  const double alpha = sin(w0) / (2.0 * Q), c = cos(w0), s = 2.0 * sqrt(A) * alpha;
+  double b0, b1, b2, a0, a1, a2;
+  if (type == 1) {
+    b0 = 1.0 + alpha * A; b1 = -2.0 * c; b2 = 1.0 - alpha * A;
+    a0 = 1.0 + alpha / A; a1 = -2.0 * c; a2 = 1.0 - alpha / A;
+  } else if (type == 0) {
+    b0 = A * ((A + 1) - (A - 1) * c + s); b1 = 2 * A * ((A - 1) - (A + 1) * c); b2 = A * ((A + 1) - (A - 1) * c - s);
+    a0 = (A + 1) + (A - 1) * c + s; a1 = -2 * ((A - 1) + (A + 1) * c); a2 = (A + 1) + (A - 1) * c - s;
+  } else {
+    b0 = A * ((A + 1) + (A - 1) * c + s); b1 = -2 * A * ((A - 1) + (A + 1) * c); b2 = A * ((A + 1) + (A - 1) * c - s);
+    a0 = (A + 1) - (A - 1) * c + s; a1 = 2 * ((A - 1) - (A + 1) * c); a2 = (A + 1) - (A - 1) * c - s;
+  }
+  Biquad q;
+  q.b0 = b0 / a0; q.b1 = b1 / a0; q.b2 = b2 / a0; q.a1 = a1 / a0; q.a2 = a2 / a0;
+  return q;
+}
+
+// =====================================================================================================================
+// Tile staging: a warp moves NF frames per lane (32 * NF consecutive frames per channel) between global memory and
+// registers through its private shared-memory buffer stg[2][32 * ROW] (ROW = NF + 4 floats).
+//   global side : 16-byte accesses, lane l of access i covers frames 4 * (32 i + l) .. +3  -> 512 contiguous bytes
+//   register side: lane l owns frames NF * l .. NF * l + NF - 1 (row l of the buffer)
+// Frame f lives at stg[ch][(f / NF) * ROW + f % NF].  `fast` = whole tile inside the row and 16-byte aligned; otherwise
+// a scalar, bounds-checked path zero-fills / skips frames >= L.
+// =====================================================================================================================
+template <int NF, int ROW>
+__device__ __forceinline__ void stage_in(const float* __restrict__ g0, const float* __restrict__ g1, int wf0, int L, bool fast,
+                                         float* stg, int lane) {
+  constexpr int N4 = NF / 4;   // 16-byte accesses per lane per channel
+  if (fast) {
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const float* g = (ch == 0 ? g0 : g1) + wf0;
+      float4 q[N4];
+#pragma unroll
+      for (int i = 0; i < N4; ++i) q[i] = __ldg(reinterpret_cast<const float4*>(g) + 32 * i + lane);
+#pragma unroll
+      for (int i = 0; i < N4; ++i) {
+        const int f = 4 * (32 * i + lane);
+        *reinterpret_cast<float4*>(stg + ch * 32 * ROW + (f / NF) * ROW + (f % NF)) = q[i];
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      const float* g = (ch == 0 ? g0 : g1);
+#pragma unroll 4
+      for (int j = 0; j < NF; ++j) {
+        const int f = 32 * j + lane;
+        stg[ch * 32 * ROW + (f / NF) * ROW + (f % NF)] = (wf0 + f < L) ? __ldg(g + wf0 + f) : 0.f;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int NF, int ROW>
+__device__ __forceinline__ void stage_out(float* __restrict__ g0, float* __restrict__ g1, int wf0, int L, bool fast,
+                                          const float* stg, int lane) {
+  constexpr int N4 = NF / 4;
+  __syncwarp();
+  if (fast) {
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      float* g = (ch == 0 ? g0 : g1) + wf0;
+#pragma unroll
+      for (int i = 0; i < N4; ++i) {
+        const int f = 4 * (32 * i + lane);
+        const float4 q = *reinterpret_cast<const float4*>(stg + ch * 32 * ROW + (f / NF) * ROW + (f % NF));
+        reinterpret_cast<float4*>(g)[32 * i + lane] = q;
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      float* g = (ch == 0 ? g0 : g1);
+#pragma unroll 4
+      for (int j = 0; j < NF; ++j) {
+        const int f = 32 * j + lane;
+        if (wf0 + f < L) g[wf0 + f] = stg[ch * 32 * ROW + (f / NF) * ROW + (f % NF)];
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// =====================================================================================================================
+// pass A: EQ (5 cascaded biquads), x -> y, per-channel sums of x^2 and y^2
+// =====================================================================================================================
+struct EqShared {
+  double mpow[5][33][4];      // (32-frame lane transition)^l, l = 0..32, row-major 2x2, (u, beta) coordinates
+  double m16[5][4];           // 16-frame chunk transition
+  float4 nat[5][kChunk];      // natural response of y to unit (u, beta): (Nu, Nu, Nb, Nb)
+  float2 cf[5][5];            // duplicated coefficient pairs: b0, B = b0+b1+b2, -delta = -(1+a1+a2), cy = -(1+a1), cx = b0+b1
+  double carry[2][5][2][2];   // [tile parity][biquad][channel][u, beta]: state entering the tile
+  double wtot[2][5][kWarps][2][2];   // [tile parity][biquad][warp][channel][u, beta]: warp totals of the scan
+  double red[kWarps][4];
+};
+
+__device__ __forceinline__ void mat_apply(const double* M, double x0, double x1, double& y0, double& y1) {
+  y0 = fma(M[0], x0, M[1] * x1);
+  y1 = fma(M[2], x0, M[3] * x1);
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+eq_kernel(const float* __restrict__ x, const float* __restrict__ params, float* __restrict__ y, double* __restrict__ stats,
+          int L, float sample_rate, int enable, int vec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EqShared& sh = *reinterpret_cast<EqShared*>(smem_raw);
+  float* stg_all = reinterpret_cast<float*>(smem_raw + ((sizeof(EqShared) + 15) / 16) * 16);
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float* stg = stg_all + wid * (2 * 32 * kEqRow);
+  const float* p = params + (size_t)b * MST_FX_NPARAMS;
+
+  if (tid < 5) {
+    // dict order low_shelf, first, second, third, high_shelf (:391); shelves Q = 0.707 (:454)
+    const int gi[5] = {0, 2, 5, 8, 11}, fi[5] = {1, 3, 6, 9, 12}, qi[5] = {-1, 4, 7, 10, -1}, ty[5] = {0, 1, 1, 1, 2};
+    const double Q = qi[tid] < 0 ? 0.707 : (double)p[qi[tid]];
+    const Biquad q = rbj((double)p[gi[tid]], Q, (double)p[fi[tid]], (double)sample_rate, ty[tid]);
+    const double Bc = q.b0 + q.b1 + q.b2, dl = 1.0 + q.a1 + q.a2, cy = -(1.0 + q.a1), cx = q.b0 + q.b1;
+    sh.cf[tid][0] = make_float2((float)q.b0, (float)q.b0);
+    sh.cf[tid][1] = make_float2((float)Bc, (float)Bc);
+    sh.cf[tid][2] = make_float2((float)-dl, (float)-dl);
+    sh.cf[tid][3] = make_float2((float)cy, (float)cy);
+    sh.cf[tid][4] = make_float2((float)cx, (float)cx);
+    // natural response and 16-frame transition from the two unit states (float64)
+    double M[4];
+    for (int s = 0; s < 2; ++s) {
+      double u = s == 0 ? 1.0 : 0.0, be = s == 0 ? 0.0 : 1.0;
+      for (int i = 0; i < kChunk; ++i) {
+        const double yy = u;
+        if (s == 0) { sh.nat[tid][i].x = (float)yy; sh.nat[tid][i].y = (float)yy; }
+        else        { sh.nat[tid][i].z = (float)yy; sh.nat[tid][i].w = (float)yy; }
+        const double un = fma(cy, yy, be);
+        be = fma(-dl, yy, be);
+        u = un;
+      }
+      M[0 + s] = u;   // column s of the transition
+      M[2 + s] = be;
+    }
+    for (int e = 0; e < 4; ++e) sh.m16[tid][e] = M[e];
+    // lane transition = M16^2, and its powers 0..32
+    double M32[4];
+    M32[0] = M[0] * M[0] + M[1] * M[2]; M32[1] = M[0] * M[1] + M[1] * M[3];
+    M32[2] = M[2] * M[0] + M[3] * M[2]; M32[3] = M[2] * M[1] + M[3] * M[3];
+    double P[4] = {1.0, 0.0, 0.0, 1.0};
+    for (int l = 0; l <= 32; ++l) {
+      for (int e = 0; e < 4; ++e) sh.mpow[tid][l][e] = P[e];
+      const double n0 = M32[0] * P[0] + M32[1] * P[2], n1 = M32[0] * P[1] + M32[1] * P[3];
+      const double n2 = M32[2] * P[0] + M32[3] * P[2], n3 = M32[2] * P[1] + M32[3] * P[3];
+      P[0] = n0; P[1] = n1; P[2] = n2; P[3] = n3;
+    }
+    for (int ch = 0; ch < 2; ++ch) { sh.carry[0][tid][ch][0] = 0.0; sh.carry[0][tid][ch][1] = 0.0; }  // state reset (:512)
+  }
+  __syncthreads();
+
+  const float* x0 = x + ((size_t)b * 2) * L;
+  const float* x1 = x0 + L;
+  float* y0 = y + ((size_t)b * 2) * L;
+  float* y1 = y0 + L;
+  double sum_x2[2] = {0.0, 0.0}, sum_y2[2] = {0.0, 0.0};
+  int par = 0;
+
+#pragma unroll 1
+  for (int tile0 = 0; tile0 < L; tile0 += kEqTile, par ^= 1) {
+    const int wf0 = tile0 + wid * (32 * kEqLane);          // first frame of this warp
+    const bool fast = vec && (tile0 + kEqTile <= L);
+    stage_in<kEqLane, kEqRow>(x0, x1, wf0, L, fast, stg, lane);
+    u64 v[2][kChunk];                                      // [chunk][i] = (L, R)
+    {
+      const float* r0 = stg + lane * kEqRow;
+      const float* r1 = stg + 32 * kEqRow + lane * kEqRow;
+#pragma unroll
+      for (int i = 0; i < kEqLane / 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(r0 + 4 * i);
+        const float4 c = *reinterpret_cast<const float4*>(r1 + 4 * i);
+        const int cc = (4 * i) / kChunk, ii = (4 * i) % kChunk;
+        v[cc][ii] = pk(a.x, c.x); v[cc][ii + 1] = pk(a.y, c.y); v[cc][ii + 2] = pk(a.z, c.z); v[cc][ii + 3] = pk(a.w, c.w);
+      }
+    }
+    {
+      u64 sx = 0ull;
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) sx = fma2(v[c][i], v[c][i], sx);
+      sum_x2[0] += (double)lo_of(sx);
+      sum_x2[1] += (double)hi_of(sx);
+    }
+    if (enable) {
+#pragma unroll 1
+      for (int k = 0; k < 5; ++k) {
+        // (1) zero-state response of both chunks, packed over the channels (float32, 5 FMAs per frame and chunk)
+        u64 uA = 0ull, bA = 0ull, uB = 0ull, bB = 0ull;
+        {
+          const u64 c_b0 = *reinterpret_cast<const u64*>(&sh.cf[k][0]);
+          const u64 c_B = *reinterpret_cast<const u64*>(&sh.cf[k][1]);
+          const u64 c_nd = *reinterpret_cast<const u64*>(&sh.cf[k][2]);
+          const u64 c_cy = *reinterpret_cast<const u64*>(&sh.cf[k][3]);
+          const u64 c_cx = *reinterpret_cast<const u64*>(&sh.cf[k][4]);
+#pragma unroll
+          for (int i = 0; i < kChunk; ++i) {
+            const u64 xa = v[0][i], xb = v[1][i];
+            const u64 ya = fma2(c_b0, xa, uA), yb = fma2(c_b0, xb, uB);
+            const u64 tba = fma2(c_B, xa, bA), tbb = fma2(c_B, xb, bB);
+            const u64 tua = fma2(c_cx, xa, bA), tub = fma2(c_cx, xb, bB);
+            bA = fma2(c_nd, ya, tba); bB = fma2(c_nd, yb, tbb);
+            uA = fma2(c_cy, ya, tua); uB = fma2(c_cy, yb, tub);
+            v[0][i] = ya; v[1][i] = yb;
+          }
+        }
+        // (2) per channel: lane total Z = M16 zA + zB, inclusive warp scan I_l = sum_{i<=l} M32^(l-i) Z_i   (float64)
+        double zA[2][2], zB[2][2], I[2][2], E[2][2];
+        zA[0][0] = (double)lo_of(uA); zA[0][1] = (double)lo_of(bA); zA[1][0] = (double)hi_of(uA); zA[1][1] = (double)hi_of(bA);
+        zB[0][0] = (double)lo_of(uB); zB[0][1] = (double)lo_of(bB); zB[1][0] = (double)hi_of(uB); zB[1][1] = (double)hi_of(bB);
+        const double* M16 = sh.m16[k];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          double t0, t1;
+          mat_apply(M16, zA[ch][0], zA[ch][1], t0, t1);
+          I[ch][0] = t0 + zB[ch][0];
+          I[ch][1] = t1 + zB[ch][1];
+        }
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+          const int off = 1 << st;
+          const double* Mp = sh.mpow[k][off];
+          const double m0 = Mp[0], m1 = Mp[1], m2 = Mp[2], m3 = Mp[3];
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            const double o0 = __shfl_up_sync(0xffffffffu, I[ch][0], off), o1 = __shfl_up_sync(0xffffffffu, I[ch][1], off);
+            if (lane >= off) {
+              I[ch][0] = fma(m0, o0, fma(m1, o1, I[ch][0]));
+              I[ch][1] = fma(m2, o0, fma(m3, o1, I[ch][1]));
+            }
+          }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          if (lane == 31) { sh.wtot[par][k][wid][ch][0] = I[ch][0]; sh.wtot[par][k][wid][ch][1] = I[ch][1]; }
+          E[ch][0] = __shfl_up_sync(0xffffffffu, I[ch][0], 1);
+          E[ch][1] = __shfl_up_sync(0xffffffffu, I[ch][1], 1);
+          if (lane == 0) { E[ch][0] = 0.0; E[ch][1] = 0.0; }
+        }
+        __syncthreads();
+        // (3) state entering this lane: Q_0 = carry, Q_{w+1} = M32^32 Q_w + W_w;  in_A = M32^lane Q_w + E;  in_B = M16 in_A + zA
+        const double* M1024 = sh.mpow[k][32];
+        const double* Ml = sh.mpow[k][lane];
+        u64 inUA, inBA, inUB, inBB;
+        {
+          float fa[2][2], fb[2][2];
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            double q0 = sh.carry[par][k][ch][0], q1 = sh.carry[par][k][ch][1];
+            for (int w = 0; w < wid; ++w) {
+              double n0, n1;
+              mat_apply(M1024, q0, q1, n0, n1);
+              q0 = n0 + sh.wtot[par][k][w][ch][0];
+              q1 = n1 + sh.wtot[par][k][w][ch][1];
+            }
+            double a0, a1, b0, b1;
+            mat_apply(Ml, q0, q1, a0, a1);
+            a0 += E[ch][0]; a1 += E[ch][1];
+            mat_apply(M16, a0, a1, b0, b1);
+            b0 += zA[ch][0]; b1 += zA[ch][1];
+            fa[ch][0] = (float)a0; fa[ch][1] = (float)a1; fb[ch][0] = (float)b0; fb[ch][1] = (float)b1;
+            if (tid == kThreads - 1) {   // state leaving the tile = M16 in_B + zB; read by the NEXT tile (other parity)
+              double c0, c1;
+              mat_apply(M16, b0, b1, c0, c1);
+              sh.carry[par ^ 1][k][ch][0] = c0 + zB[ch][0];
+              sh.carry[par ^ 1][k][ch][1] = c1 + zB[ch][1];
+            }
+          }
+          inUA = pk(fa[0][0], fa[1][0]); inBA = pk(fa[0][1], fa[1][1]);
+          inUB = pk(fb[0][0], fb[1][0]); inBB = pk(fb[0][1], fb[1][1]);
+        }
+        // (4) add the natural response to the true incoming state
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) {
+          const float4 n = sh.nat[k][i];
+          const u64 nu = pk(n.x, n.y), nb = pk(n.z, n.w);
+          v[0][i] = fma2(nu, inUA, fma2(nb, inBA, v[0][i]));
+          v[1][i] = fma2(nu, inUB, fma2(nb, inBB, v[1][i]));
+        }
+      }
+    }
+    // sums of y^2 (frames >= L excluded: the filters ring into the zero padding of a partial tile) and store
+    {
+      const int f0 = wf0 + lane * kEqLane;
+      u64 sy = 0ull;
+      if (fast || f0 + kEqLane <= L) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < kChunk; ++i) sy = fma2(v[c][i], v[c][i], sy);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < kChunk; ++i)
+            if (f0 + c * kChunk + i < L) sy = fma2(v[c][i], v[c][i], sy);
+      }
+      sum_y2[0] += (double)lo_of(sy);
+      sum_y2[1] += (double)hi_of(sy);
+      float* r0 = stg + lane * kEqRow;
+      float* r1 = stg + 32 * kEqRow + lane * kEqRow;
+#pragma unroll
+      for (int i = 0; i < kEqLane / 4; ++i) {
+        const int cc = (4 * i) / kChunk, ii = (4 * i) % kChunk;
+        *reinterpret_cast<float4*>(r0 + 4 * i) = make_float4(lo_of(v[cc][ii]), lo_of(v[cc][ii + 1]), lo_of(v[cc][ii + 2]), lo_of(v[cc][ii + 3]));
+        *reinterpret_cast<float4*>(r1 + 4 * i) = make_float4(hi_of(v[cc][ii]), hi_of(v[cc][ii + 1]), hi_of(v[cc][ii + 2]), hi_of(v[cc][ii + 3]));
+      }
+    }
+    stage_out<kEqLane, kEqRow>(y0, y1, wf0, L, fast, stg, lane);
+  }
+
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) { sum_x2[ch] = warp_sum(sum_x2[ch]); sum_y2[ch] = warp_sum(sum_y2[ch]); }
+  __syncthreads();
+  if (lane == 0) { sh.red[wid][0] = sum_x2[0]; sh.red[wid][1] = sum_x2[1]; sh.red[wid][2] = sum_y2[0]; sh.red[wid][3] = sum_y2[1]; }
+  __syncthreads();
+  if (tid < 4) {
+    double a = 0.0;
+    for (int w = 0; w < kWarps; ++w) a += sh.red[w][tid];
+    const int slot[4] = {S_X2_0, S_X2_1, S_Y1_0, S_Y1_1};
+    stats[(size_t)b * kFxStats + slot[tid]] = a;
+  }
+}
+
+// =====================================================================================================================
+// pass B: compressor, in place on y; per-channel sums, sum L*R, and the final-pass matrix of the segment
+// =====================================================================================================================
+struct CompShared {
+  float wa[2][2][kWarps], wb[2][2][kWarps];   // [round parity][channel][warp]: warp-total affine maps
+  float cend[2][2];                           // [round parity][channel]: smoother state leaving the tile (thread 255)
+  float pa[kChunk + 1], pr[kChunk + 1];       // alpha_att^k, alpha_rel^k
+  double red[kWarps][5];
+};
+
+__device__ void final_matrix(const float* p, double* st, int L, int stages);
+
+__global__ void __launch_bounds__(kThreads, 2)
+comp_kernel(const float* __restrict__ params, float* __restrict__ y, double* __restrict__ stats, int L, float sample_rate,
+            int stages, int vec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CompShared& sh = *reinterpret_cast<CompShared*>(smem_raw);
+  float* stg_all = reinterpret_cast<float*>(smem_raw + ((sizeof(CompShared) + 15) / 16) * 16);
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float* stg = stg_all + wid * (2 * 32 * kCpRow);
+  const float* p = params + (size_t)b * MST_FX_NPARAMS;
+  double* st = stats + (size_t)b * kFxStats;
+  const bool enable = (stages & MST_FX_COMP) != 0;
+  const bool rms_in = (stages & MST_FX_RMSNORM) && (stages & MST_FX_EQ);
+
+  // RMS re-normalisation of the EQ stage (common_audioeffects.py:142-145), float32 like numpy's `y *= scale`
+  float scale1 = 1.f;
+  if (rms_in) {
+    const double n = 2.0 * (double)L;
+    const double mx = (st[S_X2_0] + st[S_X2_1]) / n, my = (st[S_Y1_0] + st[S_Y1_1]) / n;
+    scale1 = (float)sqrt(mx / fmax(1e-7, my));
+  }
+  const double thr_d = (double)p[13], att_ms = (double)p[14], rel_ms = (double)p[15], ratio_d = (double)p[16];
+  const double a_att_d = exp(-1.0 / (0.001 * (double)sample_rate * att_ms));   // :555
+  const double a_rel_d = exp(-1.0 / (0.001 * (double)sample_rate * rel_ms));   // :556
+  const bool active = enable && !(thr_d == 0.0 && ratio_d == 1.0);              // :635
+  // static curve (:564-573) folded into x_l = x_g - y_g:
+  //   ratio > 1: x_l = max(0, (x_g - T)(1 - 1/R));  ratio < 1: x_l = min(0, (x_g - T)(1 - R));  ratio == 1: x_l = x_g
+  //   i.e. x_l = clamp(x_g * cs + co, c_lo, c_hi) with the bounds below (branch-free in the sample loop)
+  float cs, co, c_lo, c_hi;
+  const float kInf = __int_as_float(0x7f800000);
+  if (ratio_d > 1.0)      { cs = (float)(1.0 - 1.0 / ratio_d); co = (float)(-thr_d * (1.0 - 1.0 / ratio_d)); c_lo = 0.f; c_hi = kInf; }
+  else if (ratio_d < 1.0) { cs = (float)(1.0 - ratio_d);       co = (float)(-thr_d * (1.0 - ratio_d));       c_lo = -kInf; c_hi = 0.f; }
+  else                    { cs = 1.f; co = 0.f; c_lo = -kInf; c_hi = kInf; }
+  const u64 c_att2 = dup((float)(1.0 - a_att_d)), c_rel2 = dup((float)(1.0 - a_rel_d)), m_one2 = dup(-1.f);
+  const u64 scale1_2 = dup(scale1);
+
+  if (tid == 0) {
+    double pa = 1.0, pr = 1.0;
+    for (int k = 0; k <= kChunk; ++k) { sh.pa[k] = (float)pa; sh.pr[k] = (float)pr; pa *= a_att_d; pr *= a_rel_d; }
+  }
+  __syncthreads();
+
+  float* y0 = y + ((size_t)b * 2) * L;
+  float* y1 = y0 + L;
+  double sum_u2[2] = {0.0, 0.0}, sum_y2[2] = {0.0, 0.0}, sum_lr = 0.0;
+  int rpar = 0;
+  unsigned rounds_local = 0;
+  float tile_in[2] = {0.f, 0.f};        // smoother state entering the tile; yL_prev = 0 at every call (:553)
+
+#pragma unroll 1
+  for (int tile0 = 0; tile0 < L; tile0 += kCpTile) {
+    const int wf0 = tile0 + wid * (32 * kCpLane);
+    const bool fast = vec && (tile0 + kCpTile <= L);
+    stage_in<kCpLane, kCpRow>(y0, y1, wf0, L, fast, stg, lane);
+    float* r0 = stg + lane * kCpRow;
+    float* r1 = stg + 32 * kCpRow + lane * kCpRow;
+    u64 w[kChunk];   // x_l (dB over the static curve) while the smoother runs, then the output
+    {
+      u64 su = 0ull;
+#pragma unroll
+      for (int i = 0; i < kCpLane / 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(r0 + 4 * i);
+        const float4 c = *reinterpret_cast<const float4*>(r1 + 4 * i);
+        w[4 * i] = mul2(pk(a.x, c.x), scale1_2); w[4 * i + 1] = mul2(pk(a.y, c.y), scale1_2);
+        w[4 * i + 2] = mul2(pk(a.z, c.z), scale1_2); w[4 * i + 3] = mul2(pk(a.w, c.w), scale1_2);
+      }
+#pragma unroll
+      for (int i = 0; i < kChunk; ++i) su = fma2(w[i], w[i], su);
+      sum_u2[0] += (double)lo_of(su);
+      sum_u2[1] += (double)hi_of(su);
+    }
+    if (active) {
+      // gain computer (:559-575): x_g = 20 log10 |u| (-120 below 1e-6), static curve, x_l = x_g - y_g      (float32)
+#pragma unroll
+      for (int i = 0; i < kChunk; ++i) {
+        float xl[2];
+        xl[0] = lo_of(w[i]); xl[1] = hi_of(w[i]);
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const float xg = 6.0205999132796239f * lg2_approx(fmaxf(fabsf(xl[ch]), 0.000001f));
+          xl[ch] = fminf(fmaxf(fmaf(xg, cs, co), c_lo), c_hi);
+        }
+        w[i] = pk(xl[0], xl[1]);
+      }
+      // smoother (:577-583): attack/release pattern fixed-point iteration + affine block scan (float32)
+      u64 yl[kChunk];
+      float g_in[2] = {tile_in[0], tile_in[1]};
+      unsigned prev_mask[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};   // impossible 16-bit pattern -> first round always "changed"
+      float y_end[2] = {0.f, 0.f};
+      int round = 0;
+#pragma unroll 1
+      while (true) {
+        u64 yy = pk(g_in[0], g_in[1]);
+        unsigned mask[2] = {0u, 0u};
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) {
+          const u64 d = fma2(yy, m_one2, w[i]);            // x_l - y
+          const u64 ya = fma2(c_att2, d, yy), yr = fma2(c_rel2, d, yy);
+          float n0, n1;                                   // attack <=> x_l > y (:578): select + pattern bit
+          step_select(n0, mask[0], lo_of(d), lo_of(ya), lo_of(yr), 1u << i);
+          step_select(n1, mask[1], hi_of(d), hi_of(ya), hi_of(yr), 1u << i);
+          yy = pk(n0, n1);
+          yl[i] = yy;
+        }
+        y_end[0] = lo_of(yy); y_end[1] = hi_of(yy);
+        int changed = 0;
+        float sa[2], sb[2], ea[2], eb[2];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int na = __popc(mask[ch]);
+          sa[ch] = sh.pa[na] * sh.pr[kChunk - na];         // chunk map under this pattern: y_out = A y_in + B
+          sb[ch] = fmaf(-sa[ch], g_in[ch], y_end[ch]);
+          changed |= (mask[ch] != prev_mask[ch]);
+          prev_mask[ch] = mask[ch];
+        }
+        // inclusive affine scan over the warp: (A,B)_l <- map_l o ... o map_0
+#pragma unroll
+        for (int stp = 0; stp < 5; ++stp) {
+          const int off = 1 << stp;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            const float oa = __shfl_up_sync(0xffffffffu, sa[ch], off), ob = __shfl_up_sync(0xffffffffu, sb[ch], off);
+            if (lane >= off) { sb[ch] = fmaf(sa[ch], ob, sb[ch]); sa[ch] = sa[ch] * oa; }
+          }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          if (lane == 31) { sh.wa[rpar][ch][wid] = sa[ch]; sh.wb[rpar][ch][wid] = sb[ch]; }
+          if (tid == kThreads - 1) sh.cend[rpar][ch] = y_end[ch];
+          ea[ch] = __shfl_up_sync(0xffffffffu, sa[ch], 1);
+          eb[ch] = __shfl_up_sync(0xffffffffu, sb[ch], 1);
+          if (lane == 0) { ea[ch] = 1.f; eb[ch] = 0.f; }
+        }
+        const int any = __syncthreads_or(changed);
+        ++rounds_local;
+        ++round;
+        if (!any || round >= kThreads + 2) {   // pattern reproduced itself -> yl[] is the sequential solution
+          tile_in[0] = sh.cend[rpar][0];       // state leaving this tile = state entering the next one
+          tile_in[1] = sh.cend[rpar][1];
+          rpar ^= 1;                           // the next tile's first round must not overwrite what is being read here
+          break;
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          float qv = tile_in[ch];   // state entering this warp
+          for (int ww = 0; ww < wid; ++ww) qv = fmaf(sh.wa[rpar][ch][ww], qv, sh.wb[rpar][ch][ww]);
+          g_in[ch] = fmaf(ea[ch], qv, eb[ch]);   // state entering this thread's chunk under the current pattern
+        }
+        rpar ^= 1;
+      }
+      // gain: c = 10^((0 - y_l)/20), makeup 0 (:582, :646);  y = u * c (:585, :638).  u is re-read from the staging rows.
+#pragma unroll
+      for (int i = 0; i < kCpLane / 4; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(r0 + 4 * i);
+        const float4 c = *reinterpret_cast<const float4*>(r1 + 4 * i);
+        const float ua[4] = {a.x, a.y, a.z, a.w}, uc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float g0 = ex2_approx(lo_of(yl[4 * i + j]) * -0.16609640474436813f);
+          const float g1 = ex2_approx(hi_of(yl[4 * i + j]) * -0.16609640474436813f);
+          w[4 * i + j] = mul2(mul2(pk(ua[j], uc[j]), scale1_2), pk(g0, g1));
+        }
+      }
+    }
+    // sums for the compressor RMS factor and the imager energies; frames >= L hold u = 0 -> out = 0
+    {
+      u64 sy = 0ull;
+      float slr = 0.f;
+#pragma unroll
+      for (int i = 0; i < kChunk; ++i) {
+        sy = fma2(w[i], w[i], sy);
+        slr = fmaf(lo_of(w[i]), hi_of(w[i]), slr);
+      }
+      sum_y2[0] += (double)lo_of(sy);
+      sum_y2[1] += (double)hi_of(sy);
+      sum_lr += (double)slr;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kCpLane / 4; ++i) {
+      *reinterpret_cast<float4*>(r0 + 4 * i) = make_float4(lo_of(w[4 * i]), lo_of(w[4 * i + 1]), lo_of(w[4 * i + 2]), lo_of(w[4 * i + 3]));
+      *reinterpret_cast<float4*>(r1 + 4 * i) = make_float4(hi_of(w[4 * i]), hi_of(w[4 * i + 1]), hi_of(w[4 * i + 2]), hi_of(w[4 * i + 3]));
+    }
+    stage_out<kCpLane, kCpRow>(y0, y1, wf0, L, fast, stg, lane);
+  }
+
+  double r5[5] = {sum_u2[0], sum_u2[1], sum_y2[0], sum_y2[1], sum_lr};
+#pragma unroll
+  for (int j = 0; j < 5; ++j) r5[j] = warp_sum(r5[j]);
+  __syncthreads();
+  if (lane == 0)
+    for (int j = 0; j < 5; ++j) sh.red[wid][j] = r5[j];
+  __syncthreads();
+  if (tid == 0) {
+    double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int ww = 0; ww < kWarps; ++ww)
+      for (int j = 0; j < 5; ++j) a[j] += sh.red[ww][j];
+    st[S_U2_0] = a[0]; st[S_U2_1] = a[1]; st[S_Y2_0] = a[2]; st[S_Y2_1] = a[3]; st[S_LR] = a[4];
+    st[S_ROUNDS] = (double)rounds_local;
+    final_matrix(p, st, L, stages);
+  }
+}
+
+// compressor RMS factor -> imager gains (+ its RMS factor, analytic) -> gain, folded into one 2x2 matrix per segment
+__device__ void final_matrix(const float* p, double* st, int L, int stages) {
+  const bool rms = stages & MST_FX_RMSNORM;
+  const double n = 2.0 * (double)L;
+  float scale2 = 1.f;
+  if (rms && (stages & MST_FX_COMP)) {
+    const double mu = (st[S_U2_0] + st[S_U2_1]) / n, my = (st[S_Y2_0] + st[S_Y2_1]) / n;
+    scale2 = (float)sqrt(mu / fmax(1e-7, my));
+  }
+  float mg = 1.f, sg = 1.f, scale3 = 1.f;
+  const bool imager = stages & MST_FX_IMAGER;
+  if (imager) {
+    // energies of v = y2*scale2 :  mid = L+R, side = L-R   (:968-971)
+    const double s2 = (double)scale2 * (double)scale2;
+    const double ll = st[S_Y2_0] * s2, rr = st[S_Y2_1] * s2, lr = st[S_LR] * s2;
+    const float mid_e = (float)(ll + rr + 2.0 * lr), side_e = (float)fmax(ll + rr - 2.0 * lr, 0.0);
+    const float total_e = mid_e + side_e;
+    const float max_side = sqrtf(total_e / (side_e + 1e-3f));                 // :973
+    const double bal = rint((double)p[17] * 1000.0) / 1000.0;                  // round(bal, 3) (:975)
+    sg = bal <= 1.0 ? (float)bal : max_side * (float)(bal - 1.0);              // :976
+    const float new_side_e = side_e * (sg * sg);
+    const float left_mid_e = total_e - new_side_e;
+    mg = sqrtf(left_mid_e / (mid_e + 1e-3f));                                  // :981
+    if (rms) {
+      // mean(y3^2) with y3 = ((m' + s')/2, (m' - s')/2):  sum = (mg^2 mid_e + sg^2 side_e) / 2
+      const double in_ms = (ll + rr) / n;
+      const double out_ms = 0.5 * ((double)mg * mg * mid_e + (double)sg * sg * side_e) / n;
+      scale3 = (float)sqrt(in_ms / fmax(1e-7, out_ms));
+    }
+  }
+  double g = 1.0;
+  if (stages & MST_FX_GAIN) {
+    g = (double)(float)pow(10.0, (double)p[18] / 20.0);                        // :1048
+    if (p[19] >= 0.5f) g = -g;                                                 // :1049-1050
+  }
+  // out_L = g scale3 ((vl + vr) mg + (vl - vr) sg) / 2,  out_R = g scale3 ((vl + vr) mg - (vl - vr) sg) / 2,  v = y2 scale2
+  const double k = g * (double)scale3 * (double)scale2;
+  if (imager) {
+    const double a = 0.5 * k * ((double)mg + (double)sg), c = 0.5 * k * ((double)mg - (double)sg);
+    st[S_M0] = a; st[S_M1] = c; st[S_M2] = c; st[S_M3] = a;
+  } else {
+    st[S_M0] = k; st[S_M1] = 0.0; st[S_M2] = 0.0; st[S_M3] = k;
+  }
+}
+
+// =====================================================================================================================
+// pass C: out = M * (l, r) per frame, in place
+// =====================================================================================================================
+constexpr int kFinThreads = 256;
+constexpr int kFinFrames = kFinThreads * 4 * 4;   // frames per CTA: 4 float4 per thread and channel
+
+__global__ void __launch_bounds__(kFinThreads)
+final_kernel(float* __restrict__ y, const double* __restrict__ stats, int L, int vec) {
+  const int b = blockIdx.y;
+  const double* st = stats + (size_t)b * kFxStats;
+  const float m0 = (float)st[S_M0], m1 = (float)st[S_M1], m2 = (float)st[S_M2], m3 = (float)st[S_M3];
+  float* l = y + ((size_t)b * 2) * L;
+  float* r = l + L;
+  const int f0 = blockIdx.x * kFinFrames;
+  if (vec && f0 + kFinFrames <= L) {
+    float4 a[4], c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      a[i] = *(reinterpret_cast<const float4*>(l + f0) + i * kFinThreads + threadIdx.x);
+      c[i] = *(reinterpret_cast<const float4*>(r + f0) + i * kFinThreads + threadIdx.x);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 ol, orr;
+      ol.x = fmaf(m0, a[i].x, m1 * c[i].x); orr.x = fmaf(m2, a[i].x, m3 * c[i].x);
+      ol.y = fmaf(m0, a[i].y, m1 * c[i].y); orr.y = fmaf(m2, a[i].y, m3 * c[i].y);
+      ol.z = fmaf(m0, a[i].z, m1 * c[i].z); orr.z = fmaf(m2, a[i].z, m3 * c[i].z);
+      ol.w = fmaf(m0, a[i].w, m1 * c[i].w); orr.w = fmaf(m2, a[i].w, m3 * c[i].w);
+      *(reinterpret_cast<float4*>(l + f0) + i * kFinThreads + threadIdx.x) = ol;
+      *(reinterpret_cast<float4*>(r + f0) + i * kFinThreads + threadIdx.x) = orr;
+    }
+  } else {
+    const int f1 = f0 + kFinFrames < L ? f0 + kFinFrames : L;
+    for (int t = f0 + threadIdx.x; t < f1; t += kFinThreads) {
+      const float vl = l[t], vr = r[t];
+      l[t] = fmaf(m0, vl, m1 * vr);
+      r[t] = fmaf(m2, vl, m3 * vr);
+    }
+  }
+}
+
+static size_t eq_smem_bytes() { return align_up(sizeof(EqShared), 16) + (size_t)kWarps * 2 * 32 * kEqRow * sizeof(float); }
+static size_t comp_smem_bytes() { return align_up(sizeof(CompShared), 16) + (size_t)kWarps * 2 * 32 * kCpRow * sizeof(float); }
+
+}  // namespace fx2
+
+int fx2_chain_forward(const float* x, const float* params, float* y, int B, int L, float sample_rate, int stages, double* stats,
+                      cudaStream_t st) {
+  using namespace fx2;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  MST_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+    MST_CUDA_OK(cudaFuncSetAttribute(eq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eq_smem_bytes()));
+    MST_CUDA_OK(cudaFuncSetAttribute(comp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)comp_smem_bytes()));
+    attr_done[dev] = true;
+  }
+  const int vec = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) % 16 == 0) ? 1 : 0;
+  eq_kernel<<<B, kThreads, eq_smem_bytes(), st>>>(x, params, y, stats, L, sample_rate, (stages & MST_FX_EQ) ? 1 : 0, vec);
+  if (launch_ok("fx2::eq_kernel")) return 1;
+  comp_kernel<<<B, kThreads, comp_smem_bytes(), st>>>(params, y, stats, L, sample_rate, stages, vec);
+  if (launch_ok("fx2::comp_kernel")) return 1;
+  dim3 grid(cdiv(L, kFinFrames), B);
+  final_kernel<<<grid, kFinThreads, 0, st>>>(y, stats, L, vec);
+  return launch_ok("fx2::final_kernel");
+}
+
+}  // namespace mst
