@@ -32,6 +32,8 @@
 // Layout: x, y fp32 [B][2][L]; params fp32 [B][20]; stats double [B][16] (workspace).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace mst {
 namespace fx2 {
 
@@ -88,11 +90,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// n = d > 0 ? a : r;  mask |= d > 0 ? bit : 0   (FSETP + FSEL + predicated LOP3)
-__device__ __forceinline__ void step_select(float& n, unsigned& mask, float d, float a, float r, unsigned bit) {
-  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %2, 0f00000000;\n\tselp.f32 %0, %3, %4, p;\n\t@p or.b32 %1, %1, %5;\n\t}"
-      : "=f"(n), "+r"(mask)
-      : "f"(d), "f"(a), "f"(r), "r"(bit));
+// 16 smoother steps of one thread (both channels packed):  d = x_l - y;  y' = d > 0 ? y + c_att d : y + c_rel d  (:577-580).
+// The choice is a max of the two candidates when c_att >= c_rel (attack faster than release, the usual case) and a min
+// otherwise -- one FMNMX instead of compare + select.  rel[ch] collects the sign bits of d, newest in bit 0 (funnel
+// shift, one instruction per sample): bit set <=> release step (d < 0; d == 0 leaves y unchanged under either label).
+template <bool kMax>
+__device__ __forceinline__ void smoother_steps(const u64 (&w)[kChunk], u64 (&yl)[kChunk], u64& yy, unsigned (&rel)[2], u64 c_att2,
+                                               u64 c_rel2, u64 m_one2) {
+#pragma unroll
+  for (int i = 0; i < kChunk; ++i) {
+    const u64 d = fma2(yy, m_one2, w[i]);            // x_l - y
+    const u64 ya = fma2(c_att2, d, yy), yr = fma2(c_rel2, d, yy);
+    const float n0 = kMax ? fmaxf(lo_of(ya), lo_of(yr)) : fminf(lo_of(ya), lo_of(yr));
+    const float n1 = kMax ? fmaxf(hi_of(ya), hi_of(yr)) : fminf(hi_of(ya), hi_of(yr));
+    rel[0] = __funnelshift_l(__float_as_uint(lo_of(d)), rel[0], 1);
+    rel[1] = __funnelshift_l(__float_as_uint(hi_of(d)), rel[1], 1);
+    yy = pk(n0, n1);
+    yl[i] = yy;
+  }
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -191,24 +206,53 @@ __device__ __forceinline__ void stage_out(float* __restrict__ g0, float* __restr
   __syncwarp();
 }
 
+// Asynchronous variant of the fast path of stage_in: 16-byte cp.async copies straight into the staging layout (no
+// registers, the data lands while the warp works on the previous tile).  Complete with stage_wait().
+template <int NF, int ROW>
+__device__ __forceinline__ void stage_in_async(const float* __restrict__ g0, const float* __restrict__ g1, int wf0, float* stg,
+                                               int lane) {
+  constexpr int N4 = NF / 4;
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    const float* g = (ch == 0 ? g0 : g1) + wf0;
+#pragma unroll
+    for (int i = 0; i < N4; ++i) {
+      const int f = 4 * (32 * i + lane);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(stg + ch * 32 * ROW + (f / NF) * ROW + (f % NF));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g + f) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+
 // =====================================================================================================================
 // pass A: EQ (5 cascaded biquads), x -> y, per-channel sums of x^2 and y^2
+//
+// Per section and tile: every thread runs its two 16-frame chunks from zero state (packed over the channel pair), the
+// chunk end states are combined by a warp scan + one block barrier + an 8-entry prefix over the warp totals (3-step shuffle
+// scan, identical work in every warp), and the natural response to the true incoming state is added.  All of it is
+// float32: in (u, beta) coordinates the float32 scan + carry is as accurate as the float64 one (numpy emulation of this
+// very schedule: 6.6e-8 .. 2.4e-7 RMS either way, 30 Hz shelf and Q = 0.1 included).
+// Negative result kept out of the code: replacing the barrier by a warp-to-warp hand-over through shared-memory flags
+// (each warp taking its 1024-frame tile through all five sections on its own) measured 614-738 us against 499 us --
+// the spinning lanes eat issue slots and the chain moves at the pace of the slowest warp just like the barrier.
 // =====================================================================================================================
 struct EqShared {
-  double mpow[5][33][4];      // (32-frame lane transition)^l, l = 0..32, row-major 2x2, (u, beta) coordinates
-  double m16[5][4];           // 16-frame chunk transition
-  float4 nat[5][kChunk];      // natural response of y to unit (u, beta): (Nu, Nu, Nb, Nb)
-  float2 cf[5][5];            // duplicated coefficient pairs: b0, B = b0+b1+b2, -delta = -(1+a1+a2), cy = -(1+a1), cx = b0+b1
-  double carry[2][5][2][2];   // [tile parity][biquad][channel][u, beta]: state entering the tile
-  double wtot[2][5][kWarps][2][2];   // [tile parity][biquad][warp][channel][u, beta]: warp totals of the scan
+  float4 mpow[5][33];         // (32-frame lane transition)^l, l = 0..32, row-major 2x2 (m0 m1; m2 m3), (u, beta) coordinates
+  float4 m16[5];              // 16-frame chunk transition
+  float2 nat[5][kChunk];      // natural response of y to unit (u, beta): (Nu, Nb)
+  float cf[5][8];             // b0, B = b0+b1+b2, -delta = -(1+a1+a2), cy = -(1+a1), cx = b0+b1
+  float4 mw[5][kWarps + 1];   // (warp transition = M32^32)^j, j = 0..8
+  float4 wtot[2][5][kWarps];  // [tile parity][biquad][warp]: warp totals (u_L, u_R, beta_L, beta_R)
+  float4 carryb[2][5];        // [tile parity][biquad]: state entering the tile
   double red[kWarps][4];
 };
 
-__device__ __forceinline__ void mat_apply(const double* M, double x0, double x1, double& y0, double& y1) {
-  y0 = fma(M[0], x0, M[1] * x1);
-  y1 = fma(M[2], x0, M[3] * x1);
-}
-
+__device__ __forceinline__ u64 shfl_up2(u64 v, int off) { return __shfl_up_sync(0xffffffffu, v, off); }
 __global__ void __launch_bounds__(kThreads, 2)
 eq_kernel(const float* __restrict__ x, const float* __restrict__ params, float* __restrict__ y, double* __restrict__ stats,
           int L, float sample_rate, int enable, int vec) {
@@ -225,19 +269,19 @@ eq_kernel(const float* __restrict__ x, const float* __restrict__ params, float* 
     const double Q = qi[tid] < 0 ? 0.707 : (double)p[qi[tid]];
     const Biquad q = rbj((double)p[gi[tid]], Q, (double)p[fi[tid]], (double)sample_rate, ty[tid]);
     const double Bc = q.b0 + q.b1 + q.b2, dl = 1.0 + q.a1 + q.a2, cy = -(1.0 + q.a1), cx = q.b0 + q.b1;
-    sh.cf[tid][0] = make_float2((float)q.b0, (float)q.b0);
-    sh.cf[tid][1] = make_float2((float)Bc, (float)Bc);
-    sh.cf[tid][2] = make_float2((float)-dl, (float)-dl);
-    sh.cf[tid][3] = make_float2((float)cy, (float)cy);
-    sh.cf[tid][4] = make_float2((float)cx, (float)cx);
-    // natural response and 16-frame transition from the two unit states (float64)
+    sh.cf[tid][0] = (float)q.b0;
+    sh.cf[tid][1] = (float)Bc;
+    sh.cf[tid][2] = (float)-dl;
+    sh.cf[tid][3] = (float)cy;
+    sh.cf[tid][4] = (float)cx;
+    // natural response and 16-frame transition from the two unit states (float64, stored as float32)
     double M[4];
     for (int s = 0; s < 2; ++s) {
       double u = s == 0 ? 1.0 : 0.0, be = s == 0 ? 0.0 : 1.0;
       for (int i = 0; i < kChunk; ++i) {
         const double yy = u;
-        if (s == 0) { sh.nat[tid][i].x = (float)yy; sh.nat[tid][i].y = (float)yy; }
-        else        { sh.nat[tid][i].z = (float)yy; sh.nat[tid][i].w = (float)yy; }
+        if (s == 0) sh.nat[tid][i].x = (float)yy;
+        else        sh.nat[tid][i].y = (float)yy;
         const double un = fma(cy, yy, be);
         be = fma(-dl, yy, be);
         u = un;
@@ -245,19 +289,36 @@ eq_kernel(const float* __restrict__ x, const float* __restrict__ params, float* 
       M[0 + s] = u;   // column s of the transition
       M[2 + s] = be;
     }
-    for (int e = 0; e < 4; ++e) sh.m16[tid][e] = M[e];
+    sh.m16[tid] = make_float4((float)M[0], (float)M[1], (float)M[2], (float)M[3]);
     // lane transition = M16^2, and its powers 0..32
     double M32[4];
     M32[0] = M[0] * M[0] + M[1] * M[2]; M32[1] = M[0] * M[1] + M[1] * M[3];
     M32[2] = M[2] * M[0] + M[3] * M[2]; M32[3] = M[2] * M[1] + M[3] * M[3];
     double P[4] = {1.0, 0.0, 0.0, 1.0};
     for (int l = 0; l <= 32; ++l) {
-      for (int e = 0; e < 4; ++e) sh.mpow[tid][l][e] = P[e];
+      sh.mpow[tid][l] = make_float4((float)P[0], (float)P[1], (float)P[2], (float)P[3]);
       const double n0 = M32[0] * P[0] + M32[1] * P[2], n1 = M32[0] * P[1] + M32[1] * P[3];
       const double n2 = M32[2] * P[0] + M32[3] * P[2], n3 = M32[2] * P[1] + M32[3] * P[3];
       P[0] = n0; P[1] = n1; P[2] = n2; P[3] = n3;
     }
-    for (int ch = 0; ch < 2; ++ch) { sh.carry[0][tid][ch][0] = 0.0; sh.carry[0][tid][ch][1] = 0.0; }  // state reset (:512)
+    {
+      // P now holds M32^33; M32^32 was stored at l = 32.  Powers of the warp transition W = M32^32 in float64:
+      double Wm[4], R[4] = {1.0, 0.0, 0.0, 1.0};
+      double T[4] = {1.0, 0.0, 0.0, 1.0};
+      for (int l = 0; l < 32; ++l) {
+        const double n0 = M32[0] * T[0] + M32[1] * T[2], n1 = M32[0] * T[1] + M32[1] * T[3];
+        const double n2 = M32[2] * T[0] + M32[3] * T[2], n3 = M32[2] * T[1] + M32[3] * T[3];
+        T[0] = n0; T[1] = n1; T[2] = n2; T[3] = n3;
+      }
+      for (int e = 0; e < 4; ++e) Wm[e] = T[e];
+      for (int j = 0; j <= kWarps; ++j) {
+        sh.mw[tid][j] = make_float4((float)R[0], (float)R[1], (float)R[2], (float)R[3]);
+        const double n0 = Wm[0] * R[0] + Wm[1] * R[2], n1 = Wm[0] * R[1] + Wm[1] * R[3];
+        const double n2 = Wm[2] * R[0] + Wm[3] * R[2], n3 = Wm[2] * R[1] + Wm[3] * R[3];
+        R[0] = n0; R[1] = n1; R[2] = n2; R[3] = n3;
+      }
+    }
+    sh.carryb[0][tid] = make_float4(0.f, 0.f, 0.f, 0.f);   // state reset (:512)
   }
   __syncthreads();
 
@@ -266,7 +327,7 @@ eq_kernel(const float* __restrict__ x, const float* __restrict__ params, float* 
   float* y0 = y + ((size_t)b * 2) * L;
   float* y1 = y0 + L;
   double sum_x2[2] = {0.0, 0.0}, sum_y2[2] = {0.0, 0.0};
-  int par = 0;
+  int par = 0;                                             // tile parity (double-buffered warp totals / carry)
 
 #pragma unroll 1
   for (int tile0 = 0; tile0 < L; tile0 += kEqTile, par ^= 1) {
@@ -300,11 +361,9 @@ eq_kernel(const float* __restrict__ x, const float* __restrict__ params, float* 
         // (1) zero-state response of both chunks, packed over the channels (float32, 5 FMAs per frame and chunk)
         u64 uA = 0ull, bA = 0ull, uB = 0ull, bB = 0ull;
         {
-          const u64 c_b0 = *reinterpret_cast<const u64*>(&sh.cf[k][0]);
-          const u64 c_B = *reinterpret_cast<const u64*>(&sh.cf[k][1]);
-          const u64 c_nd = *reinterpret_cast<const u64*>(&sh.cf[k][2]);
-          const u64 c_cy = *reinterpret_cast<const u64*>(&sh.cf[k][3]);
-          const u64 c_cx = *reinterpret_cast<const u64*>(&sh.cf[k][4]);
+          // scalar coefficients, duplicated at use: ptxas turns dup() into the FFMA2 ".F32" broadcast operand form
+          const u64 c_b0 = dup(sh.cf[k][0]), c_B = dup(sh.cf[k][1]), c_nd = dup(sh.cf[k][2]);
+          const u64 c_cy = dup(sh.cf[k][3]), c_cx = dup(sh.cf[k][4]);
 #pragma unroll
           for (int i = 0; i < kChunk; ++i) {
             const u64 xa = v[0][i], xb = v[1][i];
@@ -316,76 +375,72 @@ eq_kernel(const float* __restrict__ x, const float* __restrict__ params, float* 
             v[0][i] = ya; v[1][i] = yb;
           }
         }
-        // (2) per channel: lane total Z = M16 zA + zB, inclusive warp scan I_l = sum_{i<=l} M32^(l-i) Z_i   (float64)
-        double zA[2][2], zB[2][2], I[2][2], E[2][2];
-        zA[0][0] = (double)lo_of(uA); zA[0][1] = (double)lo_of(bA); zA[1][0] = (double)hi_of(uA); zA[1][1] = (double)hi_of(bA);
-        zB[0][0] = (double)lo_of(uB); zB[0][1] = (double)lo_of(bB); zB[1][0] = (double)hi_of(uB); zB[1][1] = (double)hi_of(bB);
-        const double* M16 = sh.m16[k];
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          double t0, t1;
-          mat_apply(M16, zA[ch][0], zA[ch][1], t0, t1);
-          I[ch][0] = t0 + zB[ch][0];
-          I[ch][1] = t1 + zB[ch][1];
-        }
+        // (2) lane total Z = M16 zA + zB, inclusive warp scan I_l = sum_{i<=l} M32^(l-i) Z_i
+        const float4 m16 = sh.m16[k];
+        const u64 h0 = dup(m16.x), h1 = dup(m16.y), h2 = dup(m16.z), h3 = dup(m16.w);
+        u64 IU = fma2(h0, uA, fma2(h1, bA, uB));
+        u64 IB = fma2(h2, uA, fma2(h3, bA, bB));
 #pragma unroll
         for (int st = 0; st < 5; ++st) {
           const int off = 1 << st;
-          const double* Mp = sh.mpow[k][off];
-          const double m0 = Mp[0], m1 = Mp[1], m2 = Mp[2], m3 = Mp[3];
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            const double o0 = __shfl_up_sync(0xffffffffu, I[ch][0], off), o1 = __shfl_up_sync(0xffffffffu, I[ch][1], off);
-            if (lane >= off) {
-              I[ch][0] = fma(m0, o0, fma(m1, o1, I[ch][0]));
-              I[ch][1] = fma(m2, o0, fma(m3, o1, I[ch][1]));
-            }
+          const float4 mp = sh.mpow[k][off];
+          const u64 oU = shfl_up2(IU, off), oB = shfl_up2(IB, off);
+          if (lane >= off) {
+            const u64 nU = fma2(dup(mp.x), oU, fma2(dup(mp.y), oB, IU));
+            const u64 nB = fma2(dup(mp.z), oU, fma2(dup(mp.w), oB, IB));
+            IU = nU; IB = nB;
           }
         }
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          if (lane == 31) { sh.wtot[par][k][wid][ch][0] = I[ch][0]; sh.wtot[par][k][wid][ch][1] = I[ch][1]; }
-          E[ch][0] = __shfl_up_sync(0xffffffffu, I[ch][0], 1);
-          E[ch][1] = __shfl_up_sync(0xffffffffu, I[ch][1], 1);
-          if (lane == 0) { E[ch][0] = 0.0; E[ch][1] = 0.0; }
-        }
-        __syncthreads();
-        // (3) state entering this lane: Q_0 = carry, Q_{w+1} = M32^32 Q_w + W_w;  in_A = M32^lane Q_w + E;  in_B = M16 in_A + zA
-        const double* M1024 = sh.mpow[k][32];
-        const double* Ml = sh.mpow[k][lane];
-        u64 inUA, inBA, inUB, inBB;
+        u64 EU = shfl_up2(IU, 1), EB = shfl_up2(IB, 1);    // state after the lanes before this one, from zero
+        if (lane == 0) { EU = 0ull; EB = 0ull; }
+        // (3) state entering this warp
+        u64 QU, QB;
         {
-          float fa[2][2], fb[2][2];
+          // warp totals -> shared memory, one block barrier, then every warp computes the prefix over the
+          // (at most 8) warp totals with a 3-step shuffle scan: P_j = state after warps 0..j from zero
+          if (lane == 31) sh.wtot[par][k][wid] = make_float4(lo_of(IU), hi_of(IU), lo_of(IB), hi_of(IB));
+          __syncthreads();
+          const float4 cq = sh.carryb[par][k];
+          const u64 CU = pk(cq.x, cq.y), CB = pk(cq.z, cq.w);
+          u64 PU = 0ull, PB = 0ull;
+          if (lane < kWarps) {
+            const float4 w4 = sh.wtot[par][k][lane];
+            PU = pk(w4.x, w4.y); PB = pk(w4.z, w4.w);
+          }
 #pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            double q0 = sh.carry[par][k][ch][0], q1 = sh.carry[par][k][ch][1];
-            for (int w = 0; w < wid; ++w) {
-              double n0, n1;
-              mat_apply(M1024, q0, q1, n0, n1);
-              q0 = n0 + sh.wtot[par][k][w][ch][0];
-              q1 = n1 + sh.wtot[par][k][w][ch][1];
-            }
-            double a0, a1, b0, b1;
-            mat_apply(Ml, q0, q1, a0, a1);
-            a0 += E[ch][0]; a1 += E[ch][1];
-            mat_apply(M16, a0, a1, b0, b1);
-            b0 += zA[ch][0]; b1 += zA[ch][1];
-            fa[ch][0] = (float)a0; fa[ch][1] = (float)a1; fb[ch][0] = (float)b0; fb[ch][1] = (float)b1;
-            if (tid == kThreads - 1) {   // state leaving the tile = M16 in_B + zB; read by the NEXT tile (other parity)
-              double c0, c1;
-              mat_apply(M16, b0, b1, c0, c1);
-              sh.carry[par ^ 1][k][ch][0] = c0 + zB[ch][0];
-              sh.carry[par ^ 1][k][ch][1] = c1 + zB[ch][1];
+          for (int off = 1; off < kWarps; off <<= 1) {
+            const float4 mp = sh.mw[k][off];
+            const u64 oU = shfl_up2(PU, off), oB = shfl_up2(PB, off);
+            if (lane >= off) {
+              const u64 nU = fma2(dup(mp.x), oU, fma2(dup(mp.y), oB, PU));
+              const u64 nB = fma2(dup(mp.z), oU, fma2(dup(mp.w), oB, PB));
+              PU = nU; PB = nB;
             }
           }
-          inUA = pk(fa[0][0], fa[1][0]); inBA = pk(fa[0][1], fa[1][1]);
-          inUB = pk(fb[0][0], fb[1][0]); inBB = pk(fb[0][1], fb[1][1]);
+          const int src = (wid + 31) & 31;
+          u64 SU = __shfl_sync(0xffffffffu, PU, src), SB = __shfl_sync(0xffffffffu, PB, src);
+          if (wid == 0) { SU = 0ull; SB = 0ull; }
+          const float4 mq = sh.mw[k][wid];                  // Q_w = W^w carry + P_{w-1}
+          QU = fma2(dup(mq.x), CU, fma2(dup(mq.y), CB, SU));
+          QB = fma2(dup(mq.z), CU, fma2(dup(mq.w), CB, SB));
+          if (tid == kThreads - 1) {                         // state leaving the tile = W Q_7 + W_7 (next tile, other parity)
+            const float4 mt = sh.mw[k][1];
+            const u64 nU = fma2(dup(mt.x), QU, fma2(dup(mt.y), QB, IU));
+            const u64 nB = fma2(dup(mt.z), QU, fma2(dup(mt.w), QB, IB));
+            sh.carryb[par ^ 1][k] = make_float4(lo_of(nU), hi_of(nU), lo_of(nB), hi_of(nB));
+          }
         }
+        // in_A = M32^lane Q + E;  in_B = M16 in_A + zA
+        const float4 ml = sh.mpow[k][lane];
+        const u64 inUA = fma2(dup(ml.x), QU, fma2(dup(ml.y), QB, EU));
+        const u64 inBA = fma2(dup(ml.z), QU, fma2(dup(ml.w), QB, EB));
+        const u64 inUB = fma2(h0, inUA, fma2(h1, inBA, uA));
+        const u64 inBB = fma2(h2, inUA, fma2(h3, inBA, bA));
         // (4) add the natural response to the true incoming state
 #pragma unroll
         for (int i = 0; i < kChunk; ++i) {
-          const float4 n = sh.nat[k][i];
-          const u64 nu = pk(n.x, n.y), nb = pk(n.z, n.w);
+          const float2 n = sh.nat[k][i];
+          const u64 nu = dup(n.x), nb = dup(n.y);
           v[0][i] = fma2(nu, inUA, fma2(nb, inBA, v[0][i]));
           v[1][i] = fma2(nu, inUB, fma2(nb, inBB, v[1][i]));
         }
@@ -438,7 +493,7 @@ eq_kernel(const float* __restrict__ x, const float* __restrict__ params, float* 
 // pass B: compressor, in place on y; per-channel sums, sum L*R, and the final-pass matrix of the segment
 // =====================================================================================================================
 struct CompShared {
-  float wa[2][2][kWarps], wb[2][2][kWarps];   // [round parity][channel][warp]: warp-total affine maps
+  float4 wab[2][kWarps];                      // [round parity][warp]: warp-total affine maps (A_L, B_L, A_R, B_R)
   float cend[2][2];                           // [round parity][channel]: smoother state leaving the tile (thread 255)
   float pa[kChunk + 1], pr[kChunk + 1];       // alpha_att^k, alpha_rel^k
   double red[kWarps][5];
@@ -453,7 +508,7 @@ comp_kernel(const float* __restrict__ params, float* __restrict__ y, double* __r
   CompShared& sh = *reinterpret_cast<CompShared*>(smem_raw);
   float* stg_all = reinterpret_cast<float*>(smem_raw + ((sizeof(CompShared) + 15) / 16) * 16);
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  float* stg = stg_all + wid * (2 * 32 * kCpRow);
+  float* stg_w = stg_all + wid * (2 * 2 * 32 * kCpRow);   // two tile buffers per warp (the next tile is prefetched)
   const float* p = params + (size_t)b * MST_FX_NPARAMS;
   double* st = stats + (size_t)b * kFxStats;
   const bool enable = (stages & MST_FX_COMP) != 0;
@@ -478,7 +533,9 @@ comp_kernel(const float* __restrict__ params, float* __restrict__ y, double* __r
   if (ratio_d > 1.0)      { cs = (float)(1.0 - 1.0 / ratio_d); co = (float)(-thr_d * (1.0 - 1.0 / ratio_d)); c_lo = 0.f; c_hi = kInf; }
   else if (ratio_d < 1.0) { cs = (float)(1.0 - ratio_d);       co = (float)(-thr_d * (1.0 - ratio_d));       c_lo = -kInf; c_hi = 0.f; }
   else                    { cs = 1.f; co = 0.f; c_lo = -kInf; c_hi = kInf; }
+  const float cs_db = cs * 6.0205999132796239f;            // x_g = 20 log10 |u| = 6.0206 log2 |u|
   const u64 c_att2 = dup((float)(1.0 - a_att_d)), c_rel2 = dup((float)(1.0 - a_rel_d)), m_one2 = dup(-1.f);
+  const bool use_max = (float)(1.0 - a_att_d) >= (float)(1.0 - a_rel_d);
   const u64 scale1_2 = dup(scale1);
 
   if (tid == 0) {
@@ -490,7 +547,7 @@ comp_kernel(const float* __restrict__ params, float* __restrict__ y, double* __r
   float* y0 = y + ((size_t)b * 2) * L;
   float* y1 = y0 + L;
   double sum_u2[2] = {0.0, 0.0}, sum_y2[2] = {0.0, 0.0}, sum_lr = 0.0;
-  int rpar = 0;
+  int rpar = 0, bufi = 0;
   unsigned rounds_local = 0;
   float tile_in[2] = {0.f, 0.f};        // smoother state entering the tile; yL_prev = 0 at every call (:553)
 
@@ -498,7 +555,16 @@ comp_kernel(const float* __restrict__ params, float* __restrict__ y, double* __r
   for (int tile0 = 0; tile0 < L; tile0 += kCpTile) {
     const int wf0 = tile0 + wid * (32 * kCpLane);
     const bool fast = vec && (tile0 + kCpTile <= L);
-    stage_in<kCpLane, kCpRow>(y0, y1, wf0, L, fast, stg, lane);
+    float* stg = stg_w + bufi * (2 * 32 * kCpRow);
+    if (fast) {
+      if (tile0 == 0) stage_in_async<kCpLane, kCpRow>(y0, y1, wf0, stg, lane);
+      stage_wait();
+    } else {
+      stage_in<kCpLane, kCpRow>(y0, y1, wf0, L, false, stg, lane);
+    }
+    if (vec && tile0 + 2 * kCpTile <= L)   // prefetch the next tile into the other buffer
+      stage_in_async<kCpLane, kCpRow>(y0, y1, wf0 + kCpTile, stg_w + (bufi ^ 1) * (2 * 32 * kCpRow), lane);
+    bufi ^= 1;
     float* r0 = stg + lane * kCpRow;
     float* r1 = stg + 32 * kCpRow + lane * kCpRow;
     u64 w[kChunk];   // x_l (dB over the static curve) while the smoother runs, then the output
@@ -524,8 +590,7 @@ comp_kernel(const float* __restrict__ params, float* __restrict__ y, double* __r
         xl[0] = lo_of(w[i]); xl[1] = hi_of(w[i]);
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-          const float xg = 6.0205999132796239f * lg2_approx(fmaxf(fabsf(xl[ch]), 0.000001f));
-          xl[ch] = fminf(fmaxf(fmaf(xg, cs, co), c_lo), c_hi);
+          xl[ch] = fminf(fmaxf(fmaf(lg2_approx(fmaxf(fabsf(xl[ch]), 0.000001f)), cs_db, co), c_lo), c_hi);
         }
         w[i] = pk(xl[0], xl[1]);
       }
@@ -538,24 +603,16 @@ comp_kernel(const float* __restrict__ params, float* __restrict__ y, double* __r
 #pragma unroll 1
       while (true) {
         u64 yy = pk(g_in[0], g_in[1]);
-        unsigned mask[2] = {0u, 0u};
-#pragma unroll
-        for (int i = 0; i < kChunk; ++i) {
-          const u64 d = fma2(yy, m_one2, w[i]);            // x_l - y
-          const u64 ya = fma2(c_att2, d, yy), yr = fma2(c_rel2, d, yy);
-          float n0, n1;                                   // attack <=> x_l > y (:578): select + pattern bit
-          step_select(n0, mask[0], lo_of(d), lo_of(ya), lo_of(yr), 1u << i);
-          step_select(n1, mask[1], hi_of(d), hi_of(ya), hi_of(yr), 1u << i);
-          yy = pk(n0, n1);
-          yl[i] = yy;
-        }
+        unsigned mask[2] = {0u, 0u};                       // release pattern of this round (16 bits per channel)
+        if (use_max) smoother_steps<true>(w, yl, yy, mask, c_att2, c_rel2, m_one2);
+        else         smoother_steps<false>(w, yl, yy, mask, c_att2, c_rel2, m_one2);
         y_end[0] = lo_of(yy); y_end[1] = hi_of(yy);
         int changed = 0;
         float sa[2], sb[2], ea[2], eb[2];
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-          const int na = __popc(mask[ch]);
-          sa[ch] = sh.pa[na] * sh.pr[kChunk - na];         // chunk map under this pattern: y_out = A y_in + B
+          const int nr = __popc(mask[ch]);
+          sa[ch] = sh.pa[kChunk - nr] * sh.pr[nr];         // chunk map under this pattern: y_out = A y_in + B
           sb[ch] = fmaf(-sa[ch], g_in[ch], y_end[ch]);
           changed |= (mask[ch] != prev_mask[ch]);
           prev_mask[ch] = mask[ch];
@@ -572,12 +629,12 @@ comp_kernel(const float* __restrict__ params, float* __restrict__ y, double* __r
         }
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-          if (lane == 31) { sh.wa[rpar][ch][wid] = sa[ch]; sh.wb[rpar][ch][wid] = sb[ch]; }
           if (tid == kThreads - 1) sh.cend[rpar][ch] = y_end[ch];
           ea[ch] = __shfl_up_sync(0xffffffffu, sa[ch], 1);
           eb[ch] = __shfl_up_sync(0xffffffffu, sb[ch], 1);
           if (lane == 0) { ea[ch] = 1.f; eb[ch] = 0.f; }
         }
+        if (lane == 31) sh.wab[rpar][wid] = make_float4(sa[0], sb[0], sa[1], sb[1]);
         const int any = __syncthreads_or(changed);
         ++rounds_local;
         ++round;
@@ -587,11 +644,27 @@ comp_kernel(const float* __restrict__ params, float* __restrict__ y, double* __r
           rpar ^= 1;                           // the next tile's first round must not overwrite what is being read here
           break;
         }
+        {
+          // state entering this warp: prefix of the warp-total maps, by a 3-step scan over lanes 0..7 (every warp does the
+          // same work, so nobody arrives late at the next barrier), then lane wid-1 holds the map of warps 0..wid-1
+          float4 m = make_float4(1.f, 0.f, 1.f, 0.f);
+          if (lane < kWarps) m = sh.wab[rpar][lane];
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          float qv = tile_in[ch];   // state entering this warp
-          for (int ww = 0; ww < wid; ++ww) qv = fmaf(sh.wa[rpar][ch][ww], qv, sh.wb[rpar][ch][ww]);
-          g_in[ch] = fmaf(ea[ch], qv, eb[ch]);   // state entering this thread's chunk under the current pattern
+          for (int off = 1; off < kWarps; off <<= 1) {
+            const float oa0 = __shfl_up_sync(0xffffffffu, m.x, off), ob0 = __shfl_up_sync(0xffffffffu, m.y, off);
+            const float oa1 = __shfl_up_sync(0xffffffffu, m.z, off), ob1 = __shfl_up_sync(0xffffffffu, m.w, off);
+            if (lane >= off) {
+              m.y = fmaf(m.x, ob0, m.y); m.x = m.x * oa0;
+              m.w = fmaf(m.z, ob1, m.w); m.z = m.z * oa1;
+            }
+          }
+          const int src = (wid + 31) & 31;
+          float pa0 = __shfl_sync(0xffffffffu, m.x, src), pb0 = __shfl_sync(0xffffffffu, m.y, src);
+          float pa1 = __shfl_sync(0xffffffffu, m.z, src), pb1 = __shfl_sync(0xffffffffu, m.w, src);
+          if (wid == 0) { pa0 = 1.f; pb0 = 0.f; pa1 = 1.f; pb1 = 0.f; }
+          const float q0 = fmaf(pa0, tile_in[0], pb0), q1 = fmaf(pa1, tile_in[1], pb1);
+          g_in[0] = fmaf(ea[0], q0, eb[0]);   // state entering this thread's chunk under the current pattern
+          g_in[1] = fmaf(ea[1], q1, eb[1]);
         }
         rpar ^= 1;
       }
@@ -735,7 +808,7 @@ final_kernel(float* __restrict__ y, const double* __restrict__ stats, int L, int
 }
 
 static size_t eq_smem_bytes() { return align_up(sizeof(EqShared), 16) + (size_t)kWarps * 2 * 32 * kEqRow * sizeof(float); }
-static size_t comp_smem_bytes() { return align_up(sizeof(CompShared), 16) + (size_t)kWarps * 2 * 32 * kCpRow * sizeof(float); }
+static size_t comp_smem_bytes() { return align_up(sizeof(CompShared), 16) + (size_t)kWarps * 2 * 2 * 32 * kCpRow * sizeof(float); }
 
 }  // namespace fx2
 
