@@ -127,6 +127,20 @@ size_t mst_fx_workspace_bytes(int B, int L);
 int mst_fx_chain_forward(const float* x, const float* params, float* y, int B, int L, float sample_rate, int stages,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- WAV sample formats on the device: the steps either side of the forward -------------------
+ * mst_pcm_decode replaces load_wav_segment's int -> float conversion and de-interleave
+ * (mixing_style_transfer/data_loader/loader_utils.py:54-70) plus the stem clamp (data_loader/data_loader.py:589-590) and
+ * the mono duplication of inference/feature_extraction.py:87-89:
+ *   pcm: interleaved [n_frames][n_channels] int16 (sample_bytes 2, x / 2^15) or int32 (sample_bytes 4, x / 2^31)
+ *   out: fp32 planar, channel c at out + c * out_stride (always two planes; mono input fills both)
+ * mst_pcm_encode_mix replaces the remix `sum(inst_outputs)` and the PCM_16 file quantisation
+ * (inference/style_transfer.py:165-177): stems fp32 [n_stems][2][stem_stride] -> int16 interleaved [n_frames][2],
+ * float32 adds in stem order, then clip(rint(x * 32768), -32768, 32767). */
+int mst_pcm_decode(const void* pcm, int sample_bytes, int n_channels, long long n_frames, float* out,
+                   long long out_stride, void* stream);
+int mst_pcm_encode_mix(const float* stems, int n_stems, long long stem_stride, long long n_frames, int16_t* pcm,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

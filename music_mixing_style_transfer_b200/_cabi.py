@@ -57,6 +57,8 @@ SIGNATURES = {
     "mst_fx_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mst_fx_chain_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_size_t,
                                      c_void_p]),
+    "mst_pcm_decode": (c_int, [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, ctypes.c_longlong, c_void_p]),
+    "mst_pcm_encode_mix": (c_int, [c_void_p, c_int, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_void_p]),
 }
 
 _lib = None

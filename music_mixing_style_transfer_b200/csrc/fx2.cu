@@ -334,6 +334,12 @@ eq_kernel(const float* __restrict__ x, const float* __restrict__ params, float* 
     const int wf0 = tile0 + wid * (32 * kEqLane);          // first frame of this warp
     const bool fast = vec && (tile0 + kEqTile <= L);
     stage_in<kEqLane, kEqRow>(x0, x1, wf0, L, fast, stg, lane);
+    if (tile0 + 2 * kEqTile <= L) {
+      // pull this warp's part of the NEXT tile into L2 now (one 128-byte line per lane and channel): the staging buffer is
+      // busy until the end of the tile, so the next stage_in cannot be issued early, but it can find its lines in L2
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(x0 + wf0 + kEqTile + lane * kEqLane));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(x1 + wf0 + kEqTile + lane * kEqLane));
+    }
     u64 v[2][kChunk];                                      // [chunk][i] = (L, R)
     {
       const float* r0 = stg + lane * kEqRow;

@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(256) tcn_act_unpack_kernel(const uint8_t* __re
 // =====================================================================================================================
 struct TcnLayerArgs {
   int B, T, dilation, tiles_per_seg, n_tiles, n_cond;
+  int pair_m;           // PAIRED kernels: sub-tiles per half block = dilation / 128
   const float4* film;   // this block's [n_cond][128] (bn_bias, gamma, beta, res)
   int fuse_out;         // 1 on the last block: Conv1d(128 -> n_out, k=1) + clamp fused, fp32 [B][n_out][T] written
   int n_out;
@@ -347,7 +348,32 @@ constexpr size_t kTcnSmemBytes = 1024 /*align slack*/ + (size_t)kRingBytes + kSt
 // rows [ts, ts+128) of a shifted sub-tile intersect the real signal [0, T)?  (otherwise it is all zero padding)
 __device__ __forceinline__ bool tap_live(long long ts, int T) { return ts < (long long)T && ts + kSubRows > 0; }
 
-template <int KCH>
+// Where the two 128-row sub-tiles of work item `tile` live.
+//   PAIRED = false: one 256-row tile, sub-tile 1 directly after sub-tile 0.
+//   PAIRED = true (dilation d a multiple of 128): sub-tile 1 sits d rows after sub-tile 0.  The time axis is cut into
+//   blocks of 2d rows; item i of a block pairs rows [i*128, +128) of its first half with the same rows of its second half.
+//   Then tap j of sub-tile 1 reads exactly the rows that tap j+1 of sub-tile 0 reads, so one activation slot serves two
+//   MMA groups and the operand bytes entering the SM per MMA drop by a third (see the producer / issuer loops).
+struct TcnTile { int b; long long r0, r1; bool sub0, sub1; };
+template <bool PAIRED>
+__device__ __forceinline__ TcnTile tcn_tile(int tile, const TcnLayerArgs& a) {
+  TcnTile c;
+  c.b = tile / a.tiles_per_seg;
+  const int p = tile - c.b * a.tiles_per_seg;
+  if (PAIRED) {
+    const int blk = p / a.pair_m, i = p - blk * a.pair_m;
+    c.r0 = (long long)blk * 2 * a.dilation + (long long)i * kSubRows;
+    c.r1 = c.r0 + a.dilation;
+  } else {
+    c.r0 = (long long)p * kTileRows;
+    c.r1 = c.r0 + kSubRows;
+  }
+  c.sub0 = c.r0 < a.T;
+  c.sub1 = c.r1 < a.T;
+  return c;
+}
+
+template <int KCH, bool PAIRED>
 __global__ void __launch_bounds__(256, 1)
 tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                       const __grid_constant__ CUtensorMap tm_xs, const __grid_constant__ CUtensorMap tm_y,
@@ -401,40 +427,52 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
       auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
+      auto load_w = [&](int j, int kc) {
+        // weights: rows ((j*kKcPerTap+kc)*2 + split)*128 .. : hi tile then lo tile
+        ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
+        ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
+        uint8_t* dst = ring + (size_t)slot * kSlotBytes;
+        const int wrow = ((j * kKcPerTap + kc) * 2) * kCh;
+        ptx::tma_load_2d(&tm_w, &bars->full[slot], dst, 0, wrow);
+        ptx::tma_load_2d(&tm_w, &bars->full[slot], dst + kHalf, 0, wrow + kCh);
+        next();
+      };
+      auto load_x = [&](int kc, long long ts, int b) {
+        // activation columns of this chunk: plane (hi / lo) of channel half kc*KCH/64, offset inside the plane
+        const int c_hi = ((kc * KCH) / 64) * 128 + (kc * KCH) % 64, c_lo = c_hi + 64;
+        ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
+        ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
+        uint8_t* dst = ring + (size_t)slot * kSlotBytes;
+        ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, c_hi, (int)ts, b);
+        ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + kHalf, c_lo, (int)ts, b);
+        next();
+      };
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int b = tile / a.tiles_per_seg;
-        const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
-        const bool sub1 = t0 + kSubRows < a.T;
-        for (int j = 0; j < kTaps; ++j) {
-          const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
-          const bool live0 = tap_live(ts0, a.T), live1 = sub1 && tap_live(ts1, a.T);
-          if (!live0 && !live1) continue;
+        const TcnTile c = tcn_tile<PAIRED>(tile, a);
+        if (!c.sub0) continue;
+        if (PAIRED) {
+          // slot order per executed step (kc, j): W, [rows of sub-tile 0's tap j unless step j-1 loaded them as sub-tile 1's
+          // tap j-1], [rows of sub-tile 1's tap j]
           for (int kc = 0; kc < kKcPerTap; ++kc) {
-            // weights: rows ((j*kKcPerTap+kc)*2 + split)*128 .. : hi tile then lo tile
-            ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
-            ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
-            uint8_t* dst = ring + (size_t)slot * kSlotBytes;
-            const int wrow = ((j * kKcPerTap + kc) * 2) * kCh;
-            ptx::tma_load_2d(&tm_w, &bars->full[slot], dst, 0, wrow);
-            ptx::tma_load_2d(&tm_w, &bars->full[slot], dst + kHalf, 0, wrow + kCh);
-            next();
-            // activation columns of this chunk: plane (hi / lo) of channel half kc*KCH/64, offset inside the plane
-            const int c_hi = ((kc * KCH) / 64) * 128 + (kc * KCH) % 64, c_lo = c_hi + 64;
-            if (live0) {
-              ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
-              ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
-              dst = ring + (size_t)slot * kSlotBytes;
-              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, c_hi, (int)ts0, b);
-              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + kHalf, c_lo, (int)ts0, b);
-              next();
+            for (int j = 0; j < kTaps; ++j) {
+              const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
+              const bool live0 = tap_live(ts0, a.T), live1 = c.sub1 && tap_live(ts1, a.T);
+              if (!live0 && !live1) continue;
+              load_w(j, kc);
+              const bool resident = j >= 1 && c.sub1 && live0;   // ts0 == rows of sub-tile 1 at tap j-1 (same liveness)
+              if (live0 && !resident) load_x(kc, ts0, c.b);
+              if (live1) load_x(kc, ts1, c.b);
             }
-            if (live1) {
-              ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
-              ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
-              dst = ring + (size_t)slot * kSlotBytes;
-              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, c_hi, (int)ts1, b);
-              ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + kHalf, c_lo, (int)ts1, b);
-              next();
+          }
+        } else {
+          for (int j = 0; j < kTaps; ++j) {
+            const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
+            const bool live0 = tap_live(ts0, a.T), live1 = c.sub1 && tap_live(ts1, a.T);
+            if (!live0 && !live1) continue;
+            for (int kc = 0; kc < kKcPerTap; ++kc) {
+              load_w(j, kc);
+              if (live0) load_x(kc, ts0, c.b);
+              if (live1) load_x(kc, ts1, c.b);
             }
           }
         }
@@ -459,44 +497,86 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         }
       };
       int it = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        const int b = tile / a.tiles_per_seg;
-        const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
-        const bool sub1 = t0 + kSubRows < a.T;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const TcnTile c = tcn_tile<PAIRED>(tile, a);
+        if (!c.sub0) continue;
         const int buf = it & 1;
         ptx::mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 + 0) * kCh, acc1 = tmem_base + (uint32_t)(buf * 2 + 1) * kCh;
         bool first0 = true, first1 = true;
-        for (int j = 0; j < kTaps; ++j) {
-          const long long ts0 = t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
-          const bool live0 = tap_live(ts0, a.T), live1 = sub1 && tap_live(ts1, a.T);
-          if (!live0 && !live1) continue;
+        if (PAIRED) {
           for (int kc = 0; kc < kKcPerTap; ++kc) {
-            const uint32_t wslot = slot;
-            ptx::mbar_wait(&bars->full[wslot], phase);
-            const uint32_t w_addr = ptx::smem_u32(ring + (size_t)wslot * kSlotBytes);
-            next();
-            if (live0) {
-              ptx::mbar_wait(&bars->full[slot], phase);
-              ptx::tc_fence_after();
-              issue_group(ptx::smem_u32(ring + (size_t)slot * kSlotBytes), w_addr, acc0, first0);
-              first0 = false;
-              ptx::umma_commit(&bars->empty[slot]);
+            int carried = -1;      // slot holding the rows sub-tile 1 used at the previous tap = rows of sub-tile 0 at this tap
+            for (int j = 0; j < kTaps; ++j) {
+              const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
+              const bool live0 = tap_live(ts0, a.T), live1 = c.sub1 && tap_live(ts1, a.T);
+              if (!live0 && !live1) continue;
+              const uint32_t wslot = slot;
+              ptx::mbar_wait(&bars->full[wslot], phase);
+              const uint32_t w_addr = ptx::smem_u32(ring + (size_t)wslot * kSlotBytes);
               next();
+              if (live0) {
+                uint32_t xs;
+                if (carried >= 0) {
+                  xs = (uint32_t)carried;
+                } else {
+                  xs = slot;
+                  ptx::mbar_wait(&bars->full[xs], phase);
+                  next();
+                }
+                ptx::tc_fence_after();
+                issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc0, first0);
+                first0 = false;
+                ptx::umma_commit(&bars->empty[xs]);
+              }
+              carried = -1;
+              if (live1) {
+                const uint32_t xs = slot;
+                ptx::mbar_wait(&bars->full[xs], phase);
+                next();
+                ptx::tc_fence_after();
+                issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc1, first1);
+                first1 = false;
+                // the same rows are sub-tile 0's operand at tap j+1 (ts1 = r0 + (j-6) d): keep the slot if that tap runs
+                if (j + 1 < kTaps) carried = (int)xs;
+                else ptx::umma_commit(&bars->empty[xs]);
+              }
+              ptx::umma_commit(&bars->empty[wslot]);
             }
-            if (live1) {
-              ptx::mbar_wait(&bars->full[slot], phase);
-              ptx::tc_fence_after();
-              issue_group(ptx::smem_u32(ring + (size_t)slot * kSlotBytes), w_addr, acc1, first1);
-              first1 = false;
-              ptx::umma_commit(&bars->empty[slot]);
+          }
+        } else {
+          for (int j = 0; j < kTaps; ++j) {
+            const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
+            const bool live0 = tap_live(ts0, a.T), live1 = c.sub1 && tap_live(ts1, a.T);
+            if (!live0 && !live1) continue;
+            for (int kc = 0; kc < kKcPerTap; ++kc) {
+              const uint32_t wslot = slot;
+              ptx::mbar_wait(&bars->full[wslot], phase);
+              const uint32_t w_addr = ptx::smem_u32(ring + (size_t)wslot * kSlotBytes);
               next();
+              if (live0) {
+                ptx::mbar_wait(&bars->full[slot], phase);
+                ptx::tc_fence_after();
+                issue_group(ptx::smem_u32(ring + (size_t)slot * kSlotBytes), w_addr, acc0, first0);
+                first0 = false;
+                ptx::umma_commit(&bars->empty[slot]);
+                next();
+              }
+              if (live1) {
+                ptx::mbar_wait(&bars->full[slot], phase);
+                ptx::tc_fence_after();
+                issue_group(ptx::smem_u32(ring + (size_t)slot * kSlotBytes), w_addr, acc1, first1);
+                first1 = false;
+                ptx::umma_commit(&bars->empty[slot]);
+                next();
+              }
+              ptx::umma_commit(&bars->empty[wslot]);
             }
-            ptx::umma_commit(&bars->empty[wslot]);
           }
         }
         ptx::umma_commit(&bars->tmem_full[buf]);
+        ++it;
       }
     }
   } else if (warp >= 4) {
@@ -506,15 +586,16 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const int rl = q * 32 + lane;           // row inside the sub-tile == TMEM lane
     uint32_t stage_phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-      const int b = tile / a.tiles_per_seg;
-      const int t0 = (tile - b * a.tiles_per_seg) * kTileRows;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const TcnTile c = tcn_tile<PAIRED>(tile, a);
+      if (!c.sub0) continue;
+      const int b = c.b;
       const int buf = it & 1;
       const float4* film = a.film + (size_t)(a.n_cond > 1 ? b : 0) * kCh;
       ptx::mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();
       for (int sub = 0; sub < 2; ++sub) {
-        const int ts = t0 + sub * kSubRows;
+        const int ts = (int)(sub == 0 ? c.r0 : c.r1);
         if (ts >= a.T) break;
         float o0 = 0.f, o1 = 0.f;
         for (int h = 0; h < 2; ++h) {
@@ -591,6 +672,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars->tmem_empty[buf]);
+      ++it;
     }
     if (et == 0) ptx::tma_store_wait_all();
   }
@@ -659,7 +741,15 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   if (encode_w_map(&tm_w, packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer, kch)) return 1;
   TcnLayerArgs a;
   a.B = B; a.T = T; a.dilation = (int)d;
-  a.tiles_per_seg = cdiv(T, kTileRows);
+  // MST_TCN_PAIRED=1: paired sub-tiles (tcn_tile<true>) for dilations that are a multiple of 128.  Measured (ncu, isolated
+  // launches, blocks 7-13): L2->SM bytes 100.9 -> 70 GB per launch, SM clock under the power cap 1.48 -> 1.58 GHz, but
+  // tensor-pipe activity per cycle 78.1 -> 74.3 %, so 8.88 -> 8.73 ms isolated and no difference in a sustained forward
+  // (9.75-9.97 ms/launch either way): parity-green, off by default.
+  static int paired_env = -1;
+  if (paired_env < 0) { const char* e = getenv("MST_TCN_PAIRED"); paired_env = (e && atoi(e) == 1) ? 1 : 0; }
+  const bool paired = paired_env && kch == 64 && d >= kSubRows && d % kSubRows == 0;
+  a.pair_m = paired ? (int)(d / kSubRows) : 1;
+  a.tiles_per_seg = paired ? (int)(((T + 2 * d - 1) / (2 * d)) * a.pair_m) : cdiv(T, kTileRows);
   a.n_tiles = B * a.tiles_per_seg;
   a.n_cond = n_cond;
   a.film = reinterpret_cast<const float4*>(film) + (size_t)n * n_cond * kCh;
@@ -669,12 +759,15 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   a.out_b = reinterpret_cast<const float*>(packed + L.out_b);
   a.out = out;
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-  if (kch == 64) {
-    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));
-    tcn_block_umma_kernel<64><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, a);
+  if (paired) {
+    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));
+    tcn_block_umma_kernel<64, true><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, a);
+  } else if (kch == 64) {
+    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));
+    tcn_block_umma_kernel<64, false><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, a);
   } else {
-    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));
-    tcn_block_umma_kernel<32><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, a);
+    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));
+    tcn_block_umma_kernel<32, false><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, a);
   }
   return launch_ok("tcn_block_umma_kernel");
 }

@@ -17,7 +17,11 @@
     mean over ALL reference segments also when the last batch is short, where the reference's torch.stack would throw
     (:152); (c) under torchrun (WORLD_SIZE > 1) input batches are sharded over the ranks (shard.py); (d) the CPU
     "FX normalisation" pre-step (--normalize_input, data_loader.py:586-587) and the demucs subprocess (:77-90) are outside
-    this engine: pass --normalize_input False --do_not_separate True with stems already separated.
+    this engine: pass --normalize_input False --do_not_separate True with stems already separated; (e) the host I/O either
+    side of the forward runs on the device (wav_io.py / csrc/pcm.cu): raw int16 PCM is copied to the GPU and
+    converted / de-interleaved / clamped there, segments are cut from the device-resident stem, the converted stems stay
+    on the device, and remix + PCM_16 quantisation produce ONE int16 mixture that is copied back and written -- bit-identical
+    to the host path (`--device_io False` keeps that path).
 """
 import os
 import sys
@@ -30,7 +34,7 @@ import torch
 currentdir = os.path.dirname(os.path.realpath(__file__))
 sys.path.append(os.path.dirname(os.path.dirname(currentdir)))
 from music_mixing_style_transfer_b200.networks import FXencoder, TCNModel  # noqa: E402
-from music_mixing_style_transfer_b200 import shard  # noqa: E402
+from music_mixing_style_transfer_b200 import shard, wav_io  # noqa: E402
 
 
 # ---- WAV I/O with the reference loader's semantics (mixing_style_transfer/data_loader/loader_utils.py:47-70) ----
@@ -93,9 +97,13 @@ class Song_Dataset_Inference:
         stems = []
         for inst in self.instruments:
             p = os.path.join(dir_path, self.stem_level_directory_name, self.args.separation_model, name, inst + '.wav')
-            x = load_wav_segment(p, axis=0, sample_rate=self.args.sample_rate)       # [2, T]
-            stems.append(np.clip(x, -1.0, 1.0))                                       # data_loader.py:589-590
-        return torch.from_numpy(np.stack(stems, axis=0)).float()
+            if getattr(self.args, "device_io", True):
+                # raw PCM -> GPU, int -> float / de-interleave / clamp there (csrc/pcm.cu); same values as the host path
+                stems.append(wav_io.load_wav_to_device(p, sample_rate=self.args.sample_rate))
+            else:
+                x = load_wav_segment(p, axis=0, sample_rate=self.args.sample_rate)       # [2, T]
+                stems.append(torch.from_numpy(np.clip(x, -1.0, 1.0)).float())             # data_loader.py:589-590
+        return torch.stack(stems, dim=0)
 
     def __getitem__(self, idx):
         d = self.data_dir_paths[idx]
@@ -121,6 +129,7 @@ class Mixing_Style_Transfer_Inference:
 
         # inference computational hyperparameters
         self.args = args
+        self.device_io = bool(getattr(args, "device_io", True))
         self.segment_length = args.segment_length
         self.batch_size = args.batch_size
         self.sample_rate = 44100    # sampling rate should be 44100
@@ -199,14 +208,33 @@ class Mixing_Style_Transfer_Inference:
                     y = torch.empty(0, 2, cur_data.shape[-1], device=self.device)
                 if self.world_size > 1:
                     y = shard.allgather_segments(y, shard.shard_counts(n, self.world_size))
-                outs.append(y.cpu().detach())
+                outs.append(y.detach() if self.device_io else y.cpu().detach())
         return outs
 
-    @staticmethod
-    def combine(infered_data_list, length):
-        # combine back to whole song (:165-169)
+    def combine(self, infered_data_list, length):
+        # combine back to whole song (:165-169); a device tensor under --device_io, a numpy array otherwise
         seq = [torch.cat(torch.unbind(b, dim=0), dim=-1) for b in infered_data_list]
-        return torch.cat(seq, dim=-1)[:, :length].numpy()
+        whole = torch.cat(seq, dim=-1)[:, :length]
+        return whole if self.device_io else whole.numpy()
+
+    def write_outputs(self, cur_out_dir, inst_outputs, output_name_tag):
+        """Per-instrument files (--save_each_inst) and the remix `sum(inst_outputs)` as PCM_16 (:170-177)."""
+        if self.rank != 0:
+            return
+        if self.device_io:
+            if self.args.save_each_inst:
+                for name, y in zip(self.args.instruments, inst_outputs):
+                    wav_io.write_wav_pcm16_from_device(os.path.join(cur_out_dir, f"{name}_{output_name_tag}.wav"), y,
+                                                       self.args.sample_rate)
+            wav_io.write_wav_pcm16_from_device(os.path.join(cur_out_dir, f"mixture_{output_name_tag}.wav"),
+                                               torch.stack(inst_outputs, dim=0), self.args.sample_rate)
+        else:
+            if self.args.save_each_inst:
+                for name, y in zip(self.args.instruments, inst_outputs):
+                    write_wav_pcm16(os.path.join(cur_out_dir, f"{name}_{output_name_tag}.wav"), y.transpose(-1, -2),
+                                    self.args.sample_rate)
+            write_wav_pcm16(os.path.join(cur_out_dir, f"mixture_{output_name_tag}.wav"),
+                            sum(inst_outputs).transpose(-1, -2), self.args.sample_rate)
 
     # Inference whole song
     def inference(self, ):
@@ -248,15 +276,8 @@ class Mixing_Style_Transfer_Inference:
                 fin_data_out_inst = self.combine(infered_data_list, input_stems[0][cur_inst_idx].shape[-1])
 
                 inst_outputs.append(fin_data_out_inst)
-                # save output of each instrument
-                if self.args.save_each_inst and self.rank == 0:
-                    write_wav_pcm16(os.path.join(cur_out_dir, f"{cur_inst_name}_{output_name_tag}.wav"),
-                                    fin_data_out_inst.transpose(-1, -2), self.args.sample_rate)
-            # remix
-            fin_data_out_mix = sum(inst_outputs)
-            if self.rank == 0:
-                write_wav_pcm16(os.path.join(cur_out_dir, f"mixture_{output_name_tag}.wav"),
-                                fin_data_out_mix.transpose(-1, -2), self.args.sample_rate)
+            # per-instrument outputs (--save_each_inst) and the remix
+            self.write_outputs(cur_out_dir, inst_outputs, output_name_tag)
 
     # Inference whole song
     def inference_interpolation(self, ):
@@ -308,16 +329,8 @@ class Mixing_Style_Transfer_Inference:
                 infered_data_list = self.convert(cur_inst_input_stem, cond_of_batch)
                 fin_data_out_inst = self.combine(infered_data_list, input_stems[0][cur_inst_idx].shape[-1])
                 inst_outputs.append(fin_data_out_inst)
-
-                # save output of each instrument
-                if self.args.save_each_inst and self.rank == 0:
-                    write_wav_pcm16(os.path.join(cur_out_dir, f"{cur_inst_name}_{output_name_tag}.wav"),
-                                    fin_data_out_inst.transpose(-1, -2), self.args.sample_rate)
-            # remix
-            fin_data_out_mix = sum(inst_outputs)
-            if self.rank == 0:
-                write_wav_pcm16(os.path.join(cur_out_dir, f"mixture_{output_name_tag}.wav"),
-                                fin_data_out_mix.transpose(-1, -2), self.args.sample_rate)
+            # per-instrument outputs (--save_each_inst) and the remix
+            self.write_outputs(cur_out_dir, inst_outputs, output_name_tag)
 
     # function that segmentize an entire song into batch
     def batchwise_segmentization(self, target_song, song_name, segment_length, discard_last=False):
@@ -334,7 +347,7 @@ class Mixing_Style_Transfer_Inference:
         # pad last segment
         else:
             pad_length = segment_length - target_song.shape[-1] % segment_length
-            target_song = torch.cat((target_song, torch.zeros(2, pad_length)), axis=-1)
+            target_song = torch.cat((target_song, torch.zeros(2, pad_length, device=target_song.device)), axis=-1)
 
         # segmentize according to the given segment_length
         whole_batch_data = []
@@ -423,6 +436,7 @@ def build_parser():
     device_args.add_argument('--inference_device', type=str, default='gpu', help="the B200 engine only runs on CUDA devices")
     device_args.add_argument('--batch_size', type=int, default=1)   # for processing long audio
     device_args.add_argument('--separation_device', type=str, default='cpu', help="device for performing source separation using Demucs")
+    device_args.add_argument('--device_io', type=str2bool, default=True, help="(B200 engine) decode PCM / remix / quantise on the GPU; False = host numpy path, same bits")
     return parser
 
 

@@ -73,3 +73,21 @@ def build_reference_models(enc_sd=None, tcn_sd=None):
     if tcn_sd is not None:
         tcn.load_state_dict(tcn_sd)
     return enc.eval(), tcn.eval()
+
+
+def import_reference_loader_utils():
+    """The reference's data_loader/loader_utils.py (load_wav_segment ...), loaded straight from its file: the package
+    `data_loader/__init__.py` pulls soundfile / librosa / pyloudnorm, none of which is in this image; loader_utils itself
+    only needs `soundfile` for the writer helpers, so an empty stand-in module is registered for the import."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    import importlib.util
+    import types
+
+    if "soundfile" not in sys.modules:
+        sys.modules["soundfile"] = types.ModuleType("soundfile")
+    path = os.path.join(REFERENCE_ROOT, "mixing_style_transfer", "data_loader", "loader_utils.py")
+    spec = importlib.util.spec_from_file_location("mst_reference_loader_utils", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

@@ -100,3 +100,68 @@ def test_public_entry_on_wav_files(tmp_path, interp):
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+def test_device_io_is_bit_identical_to_host_io(tmp_path):
+    """--device_io True (PCM decode / remix / PCM_16 on the GPU, csrc/pcm.cu) must write the same bytes as the host path."""
+    from music_mixing_style_transfer_b200.inference import style_transfer as st
+    esd, tsd = state_dicts()
+    torch.save({"model": {"module." + k: v for k, v in esd.items()}}, tmp_path / "enc.pt")
+    torch.save({"model": {"module." + k: v for k, v in tsd.items()}}, tmp_path / "tcn.pt")
+    song = tmp_path / "data" / "song0"
+    insts = ["drums", "bass", "other", "vocals"]
+    seg = 16384
+    for name, L in (("input", 2 * seg + 77), ("reference", 3 * seg + 1)):
+        for i, inst in enumerate(insts):
+            x = W.synthetic_audio(1, L, seed=900 + 10 * len(name) + i)[0].numpy() * 3.0   # loud: the remix clips
+            _write_wav(str(song / "separated" / "mdx_extra" / name / f"{inst}.wav"), x)
+    outs = {}
+    for mode in ("True", "False"):
+        out_dir = tmp_path / f"out_{mode}"
+        st.main(["--target_dir", str(tmp_path / "data") + "/", "--output_dir", str(out_dir) + "/",
+                 "--ckpt_path_enc", str(tmp_path / "enc.pt"), "--ckpt_path_conv", str(tmp_path / "tcn.pt"),
+                 "--segment_length", str(seg), "--segment_length_ref", str(seg), "--batch_size", "3",
+                 "--normalize_input", "False", "--do_not_separate", "True", "--save_each_inst", "True",
+                 "--device_io", mode])
+        files = sorted(os.listdir(out_dir / "song0"))
+        assert "mixture_output_notnormed.wav" in files and "drums_output_notnormed.wav" in files
+        outs[mode] = {f: open(out_dir / "song0" / f, "rb").read() for f in files if f.endswith(".wav")}
+    assert outs["True"].keys() == outs["False"].keys()
+    for f in outs["True"]:
+        assert outs["True"][f] == outs["False"][f], f
+
+
+def test_feature_extraction_entry(tmp_path):
+    """inference/feature_extraction.py surface (BASELINE config 1 semantics): one stereo and one mono WAV, DDP checkpoint,
+    `<name>_fx_embedding.npy` = mean embedding over the zero-padded segments, vs the oracle encoder on the same PCM."""
+    oracle_threads()
+    from music_mixing_style_transfer_b200.inference import feature_extraction as fe
+    esd, _ = state_dicts()
+    torch.save({"model": {"module." + k: v for k, v in esd.items()}}, tmp_path / "enc.pt")
+    seg = 16384
+    clips = {}
+    x = W.synthetic_audio(1, 2 * seg + 311, seed=71)[0].numpy()
+    x = np.clip(np.rint(x * 32768.0), -32768, 32767) / 32768.0
+    clips["a/stereo.wav"] = x
+    _write_wav(str(tmp_path / "data" / "a" / "stereo.wav"), x)
+    m = W.synthetic_audio(1, seg, seed=72)[0, :1].numpy()                      # exact multiple: extra all-zero segment
+    m = np.clip(np.rint(m * 32768.0), -32768, 32767) / 32768.0
+    os.makedirs(tmp_path / "data" / "b", exist_ok=True)
+    with wave.open(str(tmp_path / "data" / "b" / "mono.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(44100)
+        w.writeframes(np.rint(m[0] * 32768.0).astype("<i2").tobytes())
+    clips["b/mono.wav"] = np.concatenate([m, m], axis=0)
+    fe.main(["--target_dir", str(tmp_path / "data") + "/", "--output_dir", str(tmp_path / "emb") + "/",
+             "--ckpt_path_enc", str(tmp_path / "enc.pt"), "--segment_length", str(seg), "--batch_size", "2"])
+    assert os.path.exists(tmp_path / "emb" / "feature_extraction_inference_configurations.txt")
+    for rel, audio in clips.items():
+        got = np.load(tmp_path / "emb" / rel.replace(".wav", "_fx_embedding.npy"))
+        song = torch.from_numpy(audio).float()
+        batches = O.batchwise_segmentization(song, seg, 2)
+        with torch.no_grad():
+            ref = torch.cat([O.fxencoder_forward(b, esd, W.ENC_KERNELS, W.ENC_STRIDES) for b in batches], 0).mean(0).numpy()
+        assert got.shape == (2048,) and got.dtype == np.float32
+        assert np.abs(got - ref).max() <= 1e-4 and np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 2e-5, rel
+    with pytest.raises(RuntimeError):
+        fe.main(["--target_dir", str(tmp_path / "data") + "/", "--ckpt_path_enc", str(tmp_path / "enc.pt"),
+                 "--inference_device", "cpu"])

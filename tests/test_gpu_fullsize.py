@@ -58,8 +58,12 @@ def test_fx_config3_properties():
     gain = torch.where(P[:, 19] >= 0.5, -gain, gain).float()
     assert torch.allclose(yg, x * gain[:, None, None], rtol=2e-6, atol=0)
     # full chain = the three normalised stages followed by the gain
+    # (fx2.cu folds RMS factor, imager and gain into one 2x2 matrix per segment: out_L = m0 l + m1 r can cancel, so the
+    # bound is float32 rounding relative to the segment's peak, not to each sample)
     yall = fx_chain_forward(x, P)
-    assert torch.allclose(yall, y * gain[:, None, None], rtol=2e-6, atol=1e-9)
+    want = y * gain[:, None, None]
+    peak = want.abs().amax(dim=(1, 2), keepdim=True)
+    assert float(((yall - want).abs() / peak).max()) <= 5e-7
     # batch-permutation equivariance and determinism
     perm = torch.randperm(B, device="cuda")
     assert torch.equal(fx_chain_forward(x[perm].contiguous(), P[perm].contiguous()), yall[perm])

@@ -91,3 +91,42 @@ def test_edge_cases_silence_and_mono():
     assert np.all(np.isfinite(ys[0])) and np.abs(ys[0]).max() == 0.0
     e = err_stats(ys[1].T, fx_oracle.fx_chain(m, P[1]).T)
     assert e["rms"] <= RMS_TOL, e
+
+
+def test_v1_kernels_still_match_oracle():
+    """MST_FX_IMPL=v1 keeps the first-generation kernels (fx.cu) selectable for A/B timing: they must stay parity-green.
+    The switch is read once per process, so run a child."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MST_FX_IMPL="v1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_fx.py"), "-m", "gpu", "-x", "-q",
+                        "-k", "not v1_kernels"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("L", [8192, 8192 * 3 + 4, 8191, 12289])
+def test_tile_boundaries(L):
+    """fx2.cu tiles: EQ 8192 frames, compressor 4096 frames; lengths at / around the tile size, with L % 4 != 0 (scalar staging
+    path) and L % 4 == 0 with a partial last tile (mixed fast / slow tiles)."""
+    B = 3
+    P = fx_oracle.random_params(B, seed=100 + L)
+    xs = [fixtures.fx_input(80 + i, L) for i in range(B)]
+    ys = run_gpu(xs, P)
+    for i in range(B):
+        e = err_stats(ys[i].T, fx_oracle.fx_chain(xs[i], P[i]).T)
+        assert e["rms"] <= 3e-5 and e["rel"] <= 5e-4, (L, i, e)
+
+
+def test_compressor_attack_slower_than_release_and_ratio_cases():
+    """Outside the randomisation ranges: attack slower than release (the smoother's max becomes a min), ratio < 1 and ratio == 1
+    (common_audioeffects.py:564-573), compressor switched off by threshold 0 / ratio 1 (:635)."""
+    from music_mixing_style_transfer_b200.mixing_manipulator import FX_COMP
+    x = fixtures.fx_input(90, 30000)
+    cases = [(-30.0, 300.0, 20.0, 8.0), (-30.0, 5.0, 100.0, 0.5), (-20.0, 5.0, 100.0, 1.0), (0.0, 5.0, 100.0, 1.0)]
+    for thr, att, rel, ratio in cases:
+        p = fx_oracle.random_params(1, seed=3)[0]
+        p[13], p[14], p[15], p[16] = thr, att, rel, ratio
+        y = run_gpu([x], p[None, :], FX_COMP)[0]
+        ref = np.asarray(fx_oracle.compressor(x, p), np.float32)
+        e = err_stats(y.T, ref.T)
+        assert e["rms"] <= 3e-5 and e["rel"] <= 5e-4, ((thr, att, rel, ratio), e)

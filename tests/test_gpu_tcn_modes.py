@@ -12,6 +12,7 @@ VARIANTS = [
     {"MST_TCN_PRECISION": "f16f8"},
     {"MST_TCN_PIPE": "2"},
     {"MST_TCN_KCHUNK": "32"},
+    {"MST_TCN_PAIRED": "1"},
 ]
 
 

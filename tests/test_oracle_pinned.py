@@ -4,6 +4,8 @@
      oracle/make_golden.py in the build container), and
  (2) against the reference modules themselves when /root/reference is present (it is not on the GPU box).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -104,3 +106,38 @@ def test_fx_oracle_equals_reference_code():
         y_ref = reference_fx_chain(ca, P[i])([x.copy()])[0]
         d = y_ref.astype(np.float64) - fx_oracle.fx_chain(x, P[i])
         assert np.sqrt(np.mean(d ** 2)) <= 1e-7
+
+
+@needs_ref
+def test_io_oracle_equals_reference_loader():
+    """oracle/io_oracle.decode == the reference's load_wav_segment (+ stem clamp, float cast) on the reference's own sample
+    stems (stereo int16, read with the stdlib `wave` module exactly as loader_utils.py:47-70 does)."""
+    import glob
+    import wave
+    from oracle import io_oracle
+    lu = ref_import.import_reference_loader_utils()
+    paths = sorted(glob.glob(os.path.join(ref_import.REFERENCE_ROOT, "samples", "style_transfer", "*", "separated", "*", "input", "*.wav")))[:3]
+    assert paths, "reference sample stems not found"
+    for p in paths:
+        n = 150000
+        ref = np.clip(lu.load_wav_segment(p, start_point=1000, duration=n, axis=0), -1.0, 1.0).astype(np.float32)
+        with wave.open(p, "r") as w:
+            w.setpos(1000)
+            raw = np.frombuffer(w.readframes(n), dtype="<i2").reshape(-1, w.getnchannels())
+        got = io_oracle.decode(raw)
+        assert got.shape == ref.shape and np.array_equal(got, ref), p
+
+
+def test_io_oracle_encode_known_answers():
+    """PCM_16 quantisation of the remix: ties to even, clip on both sides, float32 stem sum in order."""
+    from oracle import io_oracle
+    s = np.zeros((2, 2, 6), np.float32)
+    s[0, :, 0] = 0.5 / 32768; s[0, :, 1] = 1.5 / 32768; s[0, :, 2] = -2.5 / 32768
+    s[:, :, 3] = 0.75                      # 1.5 -> clip to 32767
+    s[:, :, 4] = -0.75                     # -1.5 -> clip to -32768
+    s[0, 0, 5] = 1e-3; s[1, 0, 5] = 2e-3
+    out = io_oracle.encode_mix(s)
+    assert out.dtype == np.int16 and out.shape == (6, 2)
+    assert out[:5, 0].tolist() == [0, 2, -2, 32767, -32768]
+    assert out[5, 0] == int(np.rint(float(np.float32(1e-3) + np.float32(2e-3)) * 32768)) and out[5, 1] == 0
+    assert io_oracle.encode_mix(s, 2).shape == (2, 2)
