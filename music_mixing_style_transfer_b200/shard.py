@@ -92,3 +92,39 @@ def sharded_style_transfer(encoder, converter, reference_batch: Optional[torch.T
     if gather and ws > 1:
         out = allgather_segments(out, shard_counts(total_segments, ws), group=group)
     return emb, out
+
+
+def interpolation_weights(total_segments: int, interpolate_segments: int, device=None) -> torch.Tensor:
+    """Per-segment weight of embedding A for BASELINE config 5: the batch holds songs of `interpolate_segments` consecutive
+    segments, row b gets w = (S - 1 - (b mod S)) / (S - 1)  (inference/style_transfer.py:250 with the index taken per
+    SEGMENT -- the reference indexes it per batch, which is the same thing at its default batch_size = 1)."""
+    S = int(interpolate_segments)
+    if S < 2:
+        raise ValueError("interpolate_segments must be >= 2")
+    idx = torch.arange(total_segments, device=device) % S
+    return (S - 1 - idx).to(torch.float32) / float(S - 1)
+
+
+def sharded_interpolation(encoder, converter, reference_a: Optional[torch.Tensor], reference_b: Optional[torch.Tensor],
+                          input_shard: torch.Tensor, total_segments: int, weights: torch.Tensor, cond_dim: int = 2048,
+                          gather: bool = True, group=None):
+    """Interpolation mode (inference/style_transfer.py:181-270) sharded over the ranks.
+      reference_a / reference_b: [B_ref, 2, L_ref] on rank 0 -> two mean embeddings -> ONE broadcast of [2, cond_dim]
+      input_shard: this rank's contiguous slice of the `total_segments` input segments
+      weights:     [total_segments] weight of embedding A per segment (interpolation_weights); every rank holds all of it
+    Each rank builds the per-segment conditioning rows of its own slice, cond = w A + (1 - w) B (:251), and runs the
+    converter with cond [B_local, cond_dim] (FiLM broadcasts per row, network_utils.py:180-182)."""
+    rank, ws = world(group)
+    embs = None
+    if rank == 0:
+        embs = torch.stack([encoder(reference_a).mean(dim=0), encoder(reference_b).mean(dim=0)], dim=0)
+    embs = broadcast_embedding(embs, (2, cond_dim), input_shard.device, src=0, group=group)
+    lo, hi = shard_bounds(total_segments, ws, rank)
+    if hi - lo != input_shard.shape[0]:
+        raise RuntimeError(f"rank {rank}: input shard has {input_shard.shape[0]} segments, expected {hi - lo}")
+    w = weights[lo:hi].to(device=input_shard.device, dtype=torch.float32).unsqueeze(1)
+    cond = w * embs[0].unsqueeze(0) + (1.0 - w) * embs[1].unsqueeze(0)
+    out = converter(input_shard, cond)
+    if gather and ws > 1:
+        out = allgather_segments(out, shard_counts(total_segments, ws), group=group)
+    return embs, out

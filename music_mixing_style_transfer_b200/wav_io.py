@@ -50,8 +50,14 @@ def decode_pcm(pcm, device=None, out=None):
     if isinstance(pcm, np.ndarray):
         if pcm.dtype not in (np.dtype('<i2'), np.dtype('<i4')):
             raise ValueError("ValueError: input audio's bit depth should be 16 or 32-bit")
-        host = torch.from_numpy(np.ascontiguousarray(pcm))
-        pcm = host.pin_memory().to(device, non_blocking=True) if host.numel() else host.to(device)
+        # one host copy: the (read-only) file buffer straight into a pinned staging tensor, then an async H2D copy
+        tdt = torch.int16 if pcm.dtype == np.dtype('<i2') else torch.int32
+        if pcm.size:
+            host = torch.empty(pcm.shape, dtype=tdt).pin_memory()
+            np.copyto(host.numpy(), pcm)
+            pcm = host.to(device, non_blocking=True)
+        else:
+            pcm = torch.empty(pcm.shape, dtype=tdt, device=device)
     if pcm.dtype not in (torch.int16, torch.int32):
         raise ValueError("ValueError: input audio's bit depth should be 16 or 32-bit")
     if pcm.dim() == 1:

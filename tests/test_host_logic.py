@@ -141,3 +141,45 @@ def test_two_rank_gloo_broadcast_and_allgather(n_total):
         p.join(timeout=60)
     assert [r[1] for r in res] == [True, True], res
     assert all(r[2] == (n_total, 2, 37) for r in res)
+
+
+def _worker_interp(rank, ws, port, n_total, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        torch.manual_seed(1)
+        full = torch.randn(n_total, 2, 29)
+        ref_a, ref_b = torch.randn(3, 2, 40), torch.randn(4, 2, 40)
+        enc = lambda x: x.mean(dim=-1).repeat(1, 8)              # noqa: E731  stand-in encoder -> [B, 16]
+        conv = lambda x, c: x + c[:, :1, None]                    # noqa: E731  stand-in converter, per-row conditioning
+        S = 4
+        w = shard.interpolation_weights(n_total, S)
+        lo, hi = shard.shard_bounds(n_total, ws, rank)
+        embs, out = shard.sharded_interpolation(enc, conv, ref_a if rank == 0 else None, ref_b if rank == 0 else None,
+                                                full[lo:hi], n_total, w, cond_dim=16)
+        ea, eb = enc(ref_a).mean(0), enc(ref_b).mean(0)
+        cond = w[:, None] * ea[None] + (1 - w[:, None]) * eb[None]
+        ok = torch.allclose(embs, torch.stack([ea, eb])) and torch.allclose(out, full + cond[:, :1, None])
+        ok = ok and torch.allclose(w[:5], torch.tensor([1.0, 2 / 3, 1 / 3, 0.0, 1.0]))
+        q.put((rank, bool(ok), tuple(out.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [8, 5])
+def test_two_rank_gloo_interpolation(n_total):
+    """BASELINE config 5 host logic: one broadcast of both reference embeddings, per-segment conditioning rows built per
+    shard, all-gather of the outputs (world size 2 over gloo)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_interp, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [True, True], res
+    assert all(r[2] == (n_total, 2, 29) for r in res)
