@@ -27,6 +27,9 @@
 //            bf16 hi/lo -> swizzled shared tile -> TMA store;  the LAST block instead fuses Conv1d(128->2,k=1)+clamp
 //            and writes the fp32 [B,2,L] output directly (the 128-channel tensor of block 13 never touches HBM).
 // Taps whose shifted tile lies entirely in the zero padding are skipped by producer and issuer alike.
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -328,6 +331,8 @@ __global__ void __launch_bounds__(256) tcn_act_unpack_kernel(const uint8_t* __re
 struct TcnLayerArgs {
   int B, T, dilation, tiles_per_seg, n_tiles, n_cond;
   int pair_m;           // PAIRED kernels: sub-tiles per half block = dilation / 128
+  const float* inv_scale;   // FMT 1 (f16f8): 1 / (S * 2^11) of this layer's packed weights (tcn_f8.cu)
+  int lookahead;        // issuer waits for the next slots' barriers before the last K-step of a group (MST_TCN_LOOKAHEAD)
   const float4* film;   // this block's [n_cond][128] (bn_bias, gamma, beta, res)
   int fuse_out;         // 1 on the last block: Conv1d(128 -> n_out, k=1) + clamp fused, fp32 [B][n_out][T] written
   int n_out;
@@ -373,12 +378,21 @@ __device__ __forceinline__ TcnTile tcn_tile(int tile, const TcnLayerArgs& a) {
   return c;
 }
 
-template <int KCH, bool PAIRED>
+// FMT 0: bf16 hi/lo operands, three products per K-step (the default).
+// FMT 1: the "2 tensor units" split of tcn_f8.cu -- rows [fp16 ch 0-63 | fp16 ch 64-127 | e4m3 (x - hi) 2^11, ch 0-127 | e4m3 x, ch
+//        0-127], weights per tap [fp16 W S 2^11 ci 0-63 | ci 64-127 | e4m3 W S | e4m3 lo]; operand group 0 = the two fp16 tiles
+//        (kind::f16), group 1 = the two e4m3 tiles (kind::f8f6f4, tile i of X times tile i of W), all into ONE accumulator; the
+//        epilogue multiplies by 1 / (S 2^11).  Tensor maps are byte-typed in this mode (coordinates in bytes).
+template <int KCH, bool PAIRED, int FMT>
 __global__ void __launch_bounds__(256, 1)
 tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                       const __grid_constant__ CUtensorMap tm_xs, const __grid_constant__ CUtensorMap tm_y,
+                      const __grid_constant__ CUtensorMap tm_l8, const __grid_constant__ CUtensorMap tm_y8,
                       const TcnLayerArgs a) {
-  // tm_x / tm_w: operand boxes {KCH ch, 128 rows}, swizzle = 2*KCH bytes;  tm_xs / tm_y: epilogue boxes {64 ch, 128 rows}
+  // tm_x / tm_w: operand boxes {KCH ch, 128 rows}, swizzle = 2*KCH bytes;  tm_xs / tm_y: epilogue boxes {64 ch, 128 rows};
+  // tm_l8 / tm_y8 (FMT 1 only): epilogue boxes {64 bytes, 128 rows}, SWIZZLE_64B, for the e4m3 half planes
+  static_assert(FMT == 0 || KCH == 64, "the f16f8 format uses 128-byte operand rows");
+  constexpr int kCoord = FMT == 1 ? 2 : 1;             // byte-typed maps: column coordinates in bytes instead of bf16 elements
   constexpr int kKcPerTap = kCh / KCH;                 // 2 or 4 input-channel chunks per tap
   constexpr int kHalf = kSubRows * KCH * 2;            // bytes of one hi (or lo) operand tile: 16 KB / 8 KB
   constexpr int kSlotBytes = 2 * kHalf;
@@ -439,7 +453,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       };
       auto load_x = [&](int kc, long long ts, int b) {
         // activation columns of this chunk: plane (hi / lo) of channel half kc*KCH/64, offset inside the plane
-        const int c_hi = ((kc * KCH) / 64) * 128 + (kc * KCH) % 64, c_lo = c_hi + 64;
+        const int c_hi = (((kc * KCH) / 64) * 128 + (kc * KCH) % 64) * kCoord, c_lo = c_hi + 64 * kCoord;
         ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
         ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
         uint8_t* dst = ring + (size_t)slot * kSlotBytes;
@@ -450,16 +464,16 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const TcnTile c = tcn_tile<PAIRED>(tile, a);
         if (!c.sub0) continue;
-        if (PAIRED) {
-          // slot order per executed step (kc, j): W, [rows of sub-tile 0's tap j unless step j-1 loaded them as sub-tile 1's
-          // tap j-1], [rows of sub-tile 1's tap j]
+        if (PAIRED || FMT == 1) {
+          // operand group (channel half / MMA kind) outermost.  Slot order per executed step (kc, j): W, [rows of sub-tile 0's
+          // tap j unless step j-1 loaded them as sub-tile 1's tap j-1 (PAIRED only)], [rows of sub-tile 1's tap j]
           for (int kc = 0; kc < kKcPerTap; ++kc) {
             for (int j = 0; j < kTaps; ++j) {
               const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
               const bool live0 = tap_live(ts0, a.T), live1 = c.sub1 && tap_live(ts1, a.T);
               if (!live0 && !live1) continue;
               load_w(j, kc);
-              const bool resident = j >= 1 && c.sub1 && live0;   // ts0 == rows of sub-tile 1 at tap j-1 (same liveness)
+              const bool resident = PAIRED && j >= 1 && c.sub1 && live0;   // ts0 == rows of sub-tile 1 at tap j-1 (same liveness)
               if (live0 && !resident) load_x(kc, ts0, c.b);
               if (live1) load_x(kc, ts1, c.b);
             }
@@ -480,20 +494,57 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(kSubRows, kCh);
+    // all 32 lanes run this (warp-uniform) loop; only the tcgen05 instructions are predicated on the elected lane
+    {
+      const uint32_t leader = ptx::elect_one() ? 1u : 0u;
+      constexpr uint32_t idesc = FMT == 1 ? ptx::umma_idesc_f16_f32(kSubRows, kCh)     // format code 0 = F16 (kind::f16) = E4M3 (kind::f8f6f4)
+                                          : ptx::umma_idesc_bf16_f32(kSubRows, kCh);
       uint32_t slot = 0, phase = 0;
+      bool f8_group = false;     // FMT 1: the slots being consumed hold the e4m3 tiles (operand group 1)
       auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
       // 3-product split: (Xhi, Whi) + (Xlo, Whi) + (Xhi, Wlo), KCH/16 K16 steps per slot
-      auto issue_group = [&](uint32_t x_addr, uint32_t w_addr, uint32_t d_tmem, bool first) {
+      // The issuing thread is back-pressured by the tensor core's short MMA queue, and an mbarrier try_wait costs ~90 cycles
+      // even when the phase is already complete: waiting for the NEXT group's slots only after the last MMA of this group
+      // lets the queue drain.  With `lookahead` the wait for the next `n_pre` ring slots is done before the last K-step of a
+      // group, while three MMAs are still to be issued and the queue is full.
+      uint32_t prewaited = 0;   // ring slots from the consume pointer on whose full barrier has already been waited for
+      auto wait_cur = [&]() {
+        if (prewaited) --prewaited;
+        else ptx::mbar_wait(&bars->full[slot], phase);
+      };
+      auto prewait = [&](uint32_t n) {
+        uint32_t sl = slot, ph = phase;
+        for (uint32_t i = 0; i < n; ++i) {
+          if (i >= prewaited) ptx::mbar_wait(&bars->full[sl], ph);
+          if (++sl == kNumSlots) { sl = 0; ph ^= 1; }
+        }
+        if (n > prewaited) prewaited = n;
+      };
+      auto issue_group = [&](uint32_t x_addr, uint32_t w_addr, uint32_t d_tmem, bool first, uint32_t n_pre = 0) {
         const uint64_t xh = ptx::umma_desc_kmajor<kSwz>(x_addr), xl = ptx::umma_desc_kmajor<kSwz>(x_addr + kHalf);
         const uint64_t wh = ptx::umma_desc_kmajor<kSwz>(w_addr), wl = ptx::umma_desc_kmajor<kSwz>(w_addr + kHalf);
+        if (FMT == 1) {
+          // tile 0 of X times tile 0 of W, tile 1 times tile 1; four 32-byte K-steps each (K16 fp16 / K32 e4m3)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            if (f8_group) {
+              ptx::umma_mma_f8kind_elect(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u, leader);
+              ptx::umma_mma_f8kind_elect(d_tmem, xl + adv, wl + adv, idesc, 1u, leader);
+            } else {
+              ptx::umma_mma_f16kind_elect(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u, leader);
+              ptx::umma_mma_f16kind_elect(d_tmem, xl + adv, wl + adv, idesc, 1u, leader);
+            }
+          }
+          return;
+        }
 #pragma unroll
         for (int k = 0; k < kK16; ++k) {
           const uint64_t adv = (uint64_t)(k * 32 >> 4);  // +32 bytes along K inside the 128-byte swizzle row
-          ptx::umma_mma_f16kind(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u);
-          ptx::umma_mma_f16kind(d_tmem, xl + adv, wh + adv, idesc, 1u);
-          ptx::umma_mma_f16kind(d_tmem, xh + adv, wl + adv, idesc, 1u);
+          if (k == kK16 - 1 && n_pre) prewait(n_pre);
+          ptx::umma_mma_f16kind_elect(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u, leader);
+          ptx::umma_mma_f16kind_elect(d_tmem, xl + adv, wh + adv, idesc, 1u, leader);
+          ptx::umma_mma_f16kind_elect(d_tmem, xh + adv, wl + adv, idesc, 1u, leader);
         }
       };
       int it = 0;
@@ -505,8 +556,9 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         ptx::tc_fence_after();
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 + 0) * kCh, acc1 = tmem_base + (uint32_t)(buf * 2 + 1) * kCh;
         bool first0 = true, first1 = true;
-        if (PAIRED) {
+        if (PAIRED || FMT == 1) {
           for (int kc = 0; kc < kKcPerTap; ++kc) {
+            f8_group = FMT == 1 && kc == 1;
             int carried = -1;      // slot holding the rows sub-tile 1 used at the previous tap = rows of sub-tile 0 at this tap
             for (int j = 0; j < kTaps; ++j) {
               const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
@@ -528,7 +580,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 ptx::tc_fence_after();
                 issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc0, first0);
                 first0 = false;
-                ptx::umma_commit(&bars->empty[xs]);
+                ptx::umma_commit_elect(&bars->empty[xs], leader);
               }
               carried = -1;
               if (live1) {
@@ -539,43 +591,55 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc1, first1);
                 first1 = false;
                 // the same rows are sub-tile 0's operand at tap j+1 (ts1 = r0 + (j-6) d): keep the slot if that tap runs
-                if (j + 1 < kTaps) carried = (int)xs;
-                else ptx::umma_commit(&bars->empty[xs]);
+                if (PAIRED && j + 1 < kTaps) carried = (int)xs;
+                else ptx::umma_commit_elect(&bars->empty[xs], leader);
               }
-              ptx::umma_commit(&bars->empty[wslot]);
+              ptx::umma_commit_elect(&bars->empty[wslot], leader);
             }
           }
         } else {
+          // last live tap of this tile, and whether this CTA has another tile: a step that is followed by another one may
+          // wait ahead for that step's first two slots (every step consumes a weight slot and at least one activation slot)
+          int last_live = -1;
+          for (int j = kTaps - 1; j >= 0 && last_live < 0; --j) {
+            const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
+            if (tap_live(ts0, a.T) || (c.sub1 && tap_live(ts1, a.T))) last_live = j;
+          }
+          const bool more_tiles = tile + (int)gridDim.x < a.n_tiles;
           for (int j = 0; j < kTaps; ++j) {
             const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
             const bool live0 = tap_live(ts0, a.T), live1 = c.sub1 && tap_live(ts1, a.T);
             if (!live0 && !live1) continue;
             for (int kc = 0; kc < kKcPerTap; ++kc) {
+              const bool step_follows = a.lookahead && (kc + 1 < kKcPerTap || j < last_live || more_tiles);
+              wait_cur();
               const uint32_t wslot = slot;
-              ptx::mbar_wait(&bars->full[wslot], phase);
               const uint32_t w_addr = ptx::smem_u32(ring + (size_t)wslot * kSlotBytes);
               next();
               if (live0) {
-                ptx::mbar_wait(&bars->full[slot], phase);
-                ptx::tc_fence_after();
-                issue_group(ptx::smem_u32(ring + (size_t)slot * kSlotBytes), w_addr, acc0, first0);
-                first0 = false;
-                ptx::umma_commit(&bars->empty[slot]);
+                wait_cur();
+                const uint32_t xs = slot;
                 next();
+                ptx::tc_fence_after();
+                issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc0, first0,
+                            a.lookahead ? (live1 ? 1u : (step_follows ? 2u : 0u)) : 0u);
+                first0 = false;
+                ptx::umma_commit_elect(&bars->empty[xs], leader);
               }
               if (live1) {
-                ptx::mbar_wait(&bars->full[slot], phase);
-                ptx::tc_fence_after();
-                issue_group(ptx::smem_u32(ring + (size_t)slot * kSlotBytes), w_addr, acc1, first1);
-                first1 = false;
-                ptx::umma_commit(&bars->empty[slot]);
+                wait_cur();
+                const uint32_t xs = slot;
                 next();
+                ptx::tc_fence_after();
+                issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc1, first1, step_follows ? 2u : 0u);
+                first1 = false;
+                ptx::umma_commit_elect(&bars->empty[xs], leader);
               }
-              ptx::umma_commit(&bars->empty[wslot]);
+              ptx::umma_commit_elect(&bars->empty[wslot], leader);
             }
           }
         }
-        ptx::umma_commit(&bars->tmem_full[buf]);
+        ptx::umma_commit_elect(&bars->tmem_full[buf], leader);
         ++it;
       }
     }
@@ -603,9 +667,17 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           if (et == 0) ptx::tma_store_wait_read0();
           ptx::named_bar_sync(1, 128);
           if (et == 0) {
-            ptx::mbar_expect_tx(&bars->stage_full, kStageBytes);
-            ptx::tma_load_3d(&tm_xs, &bars->stage_full, staging, (2 * h) * 64, ts, b);              // x_in hi, ch 64h..
-            ptx::tma_load_3d(&tm_xs, &bars->stage_full, staging + 16384, (2 * h + 1) * 64, ts, b);  // x_in lo
+            if (FMT == 1) {
+              // x_in of channels 64h .. 64h+63: the fp16 plane h (16 KB, SWIZZLE_128B) and half of the e4m3 remainder plane
+              // (64 bytes per row, 8 KB, SWIZZLE_64B)
+              ptx::mbar_expect_tx(&bars->stage_full, 16384 + 8192);
+              ptx::tma_load_3d(&tm_xs, &bars->stage_full, staging, 128 * h, ts, b);
+              ptx::tma_load_3d(&tm_l8, &bars->stage_full, staging + 16384, 256 + 64 * h, ts, b);
+            } else {
+              ptx::mbar_expect_tx(&bars->stage_full, kStageBytes);
+              ptx::tma_load_3d(&tm_xs, &bars->stage_full, staging, (2 * h) * 64, ts, b);              // x_in hi, ch 64h..
+              ptx::tma_load_3d(&tm_xs, &bars->stage_full, staging + 16384, (2 * h + 1) * 64, ts, b);  // x_in lo
+            }
           }
           uint32_t acc[64];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * kCh + h * 64);
@@ -615,6 +687,75 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           ptx::mbar_wait(&bars->stage_full, stage_phase);
           stage_phase ^= 1;
           uint8_t* rowp = staging + rl * 128;
+          if constexpr (FMT == 1) {
+            // f16f8 rows: fp16 hi at staging (128-byte rows, SWIZZLE_128B), e4m3 remainder at +16 KB and e4m3 copy at +24 KB
+            // (64-byte rows, SWIZZLE_64B: 16-byte chunk index XOR ((row / 2) mod 4))
+            const float inv_scale = __ldg(a.inv_scale);
+            uint8_t* lrow = staging + 16384 + rl * 64;
+            uint8_t* hrow8 = staging + 24576 + rl * 64;
+            const int sw64 = (rl >> 1) & 3;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {     // 8 channels per iteration
+              const int off = ((c ^ (rl & 7)) << 4);
+              const int off8 = (((c >> 1) ^ sw64) << 4) + (c & 1) * 8;
+              const uint4 xh = *reinterpret_cast<const uint4*>(rowp + off);
+              const uint2 xl = *reinterpret_cast<const uint2*>(lrow + off8);
+              const uint32_t xhw[4] = {xh.x, xh.y, xh.z, xh.w};
+              const uint32_t xlw[2] = {xl.x, xl.y};
+              uint32_t oh[4], ol[2] = {0, 0}, oh8[2] = {0, 0};
+#pragma unroll
+              for (int pr = 0; pr < 4; ++pr) {
+                const int cl = c * 8 + 2 * pr;
+                const int ch = h * 64 + cl;
+                const float4 P0 = __ldg(film + ch), P1 = __ldg(film + ch + 1);
+                // x_in = fp16 hi + e4m3 lo * 2^-11  (two channels at once)
+                const float2 hif = __half22float2(*reinterpret_cast<const __half2*>(&xhw[pr]));
+                const unsigned short l8pair = (unsigned short)((xlw[pr >> 1] >> (16 * (pr & 1))) & 0xFFFFu);
+                const __half2_raw lraw = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)l8pair, __NV_E4M3);
+                const float2 lof = __half22float2(__half2(lraw));
+                const float xin0 = fmaf(lof.x, 1.f / 2048.f, hif.x), xin1 = fmaf(lof.y, 1.f / 2048.f, hif.y);
+                float u0 = fmaf(__uint_as_float(acc[cl]), inv_scale, P0.x);
+                float u1 = fmaf(__uint_as_float(acc[cl + 1]), inv_scale, P1.x);
+                u0 = u0 > 0.f ? u0 : 0.01f * u0;
+                u1 = u1 > 0.f ? u1 : 0.01f * u1;
+                u0 = fmaf(P0.y, u0, P0.z) + P0.w * xin0;
+                u1 = fmaf(P1.y, u1, P1.z) + P1.w * xin1;
+                if (a.fuse_out) {
+                  o0 = fmaf(u0, __ldg(a.out_w + ch), o0);
+                  o0 = fmaf(u1, __ldg(a.out_w + ch + 1), o0);
+                  if (a.n_out > 1) {
+                    o1 = fmaf(u0, __ldg(a.out_w + kCh + ch), o1);
+                    o1 = fmaf(u1, __ldg(a.out_w + kCh + ch + 1), o1);
+                  }
+                } else {
+                  const __half2 hi2 = __floats2half2_rn(fminf(fmaxf(u0, -65504.f), 65504.f), fminf(fmaxf(u1, -65504.f), 65504.f));
+                  const float2 hb = __half22float2(hi2);
+                  oh[pr] = *reinterpret_cast<const uint32_t*>(&hi2);
+                  const uint32_t l2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((u0 - hb.x) * 2048.f, (u1 - hb.y) * 2048.f),
+                                                                        __NV_SATFINITE, __NV_E4M3);
+                  const uint32_t h2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(u0, u1), __NV_SATFINITE, __NV_E4M3);
+                  ol[pr >> 1] |= l2 << (16 * (pr & 1));
+                  oh8[pr >> 1] |= h2 << (16 * (pr & 1));
+                }
+              }
+              if (!a.fuse_out) {
+                *reinterpret_cast<uint4*>(rowp + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                *reinterpret_cast<uint2*>(lrow + off8) = make_uint2(ol[0], ol[1]);
+                *reinterpret_cast<uint2*>(hrow8 + off8) = make_uint2(oh8[0], oh8[1]);
+              }
+            }
+            if (!a.fuse_out) {
+              ptx::fence_proxy_async_smem();
+              ptx::named_bar_sync(2, 128);
+              if (et == 0) {
+                ptx::tma_store_3d(&tm_y, staging, 128 * h, ts, b);
+                ptx::tma_store_3d(&tm_y8, staging + 16384, 256 + 64 * h, ts, b);
+                ptx::tma_store_3d(&tm_y8, staging + 24576, 384 + 64 * h, ts, b);
+                ptx::tma_store_commit();
+              }
+            }
+            continue;
+          }
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const int off = ((c ^ (rl & 7)) << 4);  // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
@@ -716,39 +857,85 @@ static int encode_w_map(CUtensorMap* m, const void* base, int kch) {
   return 0;
 }
 
+// byte-typed maps of the f16f8 format (FMT 1): activation rows of 512 bytes, box = box_bytes x 128 rows (128 -> SWIZZLE_128B operand /
+// fp16 epilogue tiles, 64 -> SWIZZLE_64B e4m3 half planes); weights: rows of 128 bytes, 4 tiles of 128 rows per tap
+static int encode_act_map_bytes(CUtensorMap* m, const void* base, int B, int T, int box_bytes) {
+  PFN_encodeTiled enc = tensor_map_encoder();
+  if (!enc) return 1;
+  cuuint64_t dims[3] = {(cuuint64_t)kRowBytes, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)kRowBytes, (cuuint64_t)T * kRowBytes};
+  cuuint32_t box[3] = {(cuuint32_t)box_bytes, (cuuint32_t)kSubRows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f16f8 activation B=%d T=%d box=%d) failed: CUresult %d", B, T, box_bytes, (int)r);
+  return 0;
+}
+static int encode_w_map_bytes(CUtensorMap* m, const void* base) {
+  PFN_encodeTiled enc = tensor_map_encoder();
+  if (!enc) return 1;
+  cuuint64_t dims[2] = {128, (cuuint64_t)kTaps * 4 * kCh};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {128, (cuuint32_t)kCh};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f16f8 weights) failed: CUresult %d", (int)r);
+  return 0;
+}
+
 // one dilated block (n >= 1): act_in -> act_out, or -> fp32 `out` when fuse_out
 static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, const TcnPacked& L, int n,
                              const uint8_t* act_in, uint8_t* act_out, const float* film, int n_cond, int B, int T,
                              bool fuse_out, float* out, cudaStream_t st) {
   const long long d = block_dilation(cfg, n);
   MST_CHECK(7 * d + kTileRows < (1ll << 31) - T, "tcn: dilation %lld too large", d);
-  if (tcn_mode() == 1)
+  if (tcn_mode() == 1 && tcn_pipe() == 2)
     return tcn_f8_launch_block(d, packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer,
                                reinterpret_cast<const float*>(packed + L.f8_scale) + 2 * n, act_in, act_out,
                                film + (size_t)n * n_cond * kCh * 4, n_cond, B, T, fuse_out, cfg->n_outputs,
                                reinterpret_cast<const float*>(packed + L.out_w),
                                reinterpret_cast<const float*>(packed + L.out_b), out, st);
-  const int kch = tcn_kchunk();
-  if (tcn_pipe() == 2 && kch == 64)
+  const bool f8 = tcn_mode() == 1;     // f16f8 operands through the single-ring kernel below (FMT 1)
+  const int kch = f8 ? 64 : tcn_kchunk();
+  if (!f8 && tcn_pipe() == 2 && kch == 64)
     return tcn_pipe2_launch_block(d, packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer, act_in, act_out,
                                   film + (size_t)n * n_cond * kCh * 4, n_cond, B, T, fuse_out, cfg->n_outputs,
                                   reinterpret_cast<const float*>(packed + L.out_w),
                                   reinterpret_cast<const float*>(packed + L.out_b), out, st);
-  CUtensorMap tm_x, tm_w, tm_xs, tm_y;
-  if (encode_act_map(&tm_x, act_in, B, T, kch)) return 1;
-  if (encode_act_map(&tm_xs, act_in, B, T, 64)) return 1;
-  if (encode_act_map(&tm_y, fuse_out ? act_in : act_out, B, T, 64)) return 1;
-  if (encode_w_map(&tm_w, packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer, kch)) return 1;
+  CUtensorMap tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8;
+  const uint8_t* w_layer = packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer;
+  if (f8) {
+    if (encode_act_map_bytes(&tm_x, act_in, B, T, 128)) return 1;
+    tm_xs = tm_x;
+    if (encode_act_map_bytes(&tm_y, fuse_out ? act_in : act_out, B, T, 128)) return 1;
+    if (encode_act_map_bytes(&tm_l8, act_in, B, T, 64)) return 1;
+    if (encode_act_map_bytes(&tm_y8, fuse_out ? act_in : act_out, B, T, 64)) return 1;
+    if (encode_w_map_bytes(&tm_w, w_layer)) return 1;
+  } else {
+    if (encode_act_map(&tm_x, act_in, B, T, kch)) return 1;
+    if (encode_act_map(&tm_xs, act_in, B, T, 64)) return 1;
+    if (encode_act_map(&tm_y, fuse_out ? act_in : act_out, B, T, 64)) return 1;
+    if (encode_w_map(&tm_w, w_layer, kch)) return 1;
+    tm_l8 = tm_xs;      // unused in this format
+    tm_y8 = tm_y;
+  }
   TcnLayerArgs a;
+  a.inv_scale = reinterpret_cast<const float*>(packed + L.f8_scale) + 2 * n;
   a.B = B; a.T = T; a.dilation = (int)d;
-  // MST_TCN_PAIRED=1: paired sub-tiles (tcn_tile<true>) for dilations that are a multiple of 128.  Measured (ncu, isolated
-  // launches, blocks 7-13): L2->SM bytes 100.9 -> 70 GB per launch, SM clock under the power cap 1.48 -> 1.58 GHz, but
-  // tensor-pipe activity per cycle 78.1 -> 74.3 %, so 8.88 -> 8.73 ms isolated and no difference in a sustained forward
-  // (9.75-9.97 ms/launch either way): parity-green, off by default.
+  // Paired sub-tiles (tcn_tile<true>) for dilations that are a multiple of 128; MST_TCN_PAIRED=0 switches them off (A/B).
+  // L2->SM bytes 100.9 -> 70 GB per launch.  With the single-thread issuer this bought nothing (tensor activity 78 -> 74 %);
+  // with the warp-convergent issuer it is 8.63 -> 8.20 ms on isolated launches (tensor pipe 82.8 -> 85.9 %) and 9.86 -> 9.60
+  // ms per launch in a sustained forward.
   static int paired_env = -1;
-  if (paired_env < 0) { const char* e = getenv("MST_TCN_PAIRED"); paired_env = (e && atoi(e) == 1) ? 1 : 0; }
+  if (paired_env < 0) { const char* e = getenv("MST_TCN_PAIRED"); paired_env = (e && atoi(e) == 0) ? 0 : 1; }
   const bool paired = paired_env && kch == 64 && d >= kSubRows && d % kSubRows == 0;
   a.pair_m = paired ? (int)(d / kSubRows) : 1;
+  static int lookahead_env = -1;
+  if (lookahead_env < 0) { const char* e = getenv("MST_TCN_LOOKAHEAD"); lookahead_env = (e && atoi(e) == 1) ? 1 : 0; }
+  a.lookahead = lookahead_env;
   a.tiles_per_seg = paired ? (int)(((T + 2 * d - 1) / (2 * d)) * a.pair_m) : cdiv(T, kTileRows);
   a.n_tiles = B * a.tiles_per_seg;
   a.n_cond = n_cond;
@@ -759,16 +946,18 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   a.out_b = reinterpret_cast<const float*>(packed + L.out_b);
   a.out = out;
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-  if (paired) {
-    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));
-    tcn_block_umma_kernel<64, true><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, a);
-  } else if (kch == 64) {
-    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));
-    tcn_block_umma_kernel<64, false><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, a);
-  } else {
-    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));
-    tcn_block_umma_kernel<32, false><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, a);
-  }
+#define MST_TCN_LAUNCH(KCH_, PAIRED_, FMT_)                                                                                     \
+  do {                                                                                                                         \
+    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<KCH_, PAIRED_, FMT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     (int)kTcnSmemBytes));                                                                     \
+    tcn_block_umma_kernel<KCH_, PAIRED_, FMT_><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8, a);    \
+  } while (0)
+  if (f8 && paired) MST_TCN_LAUNCH(64, true, 1);
+  else if (f8) MST_TCN_LAUNCH(64, false, 1);
+  else if (paired) MST_TCN_LAUNCH(64, true, 0);
+  else if (kch == 64) MST_TCN_LAUNCH(64, false, 0);
+  else MST_TCN_LAUNCH(32, false, 0);
+#undef MST_TCN_LAUNCH
   return launch_ok("tcn_block_umma_kernel");
 }
 

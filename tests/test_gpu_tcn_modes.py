@@ -12,7 +12,10 @@ VARIANTS = [
     {"MST_TCN_PRECISION": "f16f8"},
     {"MST_TCN_PIPE": "2"},
     {"MST_TCN_KCHUNK": "32"},
-    {"MST_TCN_PAIRED": "1"},
+    {"MST_TCN_PAIRED": "0"},
+    {"MST_TCN_PRECISION": "f16f8", "MST_TCN_PAIRED": "0"},
+    {"MST_TCN_PRECISION": "f16f8", "MST_TCN_PIPE": "2"},
+    {"MST_TCN_LOOKAHEAD": "1", "MST_TCN_PAIRED": "0"},
 ]
 
 

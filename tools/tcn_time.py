@@ -18,6 +18,6 @@ with torch.no_grad():
         tcn.forward_layers(x, c, note)
 torch.cuda.synchronize()
 d = [ev[i].elapsed_time(ev[i + 1]) for i in range(0, len(ev), 2)]
-print({k: os.environ.get(k) for k in ("MST_TCN_PRECISION", "MST_TCN_PIPE", "MST_TCN_MULTICAST", "MST_TCN_DBG", "MST_TCN_PAIRED")}, "ms/launch mean %.3f min %.3f max %.3f" % (sum(d) / len(d), min(d), max(d)))
+print({k: os.environ.get(k) for k in ("MST_TCN_PRECISION", "MST_TCN_PIPE", "MST_TCN_MULTICAST", "MST_TCN_DBG", "MST_TCN_PAIRED", "MST_TCN_LOOKAHEAD")}, "ms/launch mean %.3f min %.3f max %.3f" % (sum(d) / len(d), min(d), max(d)))
 n = len(d) // 2
 print("per block (dilation 2^n, n=1..13), ms:", " ".join("%.2f" % ((d[i] + d[i + n]) / 2) for i in range(n)))
