@@ -301,17 +301,23 @@ def main():
     achieved = flops_per_launch / (umma_ms * 1e-3) / 1e12
     n_umma = 13
     share = n_umma * umma_ms / ms_step
+    f8 = os.environ.get("MST_TCN_PRECISION", "f16f8") not in ("bf16x3", "bf16")
+    units = 2 if f8 else 3     # tensor-pipe time per algorithmic MMA in bf16-MMA equivalents (an e4m3 MMA runs at twice the rate)
     roofline = {"kernel": "tcn_block_umma_kernel", "bound": "tensor", "achieved": achieved,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
                 "peak_source": f"{pk['source']} bf16 dense (sustained: kernel timed inside a long step)",
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
                 # this command (profiles/r01_summary.md section 2); = 1.00x the algorithmic activation bytes
-                "traffic": 8.555e9 if (B == BATCH_PER_GPU and L == SEG_LEN) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu capture of this command (profiles/)
+                "traffic": 8.6e9 if (B == BATCH_PER_GPU and L == SEG_LEN) else None,
                 "traffic_algorithmic": 2.0 * B * L * 512, "ms_per_launch": umma_ms, "launches_per_step": n_umma, "share_of_step": share,
                 "algorithmic_flop_per_launch": flops_per_launch,
-                "note": "fp32-grade parity needs the 3-product bf16 split: tensor-pipe work is 3x the algorithmic FLOPs, "
-                        "so frac <= 0.333 by construction; tensor_pipe_frac = 3*frac",
-                "tensor_pipe_frac": 3 * achieved / pk["bf16_tflops_sustained"]}
+                "note": ("fp32-grade parity needs split operands: fp16 main product + two e4m3 correction products (each at twice "
+                         "the bf16 rate) = 2 bf16-MMA equivalents per algorithmic MMA, so frac <= 0.5 by construction; "
+                         "tensor_pipe_frac = 2*frac") if f8 else
+                        ("fp32-grade parity needs the 3-product bf16 split: tensor-pipe work is 3x the algorithmic FLOPs, "
+                         "so frac <= 0.333 by construction; tensor_pipe_frac = 3*frac"),
+                "tensor_pipe_frac": units * achieved / pk["bf16_tflops_sustained"]}
 
     # ---- extra: BASELINE config 3 (FX chain only, B=256 random-parameter segments) on rank 0 ----
     fx_extra = None
@@ -365,7 +371,10 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operand pairs on tcgen05, fp32 accumulate; encoder blocks 0-2 fp32)",
+                "vs_baseline": None,
+                "dtype": ("f16+2xe4m3 (TCN: fp16 main product + two e4m3 correction products on tcgen05, fp32 accumulate; encoder: "
+                          "split-bf16 x3 on tcgen05, blocks 0-2 fp32)") if f8 else
+                         "bf16x3 (split-bf16 operand pairs on tcgen05, fp32 accumulate; encoder blocks 0-2 fp32)",
                 "data": "synthetic",
                 "config": {"workload": "configs[1]: FXencoder+MixFXcloner full forward, batch=32 segments of 262144 "
                                        "stereo samples per GPU", "segment_length": L, "batch_per_gpu": B,

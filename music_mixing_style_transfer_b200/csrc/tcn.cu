@@ -61,13 +61,14 @@ struct TcnPacked {
   size_t w0, wumma, bn_bias, res, film_w, film_b, out_w, out_b, f8_scale, total;
 };
 
-// Operand-split mode of blocks >= 1: 0 = bf16 x 3 products (default), 1 = fp16 + 2 x e4m3 corrections (tcn_f8.cu).
-// Read once per process so that weight packing and launches agree.
+// Operand-split mode of blocks >= 1: 1 = fp16 + 2 x e4m3 corrections ("f16f8", 2 tensor units per algorithmic MMA; the default
+// since the warp-convergent issuer made it the faster one: 7.6 vs 9.2 ms per launch), 0 = bf16 x 3 products
+// (MST_TCN_PRECISION=bf16x3).  Read once per process so that weight packing and launches agree.
 static int tcn_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MST_TCN_PRECISION");
-    v = (e && strcmp(e, "f16f8") == 0) ? 1 : 0;
+    v = (e && (strcmp(e, "bf16x3") == 0 || strcmp(e, "bf16") == 0)) ? 0 : 1;
   }
   return v;
 }
@@ -332,7 +333,6 @@ struct TcnLayerArgs {
   int B, T, dilation, tiles_per_seg, n_tiles, n_cond;
   int pair_m;           // PAIRED kernels: sub-tiles per half block = dilation / 128
   const float* inv_scale;   // FMT 1 (f16f8): 1 / (S * 2^11) of this layer's packed weights (tcn_f8.cu)
-  int lookahead;        // issuer waits for the next slots' barriers before the last K-step of a group (MST_TCN_LOOKAHEAD)
   const float4* film;   // this block's [n_cond][128] (bn_bias, gamma, beta, res)
   int fuse_out;         // 1 on the last block: Conv1d(128 -> n_out, k=1) + clamp fused, fp32 [B][n_out][T] written
   int n_out;
@@ -438,6 +438,8 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
+    // one lane only: this warp spends most of its time polling `empty` barriers, and 32 polling lanes slow the issuer's
+    // barrier traffic down (measured: tensor-pipe activity 76 -> 68 % with a warp-convergent producer)
     if (lane == 0) {
       uint32_t slot = 0, phase = 0;
       auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
@@ -503,35 +505,22 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       bool f8_group = false;     // FMT 1: the slots being consumed hold the e4m3 tiles (operand group 1)
       auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
       // 3-product split: (Xhi, Whi) + (Xlo, Whi) + (Xhi, Wlo), KCH/16 K16 steps per slot
-      // The issuing thread is back-pressured by the tensor core's short MMA queue, and an mbarrier try_wait costs ~90 cycles
-      // even when the phase is already complete: waiting for the NEXT group's slots only after the last MMA of this group
-      // lets the queue drain.  With `lookahead` the wait for the next `n_pre` ring slots is done before the last K-step of a
-      // group, while three MMAs are still to be issued and the queue is full.
-      uint32_t prewaited = 0;   // ring slots from the consume pointer on whose full barrier has already been waited for
-      auto wait_cur = [&]() {
-        if (prewaited) --prewaited;
-        else ptx::mbar_wait(&bars->full[slot], phase);
-      };
-      auto prewait = [&](uint32_t n) {
-        uint32_t sl = slot, ph = phase;
-        for (uint32_t i = 0; i < n; ++i) {
-          if (i >= prewaited) ptx::mbar_wait(&bars->full[sl], ph);
-          if (++sl == kNumSlots) { sl = 0; ph ^= 1; }
-        }
-        if (n > prewaited) prewaited = n;
-      };
-      auto issue_group = [&](uint32_t x_addr, uint32_t w_addr, uint32_t d_tmem, bool first, uint32_t n_pre = 0) {
+      auto issue_group = [&](uint32_t x_addr, uint32_t w_addr, uint32_t d_tmem, bool first) {
         const uint64_t xh = ptx::umma_desc_kmajor<kSwz>(x_addr), xl = ptx::umma_desc_kmajor<kSwz>(x_addr + kHalf);
         const uint64_t wh = ptx::umma_desc_kmajor<kSwz>(w_addr), wl = ptx::umma_desc_kmajor<kSwz>(w_addr + kHalf);
         if (FMT == 1) {
           // tile 0 of X times tile 0 of W, tile 1 times tile 1; four 32-byte K-steps each (K16 fp16 / K32 e4m3)
+          if (f8_group) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            if (f8_group) {
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);
               ptx::umma_mma_f8kind_elect(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u, leader);
               ptx::umma_mma_f8kind_elect(d_tmem, xl + adv, wl + adv, idesc, 1u, leader);
-            } else {
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);
               ptx::umma_mma_f16kind_elect(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u, leader);
               ptx::umma_mma_f16kind_elect(d_tmem, xl + adv, wl + adv, idesc, 1u, leader);
             }
@@ -541,7 +530,6 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #pragma unroll
         for (int k = 0; k < kK16; ++k) {
           const uint64_t adv = (uint64_t)(k * 32 >> 4);  // +32 bytes along K inside the 128-byte swizzle row
-          if (k == kK16 - 1 && n_pre) prewait(n_pre);
           ptx::umma_mma_f16kind_elect(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u, leader);
           ptx::umma_mma_f16kind_elect(d_tmem, xl + adv, wh + adv, idesc, 1u, leader);
           ptx::umma_mma_f16kind_elect(d_tmem, xh + adv, wl + adv, idesc, 1u, leader);
@@ -598,40 +586,30 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             }
           }
         } else {
-          // last live tap of this tile, and whether this CTA has another tile: a step that is followed by another one may
-          // wait ahead for that step's first two slots (every step consumes a weight slot and at least one activation slot)
-          int last_live = -1;
-          for (int j = kTaps - 1; j >= 0 && last_live < 0; --j) {
-            const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
-            if (tap_live(ts0, a.T) || (c.sub1 && tap_live(ts1, a.T))) last_live = j;
-          }
-          const bool more_tiles = tile + (int)gridDim.x < a.n_tiles;
           for (int j = 0; j < kTaps; ++j) {
             const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
             const bool live0 = tap_live(ts0, a.T), live1 = c.sub1 && tap_live(ts1, a.T);
             if (!live0 && !live1) continue;
             for (int kc = 0; kc < kKcPerTap; ++kc) {
-              const bool step_follows = a.lookahead && (kc + 1 < kKcPerTap || j < last_live || more_tiles);
-              wait_cur();
               const uint32_t wslot = slot;
+              ptx::mbar_wait(&bars->full[wslot], phase);
               const uint32_t w_addr = ptx::smem_u32(ring + (size_t)wslot * kSlotBytes);
               next();
               if (live0) {
-                wait_cur();
                 const uint32_t xs = slot;
+                ptx::mbar_wait(&bars->full[xs], phase);
                 next();
                 ptx::tc_fence_after();
-                issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc0, first0,
-                            a.lookahead ? (live1 ? 1u : (step_follows ? 2u : 0u)) : 0u);
+                issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc0, first0);
                 first0 = false;
                 ptx::umma_commit_elect(&bars->empty[xs], leader);
               }
               if (live1) {
-                wait_cur();
                 const uint32_t xs = slot;
+                ptx::mbar_wait(&bars->full[xs], phase);
                 next();
                 ptx::tc_fence_after();
-                issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc1, first1, step_follows ? 2u : 0u);
+                issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc1, first1);
                 first1 = false;
                 ptx::umma_commit_elect(&bars->empty[xs], leader);
               }
@@ -933,9 +911,6 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   if (paired_env < 0) { const char* e = getenv("MST_TCN_PAIRED"); paired_env = (e && atoi(e) == 0) ? 0 : 1; }
   const bool paired = paired_env && kch == 64 && d >= kSubRows && d % kSubRows == 0;
   a.pair_m = paired ? (int)(d / kSubRows) : 1;
-  static int lookahead_env = -1;
-  if (lookahead_env < 0) { const char* e = getenv("MST_TCN_LOOKAHEAD"); lookahead_env = (e && atoi(e) == 1) ? 1 : 0; }
-  a.lookahead = lookahead_env;
   a.tiles_per_seg = paired ? (int)(((T + 2 * d - 1) / (2 * d)) * a.pair_m) : cdiv(T, kTileRows);
   a.n_tiles = B * a.tiles_per_seg;
   a.n_cond = n_cond;

@@ -9,13 +9,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 VARIANTS = [
-    {"MST_TCN_PRECISION": "f16f8"},
-    {"MST_TCN_PIPE": "2"},
-    {"MST_TCN_KCHUNK": "32"},
-    {"MST_TCN_PAIRED": "0"},
-    {"MST_TCN_PRECISION": "f16f8", "MST_TCN_PAIRED": "0"},
-    {"MST_TCN_PRECISION": "f16f8", "MST_TCN_PIPE": "2"},
-    {"MST_TCN_LOOKAHEAD": "1", "MST_TCN_PAIRED": "0"},
+    {"MST_TCN_PAIRED": "0"},                                   # f16f8 (default precision), plain 256-row tiles
+    {"MST_TCN_PRECISION": "f16f8", "MST_TCN_PIPE": "2"},       # f16f8 through the dual-ring kernel of tcn_f8.cu
+    {"MST_TCN_PRECISION": "bf16x3"},                           # three bf16 products, paired sub-tiles
+    {"MST_TCN_PRECISION": "bf16x3", "MST_TCN_PAIRED": "0"},
+    {"MST_TCN_PRECISION": "bf16x3", "MST_TCN_PIPE": "2"},
+    {"MST_TCN_PRECISION": "bf16x3", "MST_TCN_KCHUNK": "32"},
 ]
 
 
