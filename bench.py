@@ -308,8 +308,10 @@ def main():
                 "peak_source": f"{pk['source']} bf16 dense (sustained: kernel timed inside a long step)",
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
                 # this command (profiles/r01_summary.md section 2); = 1.00x the algorithmic activation bytes
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu capture of this command (profiles/)
-                "traffic": 8.6e9 if (B == BATCH_PER_GPU and L == SEG_LEN) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum, mean over the 13 launches of a step, from the committed ncu
+                # captures of this workload (profiles/r01g_tcn_ncu.csv for blocks 1-6, r01g_tcn_ncu_blkfast.csv for blocks 7-13):
+                # 5.10 GB read + 3.93 GB written = 1.05x the algorithmic activation bytes
+                "traffic": 9.03e9 if (B == BATCH_PER_GPU and L == SEG_LEN and f8) else None,
                 "traffic_algorithmic": 2.0 * B * L * 512, "ms_per_launch": umma_ms, "launches_per_step": n_umma, "share_of_step": share,
                 "algorithmic_flop_per_launch": flops_per_launch,
                 "note": ("fp32-grade parity needs split operands: fp16 main product + two e4m3 correction products (each at twice "

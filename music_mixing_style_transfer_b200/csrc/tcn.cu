@@ -366,7 +366,11 @@ __device__ __forceinline__ TcnTile tcn_tile(int tile, const TcnLayerArgs& a) {
   c.b = tile / a.tiles_per_seg;
   const int p = tile - c.b * a.tiles_per_seg;
   if (PAIRED) {
-    const int blk = p / a.pair_m, i = p - blk * a.pair_m;
+    // block index fastest: consecutive work items (= the CTAs of one wave) are 2d rows apart and share 14 of their 16 tap
+    // tiles, so a wave's working set stays in L2 also for the large dilations (with i fastest the 148 x 16 tiles of a wave are
+    // all distinct at d >= 2048: 150 MB, DRAM reads up to 3x the algorithmic bytes)
+    const int nblk = a.tiles_per_seg / a.pair_m;
+    const int i = p / nblk, blk = p - i * nblk;
     c.r0 = (long long)blk * 2 * a.dilation + (long long)i * kSubRows;
     c.r1 = c.r0 + a.dilation;
   } else {
