@@ -18,10 +18,13 @@
 // ---- the hot kernel (blocks 1..13, 98 % of all FLOPs) ---------------------------------------------------------------
 // tcn_block_umma_kernel: im2col-free dilated implicit GEMM on the 5th-gen tensor cores.
 //   D[t, co] = sum_{tap, ci} X[t + (tap-7)*d, ci] * W[tap][co][ci]        M = 128 time rows, N = 128 co, K = 15*128
-// fp32-grade accuracy from bf16 tensor cores via the 3-product split  Xhi*Whi + Xlo*Whi + Xhi*Wlo  (fp32 accumulate in
-// TMEM; the dropped lo*lo term is ~2^-18 relative).  Persistent, warp-specialised, one CTA per SM:
-//   warp 0   TMA producer: streams 32 KB slots (W tap-chunk, X sub-tile hi+lo) through a 6-deep mbarrier ring
-//   warp 1   MMA issuer: one thread issues tcgen05.mma (128x128x16) x 12 per slot pair, commits slots back
+// fp32-grade accuracy from the tensor cores via split operands: by default fp16(X)*fp16(W) + two e4m3 correction products
+// (FMT 1, the format of tcn_f8.cu: 2 bf16-MMA equivalents per algorithmic MMA), or the 3-product bf16 split
+// Xhi*Whi + Xlo*Whi + Xhi*Wlo (FMT 0, MST_TCN_PRECISION=bf16x3); fp32 accumulate in TMEM.  Persistent, warp-specialised,
+// one CTA per SM:
+//   warp 0   TMA producer (one lane): streams 32 KB slots (W tap-group, X sub-tile) through a 6-deep mbarrier ring
+//   warp 1   MMA issuer: the whole warp runs the uniform loop, the tcgen05.mma / commit instructions are predicated on the
+//            elected lane -> straight UTCHMMA sequences from uniform registers (8 or 12 MMAs per slot pair)
 //   warp 2   TMEM allocator (512 columns = 2 tiles x 2 sub-tiles x 128 fp32 columns -> double-buffered accumulators)
 //   warps 4-7 epilogue: tcgen05.ld -> +BN bias -> LeakyReLU -> FiLM -> + res*x_in (x_in tile TMA-loaded) -> split to
 //            bf16 hi/lo -> swizzled shared tile -> TMA store;  the LAST block instead fuses Conv1d(128->2,k=1)+clamp
