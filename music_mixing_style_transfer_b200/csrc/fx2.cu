@@ -7,7 +7,7 @@
 //   MidSideImager.process                           :965-992
 //   Gain.process                                    :1038-1051
 //
-// Why a second generation: ncu on fx.cu (profiles/r01_fx_v1_ncu.md) shows 124 thread-instructions per sample in each of
+// Why a second generation: ncu on fx.cu (profiles/r01f_summary.md, r01f_fx_v1_ncu_full.csv) shows 124 thread-instructions per sample in each of
 // the EQ and compressor kernels, 22-25 % of the warp slots occupied and 0.7 eligible warps per scheduler cycle -- both
 // kernels are instruction- and latency-bound at ~1 TB/s.  This file keeps the time-parallel algorithms (chunked
 // recurrences + block scans, compressor pattern fixed point) and changes the arithmetic and the geometry:
@@ -18,8 +18,9 @@
 //         y = b0 x + u;   u' = -(1 + a1) y + (b0 + b1) x + beta;   beta' = beta + (b0+b1+b2) x - (1+a1+a2) y
 //     which is algebraically the same filter (5 FMAs per sample) but keeps the ill-conditioned "slope" direction of a
 //     low-frequency section (poles near z = 1) in its own small-magnitude state, so plain float32 is accurate to
-//     ~1e-7 RMS even for a 30 Hz shelf (numpy emulation + tests) -- no float64 in the per-sample work at all.
-//     Only the per-chunk end states, their scan and the tile carry are float64.
+//     ~1e-7 RMS even for a 30 Hz shelf (numpy emulation + tests) -- no float64 in the signal path at all: the per-chunk end
+//     states, their scan and the tile carry are float32 too (packed over the channel pair); only the per-segment sums of
+//     squares are accumulated in float64.
 //   * Every thread runs TWO independent 16-frame chunks (ILP 2) -> 32 frames x 2 channels per thread, 8192-frame tiles,
 //     so the scan and the five block barriers are amortised over 4x more samples per thread than in fx.cu.
 //   * Compressor: gain computer on MUFU lg2 (x_l = max(0, (x_g - T)(1 - 1/R)) in one FMA + max), smoother step
