@@ -131,7 +131,10 @@ enc_conv_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // warp-convergent MMA issue (see umma_mma_f16kind_elect in sm100_ptx.cuh): all lanes run the uniform loop, the tcgen05
+    // instructions are predicated on the elected lane, so ptxas emits straight UTCHMMA sequences
+    {
+      const uint32_t leader = ptx::elect_one() ? 1u : 0u;
       const uint32_t idesc = ptx::umma_idesc_bf16_f32(128, a.nt);
       uint32_t slot = 0, phase = 0;
       auto next = [&]() { if (++slot == kEncSlots) { slot = 0; phase ^= 1; } };
@@ -141,9 +144,9 @@ enc_conv_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t adv = (uint64_t)(k * 32 >> 4);
-          ptx::umma_mma_f16kind(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u);
-          ptx::umma_mma_f16kind(d_tmem, xl + adv, wh + adv, idesc, 1u);
-          ptx::umma_mma_f16kind(d_tmem, xh + adv, wl + adv, idesc, 1u);
+          ptx::umma_mma_f16kind_elect(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u, leader);
+          ptx::umma_mma_f16kind_elect(d_tmem, xl + adv, wh + adv, idesc, 1u, leader);
+          ptx::umma_mma_f16kind_elect(d_tmem, xh + adv, wl + adv, idesc, 1u, leader);
         }
       };
       uint32_t gtotal = 0;   // accumulation groups issued so far (buffer = gtotal & 1)
@@ -162,11 +165,11 @@ enc_conv_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           ptx::mbar_wait(&bars->full[slot], phase);
           ptx::tc_fence_after();
           issue_group(ptx::smem_u32(ring + (size_t)slot * kEncSlotBytes), w_addr, tmem_base + buf * 128u, group_start);
-          ptx::umma_commit(&bars->empty[slot]);
+          ptx::umma_commit_elect(&bars->empty[slot], leader);
           next();
-          ptx::umma_commit(&bars->empty[wslot]);
+          ptx::umma_commit_elect(&bars->empty[wslot], leader);
           if ((s % kFlushSteps) == kFlushSteps - 1 || s == n_steps - 1) {
-            ptx::umma_commit(&bars->tmem_full[buf]);
+            ptx::umma_commit_elect(&bars->tmem_full[buf], leader);
             ++gtotal;
           }
         }
