@@ -355,6 +355,42 @@ def main():
         except Exception as exc:  # the headline line must survive a failure of the extra leg
             fx_extra = {"error": repr(exc)}
 
+    # ---- extra: the sample-format kernels either side of the forward, HBM-bound streams, on rank 0 ----
+    io_extra = None
+    if rank == 0:
+        try:
+            from music_mixing_style_transfer_b200 import wav_io
+            n_fr = 2 * B * L                                     # two batches worth of stereo frames: every buffer set > the 126 MB L2
+            gen = torch.Generator(device=device)
+            gen.manual_seed(4321)
+            pcm = torch.randint(-32768, 32768, (n_fr, 2), generator=gen, device=device, dtype=torch.int32).to(torch.int16)
+            dec = torch.empty(2, n_fr, dtype=torch.float32, device=device)
+            stems = (torch.randn(4, 2, n_fr // 2, generator=gen, device=device) * 0.3)
+            for _ in range(3):
+                wav_io.decode_pcm(pcm, device, out=dec)
+                wav_io.encode_mix_pcm16(stems)
+            g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            g0.record()
+            for _ in range(10):
+                wav_io.decode_pcm(pcm, device, out=dec)
+            g1.record()
+            for _ in range(10):
+                wav_io.encode_mix_pcm16(stems)
+            g2.record()
+            torch.cuda.synchronize()
+            dec_ms, enc_ms = g0.elapsed_time(g1) / 10, g1.elapsed_time(g2) / 10
+            dec_bytes = n_fr * (4 + 8)                           # int16 stereo in, fp32 planar out
+            enc_bytes = (n_fr // 2) * (4 * 8 + 4)                # 4 fp32 stereo stems in, int16 stereo out
+            io_extra = {"workload": "8f-1: PCM16 decode of 2 batches of stereo frames (201 MB in + out); remix of 4 stems of one batch "
+                                    "+ PCM_16 quantise (302 MB); buffers exceed the L2",
+                        "decode": {"ms": dec_ms, "GB/s": dec_bytes / (dec_ms * 1e-3) / 1e9,
+                                   "frac_of_hbm_peak": dec_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
+                        "encode_mix": {"ms": enc_ms, "GB/s": enc_bytes / (enc_ms * 1e-3) / 1e9,
+                                       "frac_of_hbm_peak": enc_bytes / (enc_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}}
+            del pcm, dec, stems
+        except Exception as exc:
+            io_extra = {"error": repr(exc)}
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         cores = pick_cpu_threads()
@@ -388,7 +424,7 @@ def main():
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": args.steps * (25 + 15) if rank == 0 else args.steps * 15,
                 "gpu_launches_per_step": {"encoder (24 conv + 1 pool, rank 0)": 25, "tcn (film + block0 + 13 umma)": 15},
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": {"fx_chain_config3": fx_extra},
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": {"fx_chain_config3": fx_extra, "wav_io": io_extra},
                 "tflops_algorithmic": (TCN_FLOP_PER_SAMPLE * L * B + ENC_FLOP_PER_SEG * B) / (ms_step * 1e-3) / 1e12}
         print(json.dumps(line), flush=True)
     if world > 1:
