@@ -183,3 +183,60 @@ def test_two_rank_gloo_interpolation(n_total):
         p.join(timeout=60)
     assert [r[1] for r in res] == [True, True], res
     assert all(r[2] == (n_total, 2, 29) for r in res)
+
+
+def test_wav_header_checks_match_reference_loader(tmp_path):
+    """wav_io.read_wav_pcm keeps load_wav_segment's checks (loader_utils.py:52-53, 62-63): ValueError for a wrong sample rate
+    and for bit depths other than 16 / 32, raw interleaved PCM otherwise (no conversion on the host)."""
+    import wave
+    import numpy as np
+    from music_mixing_style_transfer_b200 import wav_io
+    x = (np.arange(2000, dtype=np.int64) * 37 % 65536 - 32768).astype("<i2").reshape(-1, 2)
+    p16 = str(tmp_path / "a16.wav")
+    with wave.open(p16, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(44100); w.writeframes(x.tobytes())
+    got = wav_io.read_wav_pcm(p16)
+    assert got.dtype == np.dtype("<i2") and got.shape == (1000, 2) and np.array_equal(got, x)
+    assert np.array_equal(wav_io.read_wav_pcm(p16, start_point=10, duration=5), x[10:15])
+    with pytest.raises(ValueError, match="sample rate"):
+        wav_io.read_wav_pcm(p16, sample_rate=48000)
+    p8 = str(tmp_path / "a8.wav")
+    with wave.open(p8, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(1); w.setframerate(44100); w.writeframes(bytes(range(200)))
+    with pytest.raises(ValueError, match="bit depth"):
+        wav_io.read_wav_pcm(p8)
+    p32 = str(tmp_path / "a32.wav")
+    y = (np.arange(300, dtype=np.int64) * 7919 % (2 ** 32) - 2 ** 31).astype("<i4").reshape(-1, 1)
+    with wave.open(p32, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(4); w.setframerate(44100); w.writeframes(y.tobytes())
+    got = wav_io.read_wav_pcm(p32)
+    assert got.dtype == np.dtype("<i4") and np.array_equal(got, y)
+    # no CPU path for the conversion itself
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            wav_io.decode_pcm(x)
+
+
+def test_feature_extraction_segmentation_matches_oracle():
+    """inference/feature_extraction.py:114-140 -- same padding quirk as the style-transfer entry (a full extra zero segment
+    when the length is an exact multiple), checked on the host against the oracle restatement."""
+    from music_mixing_style_transfer_b200.inference.feature_extraction import FXencoder_Inference
+    from oracle import networks_oracle as O
+    obj = FXencoder_Inference.__new__(FXencoder_Inference)
+    obj.segment_length, obj.batch_size = 250, 3
+    for T in (250, 1000, 1001, 1749):
+        song = torch.randn(2, T)
+        ours = obj.batchwise_segmentization(song, "s")
+        ref = O.batchwise_segmentization(song, 250, 3)
+        assert len(ours) == len(ref) and all(torch.equal(a, b) for a, b in zip(ours, ref)), T
+        assert sum(b.shape[0] for b in ours) == T // 250 + 1
+    with pytest.raises(AssertionError):
+        obj.batchwise_segmentization(torch.randn(2, 100), "s")
+
+
+def test_interpolation_weights():
+    w = shard.interpolation_weights(64, 16)
+    assert w.shape == (64,) and float(w[0]) == 1.0 and float(w[15]) == 0.0 and float(w[16]) == 1.0
+    assert torch.allclose(w[:16], (15 - torch.arange(16).float()) / 15)      # style_transfer.py:250 per segment
+    with pytest.raises(ValueError):
+        shard.interpolation_weights(4, 1)
