@@ -141,3 +141,13 @@ def test_io_oracle_encode_known_answers():
     assert out[:5, 0].tolist() == [0, 2, -2, 32767, -32768]
     assert out[5, 0] == int(np.rint(float(np.float32(1e-3) + np.float32(2e-3)) * 32768)) and out[5, 1] == 0
     assert io_oracle.encode_mix(s, 2).shape == (2, 2)
+
+
+@needs_ref
+def test_configs_yaml_equals_reference():
+    """inference/configs.yaml is written in a different layout but must parse to the reference's dictionaries."""
+    import yaml
+    ours = yaml.full_load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                            "music_mixing_style_transfer_b200", "inference", "configs.yaml")))
+    ref = yaml.full_load(open(os.path.join(ref_import.REFERENCE_ROOT, "inference", "configs.yaml")))
+    assert ours == ref
