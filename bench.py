@@ -192,6 +192,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="segments per GPU (default: BASELINE config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="auto", choices=["auto", "f16f8", "bf16x3"],
+                    help="TCN operand format (auto = f16f8 with the range guard and a bf16x3 repeat when it fires)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -217,6 +219,7 @@ def main():
     B, L = args.batch, SEG_LEN
     total = B * world
     enc, tcn = build_models(device)
+    tcn.precision = args.precision
     from music_mixing_style_transfer_b200 import synthetic as W
     ref_host = W.synthetic_audio(B, L, seed=1234).pin_memory() if rank == 0 else None
     inp_host = W.synthetic_audio(B, L, seed=2000 + rank).pin_memory()
@@ -301,7 +304,7 @@ def main():
     achieved = flops_per_launch / (umma_ms * 1e-3) / 1e12
     n_umma = 13
     share = n_umma * umma_ms / ms_step
-    f8 = os.environ.get("MST_TCN_PRECISION", "f16f8") not in ("bf16x3", "bf16")
+    f8 = tcn.precision != "bf16x3"
     units = 2 if f8 else 3     # tensor-pipe time per algorithmic MMA in bf16-MMA equivalents (an e4m3 MMA runs at twice the rate)
     roofline = {"kernel": "tcn_block_umma_kernel", "bound": "tensor", "achieved": achieved,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],

@@ -80,10 +80,21 @@ typedef struct {
   int cond_dim;          /* 2048 */
 } mst_tcn_config;
 
+/* Operand format of the dilated blocks (per call; both weight packs are always built):
+ *   MST_TCN_F16F8   fp16(X) fp16(W) + two e4m3 correction products into one fp32 accumulator: 2 tensor units per algorithmic
+ *                   MMA, fp32-grade accuracy (1e-5 RMS at full length) while every inter-block activation stays inside
+ *                   +-MST_TCN_F16F8_RANGE (the e4m3 planes saturate above it).  `range_flag` reports a violation.
+ *   MST_TCN_BF16X3  bf16 hi/lo pairs, three products: 3 tensor units, fp32 dynamic range -- the fall-back the Python
+ *                   module repeats a forward in when range_flag fired.  The reference's FiLM gamma is unbounded
+ *                   (networks/network_utils.py:180-182), hence the guard. */
+#define MST_TCN_F16F8 0
+#define MST_TCN_BF16X3 1
+#define MST_TCN_F16F8_RANGE 448.0f
+
 size_t mst_tcn_packed_bytes(const mst_tcn_config* cfg);
 /* raw: host array of device pointers, per block n: {conv1.weight, bn.weight, bn.bias, bn.running_mean,
  * bn.running_var, res.weight, film.film_fc.weight, film.film_fc.bias}, then {output.weight, output.bias}.
- * Packs: BN folded into conv1 (block 0 fp32; blocks >=1 split into bf16 hi+lo, tap-major, K-major tiles),
+ * Packs: BN folded into conv1 (block 0 fp32; blocks >=1 in BOTH operand formats, tap-major, K-major tiles),
  * per-channel BN bias and residual scale, FiLM weights, output projection. */
 int mst_tcn_pack(const mst_tcn_config* cfg, const void* const* raw, void* packed, void* stream);
 
@@ -95,25 +106,31 @@ int mst_tcn_film_precompute(const mst_tcn_config* cfg, const void* packed, const
 
 size_t mst_tcn_workspace_bytes(const mst_tcn_config* cfg, int B, int L);
 /* whole TCN: x[B,n_inputs,L] fp32 -> y[B,n_outputs,L] fp32 = clamp(output(blocks(x)), -1, 1).
- * `film` from mst_tcn_film_precompute with the same n_cond. */
+ * `film` from mst_tcn_film_precompute with the same n_cond.  precision: MST_TCN_F16F8 / MST_TCN_BF16X3.
+ * range_flag (device uint32, may be NULL; F16F8 only): zeroed at the start of the call, afterwards 0 if every inter-block
+ * activation stayed inside the f16f8 range, else the float bits of the largest |activation| seen -> y is then only
+ * single-pass-fp16 accurate and the caller should repeat the call with MST_TCN_BF16X3. */
 int mst_tcn_forward(const mst_tcn_config* cfg, const void* packed, const float* x, const float* film, int n_cond,
-                    float* y, int B, int L, void* workspace, size_t workspace_bytes, void* stream);
+                    float* y, int B, int L, void* workspace, size_t workspace_bytes, int precision,
+                    unsigned int* range_flag, void* stream);
 
-/* Layer-granular launches on the INTERNAL activation format (DESIGN.md "data layout": act[b][t][4 planes][64] bf16,
+/* Layer-granular launches on the INTERNAL activation format (DESIGN.md "data layout": act[b][t][4 planes of 128 B],
  * 512 bytes per time step, B*L*512 bytes per buffer, 1024-byte aligned).  mst_tcn_forward is exactly
  * block0 + layer(1) ... layer(n_blocks-1, fuse_out=1); these entry points exist so a host can time or interleave
  * individual launches (bench.py's roofline leg).
  *   block0: x fp32 [B,n_inputs,L] -> act_out.   layer n>=1: act_in -> act_out, or, when fuse_out != 0 (last block),
  *   -> y fp32 [B,n_outputs,L] = clamp(Conv1d(128->n_out,k=1)(block(act_in)), -1, 1) and act_out is not written. */
 int mst_tcn_block0_forward(const mst_tcn_config* cfg, const void* packed, const float* x, const float* film, int n_cond,
-                           void* act_out, int B, int L, void* stream);
+                           void* act_out, int B, int L, int precision, unsigned int* range_flag, void* stream);
 int mst_tcn_layer_forward(const mst_tcn_config* cfg, const void* packed, int block, const void* act_in, void* act_out,
-                          const float* film, int n_cond, int B, int L, int fuse_out, float* y, void* stream);
+                          const float* film, int n_cond, int B, int L, int fuse_out, float* y, int precision,
+                          unsigned int* range_flag, void* stream);
 
 /* single TCNBlock n on fp32 [B,C,L] tensors (module-level surface + per-dilation parity tests):
  * y[B,128,L] = film(leaky_relu(bn(conv1(x)))) + res(x).  workspace >= mst_tcn_workspace_bytes(cfg,B,L). */
 int mst_tcn_block_forward(const mst_tcn_config* cfg, const void* packed, int block, const float* x, const float* film,
-                          int n_cond, float* y, int B, int L, void* workspace, size_t workspace_bytes, void* stream);
+                          int n_cond, float* y, int B, int L, void* workspace, size_t workspace_bytes, int precision,
+                          void* stream);
 
 /* ---- FX chain: replaces AugmentationChain.__call__ over Equaliser/Compressor/MidSideImager/Gain
  *      (mixing_manipulator/common_audioeffects.py:156-192, 501-525, 529-652, 965-992, 1038-1051) -------------- */

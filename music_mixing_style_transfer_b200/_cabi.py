@@ -15,6 +15,8 @@ MST_MAX_ENC_BLOCKS = 16
 FX_NPARAMS = 20
 FX_EQ, FX_COMP, FX_IMAGER, FX_GAIN, FX_RMSNORM = 1, 2, 4, 8, 16
 FX_ALL = FX_EQ | FX_COMP | FX_IMAGER | FX_GAIN | FX_RMSNORM
+TCN_F16F8, TCN_BF16X3 = 0, 1          # MST_TCN_F16F8 / MST_TCN_BF16X3
+TCN_F16F8_RANGE = 448.0               # MST_TCN_F16F8_RANGE
 
 
 class EncConfig(ctypes.Structure):
@@ -47,13 +49,13 @@ SIGNATURES = {
     "mst_tcn_film_precompute": (c_int, [POINTER(TcnConfig), c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mst_tcn_workspace_bytes": (c_size_t, [POINTER(TcnConfig), c_int, c_int]),
     "mst_tcn_forward": (c_int, [POINTER(TcnConfig), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
-                                c_void_p, c_size_t, c_void_p]),
+                                c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
     "mst_tcn_block0_forward": (c_int, [POINTER(TcnConfig), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
-                                       c_void_p]),
+                                       c_int, c_void_p, c_void_p]),
     "mst_tcn_layer_forward": (c_int, [POINTER(TcnConfig), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                      c_int, c_int, c_void_p, c_void_p]),
+                                      c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "mst_tcn_block_forward": (c_int, [POINTER(TcnConfig), c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
-                                      c_int, c_void_p, c_size_t, c_void_p]),
+                                      c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "mst_fx_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mst_fx_chain_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_size_t,
                                      c_void_p]),

@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libmst_b200.so")
 STAMP = LIB_PATH + ".stamp"
-SOURCES = ["api.cu", "encoder.cu", "enc_umma.cu", "tcn.cu", "tcn_f8.cu", "fx.cu", "fx2.cu", "pcm.cu"]
+SOURCES = ["api.cu", "encoder.cu", "enc_umma.cu", "tcn.cu", "tcn_f8.cu", "fx2.cu", "pcm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--cudart", "static"]
 
@@ -29,10 +29,11 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
+    # names relative to the package, so a shipped .so is still "fresh" when the repo is mounted at another path
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(INCLUDE, "mst_b200.h")]
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -43,6 +44,23 @@ def needs_build() -> bool:
         return True
     with open(STAMP) as fh:
         return fh.read().strip() != _digest()
+
+
+def build_variant(tag: str, defines) -> str:
+    """Development builds with extra -D switches (ablation studies): build/<tag>/libmst_b200.so, never the product path."""
+    out_dir = os.path.join(PKG_DIR, "build", tag)
+    os.makedirs(out_dir, exist_ok=True)
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(out_dir, src.replace(".cu", ".o"))
+        procs.append(subprocess.Popen([_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-c",
+                                       os.path.join(CSRC, src), "-o", obj]))
+        objs.append(obj)
+    if any(p.wait() != 0 for p in procs):
+        raise RuntimeError("nvcc failed")
+    lib = os.path.join(out_dir, "libmst_b200.so")
+    subprocess.check_call([_nvcc(), "-shared", *NVCC_FLAGS, "-o", lib, *objs])
+    return lib
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -81,5 +99,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--variant", nargs="+", metavar=("TAG", "DEFINE"), help="development build: TAG then -D defines")
     a = ap.parse_args()
-    print(build(a.force, a.verbose))
+    print(build_variant(a.variant[0], a.variant[1:]) if a.variant else build(a.force, a.verbose))

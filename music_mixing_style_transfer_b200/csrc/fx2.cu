@@ -1,16 +1,16 @@
-// fx2.cu -- second-generation FX chain kernels (parametric EQ -> compressor -> mid/side imager -> gain) for sm_100a.
+// fx2.cu -- FX chain kernels (parametric EQ -> compressor -> mid/side imager -> gain) for sm_100a and their C-ABI entry.
 //
-// Replaces the same reference code as fx.cu (paths relative to /root/reference/mixing_style_transfer/mixing_manipulator/):
+// Replaces (paths relative to /root/reference/mixing_style_transfer/mixing_manipulator/):
 //   AugmentationChain.__call__ / apply_processor   common_audioeffects.py:156-192, 115-148 (RMS re-normalisation :142-145)
 //   Equaliser.process                               :501-525 (filters :438-462)
 //   compressor_process / Compressor.process         :529-587, :624-652
 //   MidSideImager.process                           :965-992
 //   Gain.process                                    :1038-1051
 //
-// Why a second generation: ncu on fx.cu (profiles/r01f_summary.md, r01f_fx_v1_ncu_full.csv) shows 124 thread-instructions per sample in each of
-// the EQ and compressor kernels, 22-25 % of the warp slots occupied and 0.7 eligible warps per scheduler cycle -- both
-// kernels are instruction- and latency-bound at ~1 TB/s.  This file keeps the time-parallel algorithms (chunked
-// recurrences + block scans, compressor pattern fixed point) and changes the arithmetic and the geometry:
+// "Second generation": ncu on the first version (profiles/r01f_summary.md, r01f_fx_v1_ncu_full.csv; removed in round 2)
+// showed 124 thread-instructions per sample in each of the EQ and compressor kernels, 22-25 % of the warp slots occupied and
+// 0.7 eligible warps per scheduler cycle -- instruction- and latency-bound at ~1 TB/s.  This file keeps the time-parallel
+// algorithms (chunked recurrences + block scans, compressor pattern fixed point) with this arithmetic and geometry:
 //   * One CTA (256 threads) per SEGMENT; a thread owns the SAME frames of both channels and works on (L, R) pairs with
 //     packed fma.rn.f32x2 (FFMA2: measured 1.46x the FMA rate of scalar FFMA on B200, tools/ubench/fp_pipes.cu) -- the two
 //     channels share every coefficient, and the compressor's cross-channel sum L*R becomes thread-local.
@@ -22,7 +22,7 @@
 //     states, their scan and the tile carry are float32 too (packed over the channel pair); only the per-segment sums of
 //     squares are accumulated in float64.
 //   * Every thread runs TWO independent 16-frame chunks (ILP 2) -> 32 frames x 2 channels per thread, 8192-frame tiles,
-//     so the scan and the five block barriers are amortised over 4x more samples per thread than in fx.cu.
+//     so the scan and the five block barriers are amortised over 4x more samples per thread than in the first version.
 //   * Compressor: gain computer on MUFU lg2 (x_l = max(0, (x_g - T)(1 - 1/R)) in one FMA + max), smoother step
 //     y' = max(y + c_att (x - y), y + c_rel (x - y)) (the attack/release choice is the max of two affine maps), float32
 //     maps and scans (all-float32 smoothing is within 1e-6 relative of the float64 reference), exp2 on MUFU.
@@ -819,8 +819,8 @@ static size_t comp_smem_bytes() { return align_up(sizeof(CompShared), 16) + (siz
 
 }  // namespace fx2
 
-int fx2_chain_forward(const float* x, const float* params, float* y, int B, int L, float sample_rate, int stages, double* stats,
-                      cudaStream_t st) {
+static int fx2_chain_forward(const float* x, const float* params, float* y, int B, int L, float sample_rate, int stages, double* stats,
+                             cudaStream_t st) {
   using namespace fx2;
   static bool attr_done[64] = {false};
   int dev = 0;
@@ -841,3 +841,23 @@ int fx2_chain_forward(const float* x, const float* params, float* y, int B, int 
 }
 
 }  // namespace mst
+
+using namespace mst;
+
+extern "C" {
+
+size_t mst_fx_workspace_bytes(int B, int L) {
+  if (B <= 0 || L <= 0) return 0;
+  return align_up((size_t)B * fx2::kFxStats * sizeof(double), 256);
+}
+
+int mst_fx_chain_forward(const float* x, const float* params, float* y, int B, int L, float sample_rate, int stages,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  MST_CHECK(x && params && y && workspace, "fx_chain_forward: null pointer");
+  MST_CHECK(B > 0 && L > 0, "fx_chain_forward: bad shape B=%d L=%d", B, L);
+  MST_CHECK(workspace_bytes >= mst_fx_workspace_bytes(B, L), "fx_chain_forward: workspace too small");
+  MST_CHECK(sample_rate > 0.f, "fx_chain_forward: bad sample rate");
+  return fx2_chain_forward(x, params, y, B, L, sample_rate, stages, reinterpret_cast<double*>(workspace), (cudaStream_t)stream);
+}
+
+}  // extern "C"

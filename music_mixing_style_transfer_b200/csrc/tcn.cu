@@ -19,8 +19,9 @@
 // tcn_block_umma_kernel: im2col-free dilated implicit GEMM on the 5th-gen tensor cores.
 //   D[t, co] = sum_{tap, ci} X[t + (tap-7)*d, ci] * W[tap][co][ci]        M = 128 time rows, N = 128 co, K = 15*128
 // fp32-grade accuracy from the tensor cores via split operands: by default fp16(X)*fp16(W) + two e4m3 correction products
-// (FMT 1, the format of tcn_f8.cu: 2 bf16-MMA equivalents per algorithmic MMA), or the 3-product bf16 split
-// Xhi*Whi + Xlo*Whi + Xhi*Wlo (FMT 0, MST_TCN_PRECISION=bf16x3); fp32 accumulate in TMEM.  Persistent, warp-specialised,
+// (FMT 1 = MST_TCN_F16F8, the format of tcn_f8.cu: 2 bf16-MMA equivalents per algorithmic MMA; activations must stay within
+// +-448, which the epilogue checks and reports through `range_flag`), or the 3-product bf16 split Xhi*Whi + Xlo*Whi + Xhi*Wlo
+// (FMT 0 = MST_TCN_BF16X3, fp32 range); fp32 accumulate in TMEM.  The precision is a per-call argument.  Persistent, warp-specialised,
 // one CTA per SM:
 //   warp 0   TMA producer (one lane): streams 32 KB slots (W tap-group, X sub-tile) through a 6-deep mbarrier ring
 //   warp 1   MMA issuer: the whole warp runs the uniform loop, the tcgen05.mma / commit instructions are predicated on the
@@ -36,6 +37,13 @@
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
+// Development-only ablation switches (tools/tcn_ablate.sh builds side libraries with -DMST_TCN_ABLATE=<mask>; the shipped
+// library is always built with 0): 1 = issue no MMAs (barrier traffic and commits only), 2 = epilogue drains TMEM but does no
+// math / residual load / store, 4 = producer moves no activation bytes (weights only).
+#ifndef MST_TCN_ABLATE
+#define MST_TCN_ABLATE 0
+#endif
+
 namespace mst {
 
 constexpr int kCh = MST_TCN_CH;      // 128
@@ -44,48 +52,15 @@ constexpr int kRowBytes = 512;       // one time step: 4 planes x 64 bf16
 constexpr int kSubRows = 128;        // UMMA M
 constexpr int kTileRows = 256;       // two sub-tiles share every weight slot
 constexpr int kStageBytes = 32768;   // epilogue staging: 64-channel hi tile (128 x 128 B) + lo tile
-constexpr int kRingBytes = 196608;   // operand ring: 6 x 32 KB (64-channel slots) or 12 x 16 KB (32-channel slots)
-constexpr int kMaxSlots = 12;
+constexpr int kRingBytes = 196608;   // operand ring: 6 x 32 KB (64-channel slots)
+constexpr int kMaxSlots = 6;
 constexpr size_t kWBytesPerLayer = (size_t)kTaps * kCh * kCh * 2 * 2;  // hi + lo bf16 = 983,040 B
 
-// Input-channel chunk per pipeline slot: 64 (SWIZZLE_128B rows, 6 slots, 2 tap-chunks in flight) or
-// 32 (SWIZZLE_64B rows, 12 slots, 4 tap-chunks in flight).  MST_TCN_KCHUNK overrides; read once per process so that
-// weight packing and kernel launches agree.
-static int tcn_kchunk() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("MST_TCN_KCHUNK");
-    v = (e && atoi(e) == 64) ? 64 : ((e && atoi(e) == 32) ? 32 : 64);
-  }
-  return v;
-}
-
+// Both operand formats of blocks >= 1 are packed (983,040 B per layer each), so the precision is a per-call choice and a
+// forward that leaves the f16f8 range can be repeated in bf16 x 3 without touching the weights again.
 struct TcnPacked {
-  size_t w0, wumma, bn_bias, res, film_w, film_b, out_w, out_b, f8_scale, total;
+  size_t w0, wumma, wbf16, bn_bias, res, film_w, film_b, out_w, out_b, f8_scale, total;
 };
-
-// Operand-split mode of blocks >= 1: 1 = fp16 + 2 x e4m3 corrections ("f16f8", 2 tensor units per algorithmic MMA; the default
-// since the warp-convergent issuer made it the faster one: 7.6 vs 9.2 ms per launch), 0 = bf16 x 3 products
-// (MST_TCN_PRECISION=bf16x3).  Read once per process so that weight packing and launches agree.
-static int tcn_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MST_TCN_PRECISION");
-    v = (e && (strcmp(e, "bf16x3") == 0 || strcmp(e, "bf16") == 0)) ? 0 : 1;
-  }
-  return v;
-}
-
-// Pipeline of blocks >= 1 in bf16 mode: 1 = one shared operand ring + TMA-staged epilogue (tcn_block_umma_kernel),
-// 2 = separate weight / activation rings + direct epilogue (block_kernel<*, 1> in tcn_f8.cu).  MST_TCN_PIPE overrides.
-static int tcn_pipe() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MST_TCN_PIPE");
-    v = (e && atoi(e) == 2) ? 2 : 1;
-  }
-  return v;
-}
 
 static int tcn_layout(const mst_tcn_config* c, TcnPacked* o) {
   MST_CHECK(c, "tcn config is null");
@@ -100,7 +75,8 @@ static int tcn_layout(const mst_tcn_config* c, TcnPacked* o) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t r = off; off += align_up(bytes, 1024); return r; };
   o->w0 = take((size_t)kCh * c->n_inputs * kTaps * 4);
-  o->wumma = take((size_t)(c->n_blocks - 1) * kWBytesPerLayer);
+  o->wumma = take((size_t)(c->n_blocks - 1) * kWBytesPerLayer);   // f16f8: [tap][fp16 ci 0-63 | fp16 ci 64-127 | e4m3 | e4m3][co][128 B]
+  o->wbf16 = take((size_t)(c->n_blocks - 1) * kWBytesPerLayer);   // bf16 x 3: [tap][kc][hi|lo][co][ci 64]
   o->bn_bias = take((size_t)c->n_blocks * kCh * 4);
   o->res = take((size_t)c->n_blocks * kCh * 4);
   o->film_w = take((size_t)c->n_blocks * 2 * kCh * c->cond_dim * 4);
@@ -336,6 +312,7 @@ struct TcnLayerArgs {
   int B, T, dilation, tiles_per_seg, n_tiles, n_cond;
   int pair_m;           // PAIRED kernels: sub-tiles per half block = dilation / 128
   const float* inv_scale;   // FMT 1 (f16f8): 1 / (S * 2^11) of this layer's packed weights (tcn_f8.cu)
+  unsigned int* range_flag; // FMT 1: receives max |activation| (float bits, atomicMax) if it exceeds the e4m3 range; may be null
   const float4* film;   // this block's [n_cond][128] (bn_bias, gamma, beta, res)
   int fuse_out;         // 1 on the last block: Conv1d(128 -> n_out, k=1) + clamp fused, fp32 [B][n_out][T] written
   int n_out;
@@ -464,6 +441,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         // activation columns of this chunk: plane (hi / lo) of channel half kc*KCH/64, offset inside the plane
         const int c_hi = (((kc * KCH) / 64) * 128 + (kc * KCH) % 64) * kCoord, c_lo = c_hi + 64 * kCoord;
         ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
+        if (MST_TCN_ABLATE & 4) { ptx::mbar_arrive(&bars->full[slot]); next(); return; }
         ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
         uint8_t* dst = ring + (size_t)slot * kSlotBytes;
         ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, c_hi, (int)ts, b);
@@ -513,6 +491,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
       // 3-product split: (Xhi, Whi) + (Xlo, Whi) + (Xhi, Wlo), KCH/16 K16 steps per slot
       auto issue_group = [&](uint32_t x_addr, uint32_t w_addr, uint32_t d_tmem, bool first) {
+        if (MST_TCN_ABLATE & 1) return;
         const uint64_t xh = ptx::umma_desc_kmajor<kSwz>(x_addr), xl = ptx::umma_desc_kmajor<kSwz>(x_addr + kHalf);
         const uint64_t wh = ptx::umma_desc_kmajor<kSwz>(w_addr), wl = ptx::umma_desc_kmajor<kSwz>(w_addr + kHalf);
         if (FMT == 1) {
@@ -634,6 +613,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const int et = threadIdx.x - 128;       // 0..127
     const int rl = q * 32 + lane;           // row inside the sub-tile == TMEM lane
     uint32_t stage_phase = 0;
+    float vmax = 0.f;                       // FMT 1: max |activation| this thread re-split (operand-range guard)
     int it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
       const TcnTile c = tcn_tile<PAIRED>(tile, a);
@@ -646,6 +626,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       for (int sub = 0; sub < 2; ++sub) {
         const int ts = (int)(sub == 0 ? c.r0 : c.r1);
         if (ts >= a.T) break;
+        if (MST_TCN_ABLATE & 2) break;
         float o0 = 0.f, o1 = 0.f;
         for (int h = 0; h < 2; ++h) {
           // staging is free once the previous TMA store has read it and every thread has left the previous half
@@ -713,6 +694,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     o1 = fmaf(u1, __ldg(a.out_w + kCh + ch + 1), o1);
                   }
                 } else {
+                  vmax = fmaxf(vmax, fmaxf(fabsf(u0), fabsf(u1)));
                   const __half2 hi2 = __floats2half2_rn(fminf(fmaxf(u0, -65504.f), 65504.f), fminf(fmaxf(u1, -65504.f), 65504.f));
                   const float2 hb = __half22float2(hi2);
                   oh[pr] = *reinterpret_cast<const uint32_t*>(&hi2);
@@ -801,6 +783,13 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       ++it;
     }
     if (et == 0) ptx::tma_store_wait_all();
+    if (FMT == 1 && a.range_flag != nullptr) {
+      // |x| > 448 saturates the e4m3 planes (x itself and (x - fp16 x) 2^11 <= |x|): the next block would then run at single-pass
+      // fp16 accuracy.  Report it (one atomic per warp, only when it happened) so the caller can repeat the forward in bf16 x 3.
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      if (lane == 0 && vmax > MST_TCN_F16F8_RANGE) atomicMax(a.range_flag, __float_as_uint(vmax));
+    }
   }
 
   ptx::tc_fence_before();
@@ -874,24 +863,12 @@ static int encode_w_map_bytes(CUtensorMap* m, const void* base) {
 // one dilated block (n >= 1): act_in -> act_out, or -> fp32 `out` when fuse_out
 static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, const TcnPacked& L, int n,
                              const uint8_t* act_in, uint8_t* act_out, const float* film, int n_cond, int B, int T,
-                             bool fuse_out, float* out, cudaStream_t st) {
+                             bool fuse_out, float* out, int precision, unsigned int* range_flag, cudaStream_t st) {
   const long long d = block_dilation(cfg, n);
   MST_CHECK(7 * d + kTileRows < (1ll << 31) - T, "tcn: dilation %lld too large", d);
-  if (tcn_mode() == 1 && tcn_pipe() == 2)
-    return tcn_f8_launch_block(d, packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer,
-                               reinterpret_cast<const float*>(packed + L.f8_scale) + 2 * n, act_in, act_out,
-                               film + (size_t)n * n_cond * kCh * 4, n_cond, B, T, fuse_out, cfg->n_outputs,
-                               reinterpret_cast<const float*>(packed + L.out_w),
-                               reinterpret_cast<const float*>(packed + L.out_b), out, st);
-  const bool f8 = tcn_mode() == 1;     // f16f8 operands through the single-ring kernel below (FMT 1)
-  const int kch = f8 ? 64 : tcn_kchunk();
-  if (!f8 && tcn_pipe() == 2 && kch == 64)
-    return tcn_pipe2_launch_block(d, packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer, act_in, act_out,
-                                  film + (size_t)n * n_cond * kCh * 4, n_cond, B, T, fuse_out, cfg->n_outputs,
-                                  reinterpret_cast<const float*>(packed + L.out_w),
-                                  reinterpret_cast<const float*>(packed + L.out_b), out, st);
+  const bool f8 = precision == MST_TCN_F16F8;
   CUtensorMap tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8;
-  const uint8_t* w_layer = packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer;
+  const uint8_t* w_layer = packed + (f8 ? L.wumma : L.wbf16) + (size_t)(n - 1) * kWBytesPerLayer;
   if (f8) {
     if (encode_act_map_bytes(&tm_x, act_in, B, T, 128)) return 1;
     tm_xs = tm_x;
@@ -900,23 +877,20 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
     if (encode_act_map_bytes(&tm_y8, fuse_out ? act_in : act_out, B, T, 64)) return 1;
     if (encode_w_map_bytes(&tm_w, w_layer)) return 1;
   } else {
-    if (encode_act_map(&tm_x, act_in, B, T, kch)) return 1;
-    if (encode_act_map(&tm_xs, act_in, B, T, 64)) return 1;
+    if (encode_act_map(&tm_x, act_in, B, T, 64)) return 1;
+    tm_xs = tm_x;
     if (encode_act_map(&tm_y, fuse_out ? act_in : act_out, B, T, 64)) return 1;
-    if (encode_w_map(&tm_w, w_layer, kch)) return 1;
+    if (encode_w_map(&tm_w, w_layer, 64)) return 1;
     tm_l8 = tm_xs;      // unused in this format
     tm_y8 = tm_y;
   }
   TcnLayerArgs a;
   a.inv_scale = reinterpret_cast<const float*>(packed + L.f8_scale) + 2 * n;
+  a.range_flag = f8 ? range_flag : nullptr;
   a.B = B; a.T = T; a.dilation = (int)d;
-  // Paired sub-tiles (tcn_tile<true>) for dilations that are a multiple of 128; MST_TCN_PAIRED=0 switches them off (A/B).
-  // L2->SM bytes 100.9 -> 70 GB per launch.  With the single-thread issuer this bought nothing (tensor activity 78 -> 74 %);
-  // with the warp-convergent issuer it is 8.63 -> 8.20 ms on isolated launches (tensor pipe 82.8 -> 85.9 %) and 9.86 -> 9.60
-  // ms per launch in a sustained forward.
-  static int paired_env = -1;
-  if (paired_env < 0) { const char* e = getenv("MST_TCN_PAIRED"); paired_env = (e && atoi(e) == 0) ? 0 : 1; }
-  const bool paired = paired_env && kch == 64 && d >= kSubRows && d % kSubRows == 0;
+  // Paired sub-tiles (tcn_tile<true>) for dilations that are a multiple of 128: L2->SM bytes 100.9 -> 70 GB per launch,
+  // tensor pipe 82.8 -> 85.9 % (profiles/r01g_summary.md)
+  const bool paired = d >= kSubRows && d % kSubRows == 0;
   a.pair_m = paired ? (int)(d / kSubRows) : 1;
   a.tiles_per_seg = paired ? (int)(((T + 2 * d - 1) / (2 * d)) * a.pair_m) : cdiv(T, kTileRows);
   a.n_tiles = B * a.tiles_per_seg;
@@ -928,26 +902,26 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   a.out_b = reinterpret_cast<const float*>(packed + L.out_b);
   a.out = out;
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-#define MST_TCN_LAUNCH(KCH_, PAIRED_, FMT_)                                                                                     \
-  do {                                                                                                                         \
-    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<KCH_, PAIRED_, FMT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                     (int)kTcnSmemBytes));                                                                     \
-    tcn_block_umma_kernel<KCH_, PAIRED_, FMT_><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8, a);    \
+#define MST_TCN_LAUNCH(PAIRED_, FMT_)                                                                                        \
+  do {                                                                                                                      \
+    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64, PAIRED_, FMT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)kTcnSmemBytes));                                                                  \
+    tcn_block_umma_kernel<64, PAIRED_, FMT_><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8, a);   \
   } while (0)
-  if (f8 && paired) MST_TCN_LAUNCH(64, true, 1);
-  else if (f8) MST_TCN_LAUNCH(64, false, 1);
-  else if (paired) MST_TCN_LAUNCH(64, true, 0);
-  else if (kch == 64) MST_TCN_LAUNCH(64, false, 0);
-  else MST_TCN_LAUNCH(32, false, 0);
+  if (f8 && paired) MST_TCN_LAUNCH(true, 1);
+  else if (f8) MST_TCN_LAUNCH(false, 1);
+  else if (paired) MST_TCN_LAUNCH(true, 0);
+  else MST_TCN_LAUNCH(false, 0);
 #undef MST_TCN_LAUNCH
   return launch_ok("tcn_block_umma_kernel");
 }
 
 static int launch_block0(const mst_tcn_config* cfg, const uint8_t* packed, const TcnPacked& L, const float* x,
-                         const float* film, int n_cond, uint8_t* act, int B, int T, cudaStream_t st) {
+                         const float* film, int n_cond, uint8_t* act, int B, int T, int precision,
+                         unsigned int* range_flag, cudaStream_t st) {
   dim3 grid(cdiv(T, 256), B);
   const float* w0 = reinterpret_cast<const float*>(packed + L.w0);
-  if (tcn_mode() == 1) return tcn_f8_launch_block0(cfg->n_inputs, x, w0, film, n_cond, act, B, T, st);
+  if (precision == MST_TCN_F16F8) return tcn_f8_launch_block0(cfg->n_inputs, x, w0, film, n_cond, act, B, T, range_flag, st);
   const float4* f = reinterpret_cast<const float4*>(film);
   if (cfg->n_inputs == 2) tcn_block0_kernel<2><<<grid, 256, 0, st>>>(x, w0, f, n_cond, act, T);
   else tcn_block0_kernel<1><<<grid, 256, 0, st>>>(x, w0, f, n_cond, act, T);
@@ -955,6 +929,12 @@ static int launch_block0(const mst_tcn_config* cfg, const uint8_t* packed, const
 }
 
 static size_t act_bytes(int B, int L) { return align_up((size_t)B * L * kRowBytes, 1024); }
+
+static int check_precision(int precision) {
+  MST_CHECK(precision == MST_TCN_F16F8 || precision == MST_TCN_BF16X3, "tcn: precision must be MST_TCN_F16F8 (0) or MST_TCN_BF16X3 (1), got %d",
+            precision);
+  return 0;
+}
 
 }  // namespace mst
 
@@ -987,13 +967,12 @@ int mst_tcn_pack(const mst_tcn_config* cfg, const void* const* raw, void* packed
     MST_CHECK(conv_w && bn_w && bn_b && bn_m && bn_v && res_w && film_w && film_b, "tcn_pack: null weight in block %d", n);
     if (n == 0) {
       tcn_pack_block0_kernel<<<16, 256, 0, st>>>(conv_w, bn_w, bn_v, cfg->n_inputs, (float*)(packed + L.w0));
-    } else if (tcn_mode() == 1) {
+    } else {
       float* sc = reinterpret_cast<float*>(packed + L.f8_scale) + 2 * n;
       if (tcn_f8_pack_layer(conv_w, bn_w, bn_v, packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer, sc,
                             reinterpret_cast<unsigned int*>(sc + 1), st)) return 1;
-    } else {
       tcn_pack_umma_kernel<<<256, 256, 0, st>>>(
-          conv_w, bn_w, bn_v, (__nv_bfloat16*)(packed + L.wumma + (size_t)(n - 1) * kWBytesPerLayer), tcn_kchunk());
+          conv_w, bn_w, bn_v, (__nv_bfloat16*)(packed + L.wbf16 + (size_t)(n - 1) * kWBytesPerLayer), 64);
     }
     tcn_pack_vec_kernel<<<1, 128, 0, st>>>(bn_w, bn_b, bn_m, bn_v, res_w, (float*)(packed + L.bn_bias) + n * kCh,
                                            (float*)(packed + L.res) + n * kCh);
@@ -1028,9 +1007,10 @@ size_t mst_tcn_workspace_bytes(const mst_tcn_config* cfg, int B, int L) {
 }
 
 int mst_tcn_forward(const mst_tcn_config* cfg, const void* packed_v, const float* x, const float* film, int n_cond,
-                    float* y, int B, int L, void* workspace, size_t workspace_bytes, void* stream) {
+                    float* y, int B, int L, void* workspace, size_t workspace_bytes, int precision,
+                    unsigned int* range_flag, void* stream) {
   TcnPacked P;
-  if (tcn_layout(cfg, &P)) return 1;
+  if (tcn_layout(cfg, &P) || check_precision(precision)) return 1;
   MST_CHECK(packed_v && x && film && y && workspace, "tcn_forward: null pointer");
   MST_CHECK(B > 0 && L > 0 && B <= 65535, "tcn_forward: bad shape B=%d L=%d", B, L);
   MST_CHECK(n_cond == 1 || n_cond == B, "tcn_forward: n_cond must be 1 or B (got %d, B=%d)", n_cond, B);
@@ -1040,30 +1020,33 @@ int mst_tcn_forward(const mst_tcn_config* cfg, const void* packed_v, const float
   cudaStream_t st = (cudaStream_t)stream;
   const uint8_t* packed = reinterpret_cast<const uint8_t*>(packed_v);
   uint8_t* act[2] = {(uint8_t*)workspace, (uint8_t*)workspace + act_bytes(B, L)};
-  if (launch_block0(cfg, packed, P, x, film, n_cond, act[0], B, L, st)) return 1;
+  if (range_flag) MST_CUDA_OK(cudaMemsetAsync(range_flag, 0, sizeof(unsigned int), st));
+  if (launch_block0(cfg, packed, P, x, film, n_cond, act[0], B, L, precision, range_flag, st)) return 1;
   int cur = 0;
   for (int n = 1; n < cfg->n_blocks; ++n) {
     const bool last = n == cfg->n_blocks - 1;
-    if (launch_umma_block(cfg, packed, P, n, act[cur], act[cur ^ 1], film, n_cond, B, L, last, y, st)) return 1;
+    if (launch_umma_block(cfg, packed, P, n, act[cur], act[cur ^ 1], film, n_cond, B, L, last, y, precision, range_flag, st))
+      return 1;
     cur ^= 1;
   }
   return 0;
 }
 
 int mst_tcn_block0_forward(const mst_tcn_config* cfg, const void* packed_v, const float* x, const float* film, int n_cond,
-                           void* act_out, int B, int L, void* stream) {
+                           void* act_out, int B, int L, int precision, unsigned int* range_flag, void* stream) {
   TcnPacked P;
-  if (tcn_layout(cfg, &P)) return 1;
+  if (tcn_layout(cfg, &P) || check_precision(precision)) return 1;
   MST_CHECK(packed_v && x && film && act_out, "tcn_block0_forward: null pointer");
   MST_CHECK(B > 0 && L > 0 && B <= 65535 && (n_cond == 1 || n_cond == B), "tcn_block0_forward: bad shape");
   return launch_block0(cfg, reinterpret_cast<const uint8_t*>(packed_v), P, x, film, n_cond, (uint8_t*)act_out, B, L,
-                       (cudaStream_t)stream);
+                       precision, range_flag, (cudaStream_t)stream);
 }
 
 int mst_tcn_layer_forward(const mst_tcn_config* cfg, const void* packed_v, int block, const void* act_in, void* act_out,
-                          const float* film, int n_cond, int B, int L, int fuse_out, float* y, void* stream) {
+                          const float* film, int n_cond, int B, int L, int fuse_out, float* y, int precision,
+                          unsigned int* range_flag, void* stream) {
   TcnPacked P;
-  if (tcn_layout(cfg, &P)) return 1;
+  if (tcn_layout(cfg, &P) || check_precision(precision)) return 1;
   MST_CHECK(packed_v && act_in && film, "tcn_layer_forward: null pointer");
   MST_CHECK(block >= 1 && block < cfg->n_blocks, "tcn_layer_forward: block %d out of range [1,%d)", block, cfg->n_blocks);
   MST_CHECK(B > 0 && L > 0 && (n_cond == 1 || n_cond == B), "tcn_layer_forward: bad shape");
@@ -1071,13 +1054,15 @@ int mst_tcn_layer_forward(const mst_tcn_config* cfg, const void* packed_v, int b
   MST_CHECK((reinterpret_cast<uintptr_t>(act_in) & 1023) == 0 && (reinterpret_cast<uintptr_t>(act_out) & 1023) == 0,
             "tcn_layer_forward: activation buffers must be 1024-byte aligned");
   return launch_umma_block(cfg, reinterpret_cast<const uint8_t*>(packed_v), P, block, (const uint8_t*)act_in,
-                           (uint8_t*)act_out, film, n_cond, B, L, fuse_out != 0, y, (cudaStream_t)stream);
+                           (uint8_t*)act_out, film, n_cond, B, L, fuse_out != 0, y, precision, range_flag,
+                           (cudaStream_t)stream);
 }
 
 int mst_tcn_block_forward(const mst_tcn_config* cfg, const void* packed_v, int block, const float* x, const float* film,
-                          int n_cond, float* y, int B, int L, void* workspace, size_t workspace_bytes, void* stream) {
+                          int n_cond, float* y, int B, int L, void* workspace, size_t workspace_bytes, int precision,
+                          void* stream) {
   TcnPacked P;
-  if (tcn_layout(cfg, &P)) return 1;
+  if (tcn_layout(cfg, &P) || check_precision(precision)) return 1;
   MST_CHECK(packed_v && x && film && y && workspace, "tcn_block_forward: null pointer");
   MST_CHECK(block >= 0 && block < cfg->n_blocks, "tcn_block_forward: block %d out of range", block);
   MST_CHECK(B > 0 && L > 0 && B <= 65535, "tcn_block_forward: bad shape B=%d L=%d", B, L);
@@ -1087,20 +1072,22 @@ int mst_tcn_block_forward(const mst_tcn_config* cfg, const void* packed_v, int b
   cudaStream_t st = (cudaStream_t)stream;
   const uint8_t* packed = reinterpret_cast<const uint8_t*>(packed_v);
   uint8_t* act[2] = {(uint8_t*)workspace, (uint8_t*)workspace + act_bytes(B, L)};
+  const bool f8 = precision == MST_TCN_F16F8;
   dim3 grid(cdiv(L, 32), B);
   if (block == 0) {
     // film for block 0 sits at the start of the table
-    if (launch_block0(cfg, packed, P, x, film, n_cond, act[1], B, L, st)) return 1;
+    if (launch_block0(cfg, packed, P, x, film, n_cond, act[1], B, L, precision, nullptr, st)) return 1;
   } else {
-    if (tcn_mode() == 1) {
+    if (f8) {
       if (tcn_f8_act_pack(x, act[0], B, L, st)) return 1;
     } else {
       tcn_act_pack_kernel<<<grid, 256, 0, st>>>(x, act[0], L);
       if (launch_ok("tcn_act_pack_kernel")) return 1;
     }
-    if (launch_umma_block(cfg, packed, P, block, act[0], act[1], film, n_cond, B, L, false, nullptr, st)) return 1;
+    if (launch_umma_block(cfg, packed, P, block, act[0], act[1], film, n_cond, B, L, false, nullptr, precision, nullptr, st))
+      return 1;
   }
-  if (tcn_mode() == 1) return tcn_f8_act_unpack(act[1], y, B, L, st);
+  if (f8) return tcn_f8_act_unpack(act[1], y, B, L, st);
   tcn_act_unpack_kernel<<<grid, 256, 0, st>>>(act[1], y, L);
   return launch_ok("tcn_act_unpack_kernel");
 }

@@ -1,7 +1,9 @@
-// tcn_f8.cu -- the "2 tensor units" precision mode of the MixFXcloner TCN (MST_TCN_PRECISION=f16f8).
+// tcn_f8.cu -- the "f16f8" operand format of the MixFXcloner TCN (MST_TCN_F16F8, the default precision): weight packer,
+// block 0 (CUDA cores, writes the format) and the fp32 <-> format converters.  The tcgen05 kernel that consumes the
+// format is tcn_block_umma_kernel<.., FMT = 1> in tcn.cu.
 //
-// Same computation, interfaces and pipeline as csrc/tcn.cu (TCNBlock.forward, architectures.py:222-234), different
-// operand split.  tcn.cu spends 3 bf16 MMAs per algorithmic MMA (Xhi*Whi + Xlo*Whi + Xhi*Wlo).  Here
+// Same computation as the bf16 x 3 split (TCNBlock.forward, architectures.py:222-234), different operand split: bf16 x 3
+// spends 3 bf16 MMAs per algorithmic MMA (Xhi*Whi + Xlo*Whi + Xhi*Wlo).  Here
 //     X*W*(S*2^11)  =  fp16(X) * fp16(W*S*2^11)                       kind::f16     (1 unit)
 //                    + e4m3((X - fp16 X)*2^11) * e4m3(W*S)            kind::f8f6f4  (1/2 unit: FP8 runs at twice the rate)
 //                    + e4m3(X) * e4m3(W*S*2^11 - fp16(W*S*2^11))      kind::f8f6f4  (1/2 unit)
@@ -29,9 +31,6 @@ constexpr int kTaps = MST_TCN_K;
 constexpr int kRowBytes = 512;
 constexpr int kSubRows = 128;
 constexpr int kTileRows = 256;
-constexpr int kSlotBytes = 32768;
-constexpr int kWSlots = 3;           // weight ring  (released only after both sub-tiles consumed a slot -> its own ring)
-constexpr int kXSlots = 4;           // activation ring
 constexpr float kLoScale = 2048.f;   // 2^11
 
 __device__ __forceinline__ float fp8_to_float(uint8_t v) {
@@ -101,7 +100,7 @@ __global__ void pack_kernel(const float* __restrict__ w, const float* __restrict
 template <int NIN>
 __global__ void __launch_bounds__(256, 2)
 block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const float4* __restrict__ film, int n_cond,
-              uint8_t* __restrict__ act, int T) {
+              uint8_t* __restrict__ act, int T, unsigned int* __restrict__ range_flag) {
   constexpr int ROWS = 256, HALO = 7, RB = 4;
   __shared__ float xs[NIN][ROWS + 2 * HALO + 4];
   const int b = blockIdx.y, t0 = blockIdx.x * ROWS;
@@ -122,6 +121,7 @@ block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const f
     P[q] = __ldg(film + (size_t)(n_cond > 1 ? b : 0) * kCh + ch[q]);
   }
   const int res_ci = ch[0] / (kCh / NIN);
+  float vmax = 0.f;     // max |activation| written by this thread (operand-range guard, see tcn.cu)
   __syncthreads();
   for (int r = rgrp * 64; r < rgrp * 64 + 64; r += RB) {
     if (t0 + r >= T) break;
@@ -155,6 +155,7 @@ block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const f
         float v = acc[u][q] + P[q].x;
         v = v > 0.f ? v : 0.01f * v;
         v = fmaf(P[q].y, v, P[q].z) + P[q].w * xin;
+        vmax = fmaxf(vmax, fabsf(v));
         encode3(v, hi[q], l8[q], h8[q]);
       }
       uint8_t* row = act + ((size_t)b * T + t) * kRowBytes;
@@ -163,6 +164,8 @@ block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const f
       reinterpret_cast<uint16_t*>(row + 384 + half * 64)[lane] = (uint16_t)h8[0] | ((uint16_t)h8[1] << 8);
     }
   }
+  // the e4m3 planes saturate at 448: report (rarely, so the atomic is not a hot spot) when this block left the format's range
+  if (range_flag != nullptr && vmax > MST_TCN_F16F8_RANGE) atomicMax(range_flag, __float_as_uint(vmax));
 }
 
 __global__ void __launch_bounds__(256) act_pack_kernel(const float* __restrict__ x, uint8_t* __restrict__ act, int T) {
@@ -212,465 +215,6 @@ __global__ void __launch_bounds__(256) act_unpack_kernel(const uint8_t* __restri
   }
 }
 
-// =====================================================================================================================
-// the tcgen05 kernel
-// =====================================================================================================================
-struct LayerArgs {
-  int B, T, dilation, tiles_per_seg, n_tiles, n_cond;
-  const float4* film;
-  const float* inv_scale;    // 1 / (S * 2^11) of this layer's packed weights
-  const uint8_t* act_in;     // residual rows are read straight from global memory (L2-hot centre tap)
-  uint8_t* act_out;          // output rows are written straight from registers (all shared memory goes to the rings)
-  int fuse_out, n_out;
-  const float* out_w;
-  const float* out_b;
-  float* out;
-  int dbg;                   // diagnostics only (MST_TCN_DBG): 1 = skip the MMAs, 2 = skip the TMA loads, 4 = skip epilogue math/stores
-};
-
-struct __align__(8) Barriers {
-  uint64_t w_full[kWSlots], w_empty[kWSlots];
-  uint64_t x_full[kXSlots], x_empty[kXSlots];
-  uint64_t tmem_full[2], tmem_empty[2];
-  uint32_t tmem_base;
-};
-constexpr int kThreads = 384;        // 4 control warps + 8 epilogue warps (two per TMEM lane quarter, one per channel half)
-
-constexpr size_t kSmemBytes = 1024 + (size_t)(kWSlots + kXSlots) * kSlotBytes + 256 + 1024;   // + fused-output partials
-
-__device__ __forceinline__ bool tap_live(long long ts, int T) { return ts < (long long)T && ts + kSubRows > 0; }
-
-__device__ __forceinline__ void mma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// TMA load whose box lands at the same shared-memory offset of EVERY CTA in `mask` and completes bytes on the mbarrier
-// at the same offset of each of them
-__device__ __forceinline__ void tma_load_2d_multicast(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(ptx::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(ptx::smem_u32(bar)), "h"(mask)
-               : "memory");
-}
-
-// Pipeline: the L2 -> shared-memory round trip of a TMA box is ~1.3 us under load; a slot that is released at time t is
-// useful again at t + 1.3 us.  One MMA group (a weight slot + its one or two activation slots) lasts only ~0.7 us in this
-// mode, so (a) weights and activations get SEPARATE rings with separate producer lanes -- the weight slot is released
-// last and needed first, in a shared ring it would stall every activation load behind it -- and (b) all 224 KB of shared
-// memory are ring slots (3 x 32 KB weights, 4 x 32 KB activations): the epilogue reads the residual and writes the output
-// rows directly from / to global memory instead of staging them for TMA.
-// tm_x / tm_w: byte tensors, box {128 B, 128 rows}, SWIZZLE_128B.
-//
-// MC2 = 1: launched as clusters of two CTAs that work on time-adjacent tiles in lockstep.  Each CTA fetches HALF of every
-// weight slot and TMA-multicasts it into both CTAs' shared memory, so the weight bytes cross the L2 -> SM fabric once per
-// pair (the kernel is bound by that fabric: ~11 TB/s, 100 GB per launch, one third of it weights).  A weight slot may be
-// overwritten only when BOTH consumers have released it: w_empty counts 2 and every release is a multicast commit.
-//
-// FMT = 0: fp16 + 2 x e4m3 operands (the f16f8 mode).  FMT = 1: the default bf16 hi/lo operands of tcn.cu (three products
-// per K-step) run through THIS pipeline; rows are [hi ch0-63 | lo ch0-63 | hi ch64-127 | lo ch64-127], so the slot
-// addressing (column 256*grp and +128, weight rows (4*tap + 2*grp) * 128 and +128) is the same in both formats.
-template <int MC2, int FMT>
-__global__ void __launch_bounds__(kThreads, 1)
-block_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const LayerArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* wring = smem;
-  uint8_t* xring = smem + (size_t)kWSlots * kSlotBytes;
-  Barriers* bars = reinterpret_cast<Barriers*>(xring + (size_t)kXSlots * kSlotBytes);
-  float2* opart = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [128 rows] partial outputs of half 1
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&tm_x);
-    ptx::prefetch_tensormap(&tm_w);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kWSlots; ++i) { ptx::mbar_init(&bars->w_full[i], 1); ptx::mbar_init(&bars->w_empty[i], MC2 ? 2 : 1); }
-    for (int i = 0; i < kXSlots; ++i) { ptx::mbar_init(&bars->x_full[i], 1); ptx::mbar_init(&bars->x_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&bars->tmem_full[i], 1);
-      ptx::mbar_init(&bars->tmem_empty[i], 256);
-    }
-    ptx::mbar_fence_init();
-  }
-  if (warp == 2) {
-    ptx::tmem_alloc(&bars->tmem_base, 512);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  if (MC2) cluster_sync_all();     // the peer's barriers are initialised before anything remote can touch them
-  const uint32_t tmem_base = bars->tmem_base;
-  const long long d = a.dilation;
-  // work assignment: CTA `rank` of cluster `cid` takes tile 2*pair + rank of every pair it visits (MC2), else tile = pair
-  const int rank = MC2 ? (int)cluster_ctarank() : 0;
-  const int cid = MC2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int ncl = MC2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int n_pairs = MC2 ? (a.n_tiles + 1) / 2 : a.n_tiles;
-  struct TileInfo { int b, t0; bool valid, sub1; };
-  auto tile_info = [&](int tile) {
-    TileInfo ti;
-    ti.valid = tile < a.n_tiles;
-    ti.b = ti.valid ? tile / a.tiles_per_seg : 0;
-    ti.t0 = ti.valid ? (tile - ti.b * a.tiles_per_seg) * kTileRows : 0;
-    ti.sub1 = ti.valid && ti.t0 + kSubRows < a.T;
-    return ti;
-  };
-  auto tap_need = [&](const TileInfo& ti, int j, bool& live0, bool& live1) {
-    const long long ts0 = ti.t0 + (long long)(j - 7) * d;
-    live0 = ti.valid && tap_live(ts0, a.T);
-    live1 = ti.sub1 && tap_live(ts0 + kSubRows, a.T);
-  };
-
-  if (warp == 0) {
-    // ============================== TMA producer: activations ==============================
-    if (lane == 0) {
-      uint32_t slot = 0, phase = 0;
-      auto load_x = [&](int c0, int r, int b) {
-        ptx::mbar_wait(&bars->x_empty[slot], phase ^ 1);
-        if (a.dbg & 2) { ptx::mbar_arrive(&bars->x_full[slot]); if (++slot == kXSlots) { slot = 0; phase ^= 1; } return; }
-        ptx::mbar_expect_tx(&bars->x_full[slot], kSlotBytes);
-        uint8_t* dst = xring + (size_t)slot * kSlotBytes;
-        ptx::tma_load_3d(&tm_x, &bars->x_full[slot], dst, c0, r, b);
-        ptx::tma_load_3d(&tm_x, &bars->x_full[slot], dst + 16384, c0 + 128, r, b);
-        if (++slot == kXSlots) { slot = 0; phase ^= 1; }
-      };
-      for (int pair = cid; pair < n_pairs; pair += ncl) {
-        const TileInfo me = tile_info(MC2 ? 2 * pair + rank : pair);
-        // all fp16 (kind::f16) tap groups of the tile first, then all e4m3 (kind::f8f6f4) ones: the tensor pipe pays for
-        // every change of MMA kind, so the kinds are switched twice per tile instead of 30 times
-        for (int grp = 0; grp < 2; ++grp) {
-          for (int j = 0; j < kTaps; ++j) {
-            bool live0, live1;
-            tap_need(me, j, live0, live1);
-            const long long ts0 = me.t0 + (long long)(j - 7) * d, ts1 = ts0 + kSubRows;
-            if (live0) load_x(256 * grp, (int)ts0, me.b);
-            if (live1) load_x(256 * grp, (int)ts1, me.b);
-          }
-        }
-      }
-    }
-  } else if (warp == 3) {
-    // ============================== TMA producer: weights ==============================
-    if (lane == 0) {
-      uint32_t slot = 0, phase = 0;
-      for (int pair = cid; pair < n_pairs; pair += ncl) {
-        const TileInfo me = tile_info(MC2 ? 2 * pair + rank : pair), peer = tile_info(MC2 ? 2 * pair + (rank ^ 1) : a.n_tiles);
-        for (int grp = 0; grp < 2; ++grp) {
-          for (int j = 0; j < kTaps; ++j) {
-            bool l0, l1, p0 = false, p1 = false;
-            tap_need(me, j, l0, l1);
-            if (MC2) tap_need(peer, j, p0, p1);
-            if (!(l0 || l1 || p0 || p1)) continue;     // neither CTA of the pair touches this tap
-            const int wrow = (j * 4 + 2 * grp) * kCh;
-            ptx::mbar_wait(&bars->w_empty[slot], phase ^ 1);
-            if (!MC2 && (a.dbg & 2)) { ptx::mbar_arrive(&bars->w_full[slot]); if (++slot == kWSlots) { slot = 0; phase ^= 1; } continue; }
-            ptx::mbar_expect_tx(&bars->w_full[slot], kSlotBytes);
-            uint8_t* dst = wring + (size_t)slot * kSlotBytes;
-            if (MC2) {   // my half of the slot, delivered to both CTAs; the peer delivers the other half
-              tma_load_2d_multicast(&tm_w, &bars->w_full[slot], dst + rank * 16384, 0, wrow + rank * kCh, (uint16_t)0x3);
-            } else {
-              ptx::tma_load_2d(&tm_w, &bars->w_full[slot], dst, 0, wrow);
-              ptx::tma_load_2d(&tm_w, &bars->w_full[slot], dst + 16384, 0, wrow + kCh);
-            }
-            if (++slot == kWSlots) { slot = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = FMT == 1 ? ptx::umma_idesc_bf16_f32(kSubRows, kCh)
-                                          : ptx::umma_idesc_f16_f32(kSubRows, kCh);   // code 0 = F16 (kind::f16) = E4M3 (kind::f8f6f4)
-      uint32_t ws = 0, wph = 0, xs = 0, xph = 0;
-      // one slot pair = two 16 KB operand tiles per side, 4 K-steps of 32 bytes each.
-      // FMT 0: tile i of X multiplies tile i of W.   FMT 1: X = [hi | lo], W = [hi | lo]: hi*hi + lo*hi + hi*lo.
-      auto issue_group = [&](uint32_t x_addr, uint32_t w_addr, uint32_t d_tmem, bool first, bool f8) {
-        if (FMT == 1) {
-          const uint64_t xh = ptx::umma_desc_kmajor<128>(x_addr), xl = ptx::umma_desc_kmajor<128>(x_addr + 16384);
-          const uint64_t wh = ptx::umma_desc_kmajor<128>(w_addr), wl = ptx::umma_desc_kmajor<128>(w_addr + 16384);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            if (a.dbg & 1) continue;
-            ptx::umma_mma_f16kind(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u);
-            if (a.dbg & 32) continue;     // ablation: leading product only
-            ptx::umma_mma_f16kind(d_tmem, xl + adv, wh + adv, idesc, 1u);
-            ptx::umma_mma_f16kind(d_tmem, xh + adv, wl + adv, idesc, 1u);
-          }
-          return;
-        }
-#pragma unroll
-        for (int tl = 0; tl < 2; ++tl) {
-          const uint64_t xd = ptx::umma_desc_kmajor<128>(x_addr + tl * 16384), wd = ptx::umma_desc_kmajor<128>(w_addr + tl * 16384);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            const uint32_t accum = (first && tl == 0 && k == 0) ? 0u : 1u;
-            if ((a.dbg & 1) || (f8 && (a.dbg & 8)) || (!f8 && (a.dbg & 16))) continue;
-            if (f8) mma_f8(d_tmem, xd + adv, wd + adv, idesc, accum);
-            else ptx::umma_mma_f16kind(d_tmem, xd + adv, wd + adv, idesc, accum);
-          }
-        }
-      };
-      int it = 0;
-      for (int pair = cid; pair < n_pairs; pair += ncl, ++it) {
-        const TileInfo me = tile_info(MC2 ? 2 * pair + rank : pair), peer = tile_info(MC2 ? 2 * pair + (rank ^ 1) : a.n_tiles);
-        const int buf = it & 1;
-        ptx::mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t acc0 = tmem_base + (uint32_t)(buf * 2 + 0) * kCh;
-        const uint32_t acc1 = (a.dbg & 128) ? acc0 : tmem_base + (uint32_t)(buf * 2 + 1) * kCh;   // ablation: one accumulator
-        bool first0 = true, first1 = true;
-        for (int grp = 0; grp < 2; ++grp) {
-          for (int j = 0; j < kTaps; ++j) {
-            bool live0, live1, p0 = false, p1 = false;
-            tap_need(me, j, live0, live1);
-            if (MC2) tap_need(peer, j, p0, p1);
-            if (!(live0 || live1 || p0 || p1)) continue;
-            ptx::mbar_wait(&bars->w_full[ws], wph);     // also when only the peer needs it: a slot is released only after it landed
-            const uint32_t w_addr = ptx::smem_u32(wring + (size_t)ws * kSlotBytes);
-            if (live0) {
-              ptx::mbar_wait(&bars->x_full[xs], xph);
-              if (!(a.dbg & 256)) ptx::tc_fence_after();
-              issue_group(ptx::smem_u32(xring + (size_t)xs * kSlotBytes), w_addr, acc0, first0, grp == 1);
-              first0 = false;
-              if (a.dbg & 64) ptx::mbar_arrive(&bars->x_empty[xs]); else ptx::umma_commit(&bars->x_empty[xs]);
-              if (++xs == kXSlots) { xs = 0; xph ^= 1; }
-            }
-            if (live1) {
-              ptx::mbar_wait(&bars->x_full[xs], xph);
-              if (!(a.dbg & 256)) ptx::tc_fence_after();
-              issue_group(ptx::smem_u32(xring + (size_t)xs * kSlotBytes), w_addr, acc1, first1, grp == 1);
-              first1 = false;
-              if (a.dbg & 64) ptx::mbar_arrive(&bars->x_empty[xs]); else ptx::umma_commit(&bars->x_empty[xs]);
-              if (++xs == kXSlots) { xs = 0; xph ^= 1; }
-            }
-            if (MC2) umma_commit_multicast(&bars->w_empty[ws], (uint16_t)0x3);
-            else if (a.dbg & 64) ptx::mbar_arrive(&bars->w_empty[ws]);     // ablation (with bit 2 only): no commit per slot
-            else ptx::umma_commit(&bars->w_empty[ws]);
-            if (++ws == kWSlots) { ws = 0; wph ^= 1; }
-          }
-        }
-        ptx::umma_commit(&bars->tmem_full[buf]);
-      }
-    }
-  } else if (warp >= 4) {
-    // ============================== epilogue (256 threads: thread <-> one time row x one 64-channel half) ==============
-    // A warp may only read the TMEM lane quarter (warp % 4); warps 4-7 take channels 0-63, warps 8-11 channels 64-127.
-    const int q = warp & 3;
-    const int h = (warp - 4) >> 2;
-    const int rl = q * 32 + lane;
-    const float inv_scale = FMT == 0 ? __ldg(a.inv_scale) : 1.f;
-    int it = 0;
-    for (int pair = cid; pair < n_pairs; pair += ncl, ++it) {
-      const TileInfo me = tile_info(MC2 ? 2 * pair + rank : pair);
-      const int b = me.b, t0 = me.t0;
-      const int buf = it & 1;
-      const float4* film = a.film + (size_t)(a.n_cond > 1 ? b : 0) * kCh;
-      ptx::mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
-      ptx::tc_fence_after();
-      for (int sub = 0; sub < 2; ++sub) {
-        const int ts = t0 + sub * kSubRows;
-        if (!me.valid || ts >= a.T || (a.dbg & 4)) break;
-        const int t = ts + rl;
-        const bool row_ok = t < a.T;
-        const size_t row_off = ((size_t)b * a.T + (row_ok ? t : 0)) * kRowBytes;
-        const uint8_t* xrow = a.act_in + row_off;
-        uint8_t* yrow = a.act_out + row_off;
-        float o0 = 0.f, o1 = 0.f;
-        if constexpr (FMT == 0) {
-          // residual x_in of this row and channel half: 8 x 16 B of fp16 hi + 8 x 8 B of e4m3 lo, all requested up front
-          // so the L2 round trips overlap each other and the TMEM read
-          uint4 xh[8];
-          uint2 xl[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            xh[c] = make_uint4(0, 0, 0, 0);
-            xl[c] = make_uint2(0, 0);
-            if (row_ok) {
-              xh[c] = __ldg(reinterpret_cast<const uint4*>(xrow + h * 128 + c * 16));
-              xl[c] = __ldg(reinterpret_cast<const uint2*>(xrow + 256 + h * 64 + c * 8));
-            }
-          }
-          uint32_t acc[64];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * kCh + h * 64);
-          ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
-          ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {     // 8 channels per iteration, processed as 4 pairs
-            const uint32_t xhw[4] = {xh[c].x, xh[c].y, xh[c].z, xh[c].w};
-            const uint32_t xlw[2] = {xl[c].x, xl[c].y};
-            uint32_t oh[4];
-            uint32_t ol[2] = {0, 0}, oh8[2] = {0, 0};
-#pragma unroll
-            for (int pr = 0; pr < 4; ++pr) {
-              const int cl = c * 8 + 2 * pr;
-              const int ch = h * 64 + cl;
-              const float4 P0 = __ldg(film + ch), P1 = __ldg(film + ch + 1);
-              // x_in = fp16 hi + e4m3 lo * 2^-11  (two channels at once)
-              const float2 hif = __half22float2(*reinterpret_cast<const __half2*>(&xhw[pr]));
-              const unsigned short l8pair = (unsigned short)((xlw[pr >> 1] >> (16 * (pr & 1))) & 0xFFFFu);
-              const __half2_raw lraw = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)l8pair, __NV_E4M3);
-              const float2 lof = __half22float2(__half2(lraw));
-              const float xin0 = fmaf(lof.x, 1.f / kLoScale, hif.x), xin1 = fmaf(lof.y, 1.f / kLoScale, hif.y);
-              float u0 = fmaf(__uint_as_float(acc[cl]), inv_scale, P0.x);
-              float u1 = fmaf(__uint_as_float(acc[cl + 1]), inv_scale, P1.x);
-              u0 = u0 > 0.f ? u0 : 0.01f * u0;
-              u1 = u1 > 0.f ? u1 : 0.01f * u1;
-              u0 = fmaf(P0.y, u0, P0.z) + P0.w * xin0;
-              u1 = fmaf(P1.y, u1, P1.z) + P1.w * xin1;
-              if (a.fuse_out) {
-                o0 = fmaf(u0, __ldg(a.out_w + ch), o0);
-                o0 = fmaf(u1, __ldg(a.out_w + ch + 1), o0);
-                if (a.n_out > 1) {
-                  o1 = fmaf(u0, __ldg(a.out_w + kCh + ch), o1);
-                  o1 = fmaf(u1, __ldg(a.out_w + kCh + ch + 1), o1);
-                }
-              } else {
-                const __half2 hi2 = __floats2half2_rn(fminf(fmaxf(u0, -65504.f), 65504.f), fminf(fmaxf(u1, -65504.f), 65504.f));
-                const float2 hb = __half22float2(hi2);
-                oh[pr] = *reinterpret_cast<const uint32_t*>(&hi2);
-                const uint32_t l2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((u0 - hb.x) * kLoScale, (u1 - hb.y) * kLoScale),
-                                                                      __NV_SATFINITE, __NV_E4M3);
-                const uint32_t h2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(u0, u1), __NV_SATFINITE, __NV_E4M3);
-                ol[pr >> 1] |= l2 << (16 * (pr & 1));
-                oh8[pr >> 1] |= h2 << (16 * (pr & 1));
-              }
-            }
-            if (!a.fuse_out && row_ok) {
-              // the thread owns its row: every 32-byte sector it touches it fills; streaming stores (evict-first) keep
-              // the write-once output from displacing the tap tiles that 14 other taps still want from L2
-              __stcs(reinterpret_cast<uint4*>(yrow + h * 128 + c * 16), make_uint4(oh[0], oh[1], oh[2], oh[3]));
-              __stcs(reinterpret_cast<uint2*>(yrow + 256 + h * 64 + c * 8), make_uint2(ol[0], ol[1]));
-              __stcs(reinterpret_cast<uint2*>(yrow + 384 + h * 64 + c * 8), make_uint2(oh8[0], oh8[1]));
-            }
-          }
-        }
-        else {
-          // residual x_in of this row and channel half: 8 x 16 B of bf16 hi and 8 x 16 B of bf16 lo, requested up front
-          uint4 xh[8], xl[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            xh[c] = make_uint4(0, 0, 0, 0);
-            xl[c] = make_uint4(0, 0, 0, 0);
-            if (row_ok) {
-              xh[c] = __ldg(reinterpret_cast<const uint4*>(xrow + h * 256 + c * 16));
-              xl[c] = __ldg(reinterpret_cast<const uint4*>(xrow + h * 256 + 128 + c * 16));
-            }
-          }
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t acc[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * kCh + h * 64 + half * 32);
-            ptx::tmem_ld_32x32(taddr, acc);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const int c = half * 4 + c4;
-              const uint32_t xhw[4] = {xh[c].x, xh[c].y, xh[c].z, xh[c].w};
-              const uint32_t xlw[4] = {xl[c].x, xl[c].y, xl[c].z, xl[c].w};
-              uint32_t oh[4], ol[4];
-#pragma unroll
-              for (int pr = 0; pr < 4; ++pr) {
-                const int cl = c4 * 8 + 2 * pr;            // column inside this 32-column half
-                const int ch = h * 64 + half * 32 + cl;
-                const float4 P0 = __ldg(film + ch), P1 = __ldg(film + ch + 1);
-                const float xin0 = __uint_as_float(xhw[pr] << 16) + __uint_as_float(xlw[pr] << 16);
-                const float xin1 = __uint_as_float(xhw[pr] & 0xFFFF0000u) + __uint_as_float(xlw[pr] & 0xFFFF0000u);
-                float u0 = __uint_as_float(acc[cl]) + P0.x;
-                float u1 = __uint_as_float(acc[cl + 1]) + P1.x;
-                u0 = u0 > 0.f ? u0 : 0.01f * u0;
-                u1 = u1 > 0.f ? u1 : 0.01f * u1;
-                u0 = fmaf(P0.y, u0, P0.z) + P0.w * xin0;
-                u1 = fmaf(P1.y, u1, P1.z) + P1.w * xin1;
-                if (a.fuse_out) {
-                  o0 = fmaf(u0, __ldg(a.out_w + ch), o0);
-                  o0 = fmaf(u1, __ldg(a.out_w + ch + 1), o0);
-                  if (a.n_out > 1) {
-                    o1 = fmaf(u0, __ldg(a.out_w + kCh + ch), o1);
-                    o1 = fmaf(u1, __ldg(a.out_w + kCh + ch + 1), o1);
-                  }
-                } else {
-                  const __nv_bfloat16 h0 = __float2bfloat16_rn(u0), h1 = __float2bfloat16_rn(u1);
-                  const __nv_bfloat16 l0 = __float2bfloat16_rn(u0 - __bfloat162float(h0));
-                  const __nv_bfloat16 l1 = __float2bfloat16_rn(u1 - __bfloat162float(h1));
-                  oh[pr] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                  ol[pr] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                }
-              }
-              if (!a.fuse_out && row_ok) {
-                __stcs(reinterpret_cast<uint4*>(yrow + h * 256 + c * 16), make_uint4(oh[0], oh[1], oh[2], oh[3]));
-                __stcs(reinterpret_cast<uint4*>(yrow + h * 256 + 128 + c * 16), make_uint4(ol[0], ol[1], ol[2], ol[3]));
-              }
-            }
-          }
-        }
-        if (a.fuse_out) {
-          // the two channel halves of a row live in different warps: half 1 hands its partial sums over in shared memory
-          if (h == 1) opart[rl] = make_float2(o0, o1);
-          ptx::named_bar_sync(1, 256);
-          if (h == 0 && row_ok) {
-            const float2 pp = opart[rl];
-            a.out[((size_t)b * a.n_out + 0) * a.T + t] = fminf(fmaxf(o0 + pp.x + __ldg(a.out_b), -1.f), 1.f);
-            if (a.n_out > 1) a.out[((size_t)b * a.n_out + 1) * a.T + t] = fminf(fmaxf(o1 + pp.y + __ldg(a.out_b + 1), -1.f), 1.f);
-          }
-          ptx::named_bar_sync(2, 256);   // opart is reused by the next sub-tile
-        }
-      }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&bars->tmem_empty[buf]);
-    }
-  }
-
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (MC2) cluster_sync_all();     // nobody leaves while the peer may still multicast into it or arrive on its barriers
-  if (warp == 2) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-static int encode_bytes_map(CUtensorMap* m, const void* base, int rank, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2,
-                            cuuint32_t box0, cuuint32_t box1, bool swizzle) {
-  PFN_encodeTiled enc = tensor_map_encoder();
-  if (!enc) return 1;
-  cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0, d0 * d1};
-  cuuint32_t box[3] = {box0, box1, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, rank, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  MST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f16f8, rank %d, box %u x %u) failed: CUresult %d", rank, box0, box1, (int)r);
-  return 0;
-}
 
 }  // namespace f8
 
@@ -687,11 +231,11 @@ int tcn_f8_pack_layer(const float* conv_w, const float* bn_w, const float* bn_va
 }
 
 int tcn_f8_launch_block0(int n_inputs, const float* x, const float* w0, const float* film, int n_cond, void* act, int B, int T,
-                         cudaStream_t st) {
+                         unsigned int* range_flag, cudaStream_t st) {
   dim3 grid(cdiv(T, 256), B);
   const float4* f = reinterpret_cast<const float4*>(film);
-  if (n_inputs == 2) f8::block0_kernel<2><<<grid, 256, 0, st>>>(x, w0, f, n_cond, (uint8_t*)act, T);
-  else f8::block0_kernel<1><<<grid, 256, 0, st>>>(x, w0, f, n_cond, (uint8_t*)act, T);
+  if (n_inputs == 2) f8::block0_kernel<2><<<grid, 256, 0, st>>>(x, w0, f, n_cond, (uint8_t*)act, T, range_flag);
+  else f8::block0_kernel<1><<<grid, 256, 0, st>>>(x, w0, f, n_cond, (uint8_t*)act, T, range_flag);
   return launch_ok("tcn f8 block0_kernel");
 }
 
@@ -702,64 +246,6 @@ int tcn_f8_act_pack(const float* x, void* act, int B, int T, cudaStream_t st) {
 int tcn_f8_act_unpack(const void* act, float* y, int B, int T, cudaStream_t st) {
   f8::act_unpack_kernel<<<dim3(cdiv(T, 32), B), 256, 0, st>>>((const uint8_t*)act, y, T);
   return launch_ok("tcn f8 act_unpack_kernel");
-}
-
-template <int FMT>
-static int launch_block_impl(long long dilation, const void* w_layer, const float* inv_scale, const void* act_in, void* act_out,
-                             const float* film_layer, int n_cond, int B, int T, bool fuse_out, int n_out, const float* out_w,
-                             const float* out_b, float* out, cudaStream_t st) {
-  CUtensorMap tm_x, tm_w;
-  if (f8::encode_bytes_map(&tm_x, act_in, 3, f8::kRowBytes, T, B, 128, f8::kSubRows, true)) return 1;
-  if (f8::encode_bytes_map(&tm_w, w_layer, 2, 128, (cuuint64_t)f8::kTaps * 4 * f8::kCh, 1, 128, f8::kCh, true)) return 1;
-  f8::LayerArgs a;
-  a.B = B; a.T = T; a.dilation = (int)dilation;
-  a.tiles_per_seg = cdiv(T, f8::kTileRows);
-  a.n_tiles = B * a.tiles_per_seg;
-  a.n_cond = n_cond;
-  a.film = reinterpret_cast<const float4*>(film_layer);
-  a.inv_scale = inv_scale;
-  a.act_in = (const uint8_t*)act_in;
-  a.act_out = (uint8_t*)act_out;
-  a.fuse_out = fuse_out ? 1 : 0;
-  a.n_out = n_out; a.out_w = out_w; a.out_b = out_b; a.out = out;
-  { const char* e = getenv("MST_TCN_DBG"); a.dbg = e ? atoi(e) : 0; }
-  static int mc2 = -1;
-  if (mc2 < 0) { const char* e = getenv("MST_TCN_MULTICAST"); mc2 = (e && atoi(e) == 1) ? 1 : 0; }   // measured slower: off by default
-  if (mc2) {
-    MST_CUDA_OK(cudaFuncSetAttribute(f8::block_kernel<1, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f8::kSmemBytes));
-    const int n_pairs = (a.n_tiles + 1) / 2;
-    const int clusters = n_pairs < sm_count() / 2 ? n_pairs : sm_count() / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(f8::kThreads);
-    cfg.dynamicSmemBytes = f8::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    MST_CUDA_OK(cudaLaunchKernelEx(&cfg, f8::block_kernel<1, FMT>, tm_x, tm_w, a));
-    return launch_ok("tcn dual-ring block_kernel<mc2>");
-  }
-  MST_CUDA_OK(cudaFuncSetAttribute(f8::block_kernel<0, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f8::kSmemBytes));
-  const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-  f8::block_kernel<0, FMT><<<grid, f8::kThreads, f8::kSmemBytes, st>>>(tm_x, tm_w, a);
-  return launch_ok("tcn dual-ring block_kernel");
-}
-
-int tcn_f8_launch_block(long long dilation, const void* w_layer, const float* inv_scale, const void* act_in, void* act_out,
-                        const float* film_layer, int n_cond, int B, int T, bool fuse_out, int n_out, const float* out_w,
-                        const float* out_b, float* out, cudaStream_t st) {
-  return launch_block_impl<0>(dilation, w_layer, inv_scale, act_in, act_out, film_layer, n_cond, B, T, fuse_out, n_out, out_w,
-                              out_b, out, st);
-}
-
-// bf16 hi/lo activations and weights of tcn.cu (64-channel chunks) through the dual-ring pipeline
-int tcn_pipe2_launch_block(long long dilation, const void* w_layer, const void* act_in, void* act_out, const float* film_layer,
-                           int n_cond, int B, int T, bool fuse_out, int n_out, const float* out_w, const float* out_b,
-                           float* out, cudaStream_t st) {
-  return launch_block_impl<1>(dilation, w_layer, nullptr, act_in, act_out, film_layer, n_cond, B, T, fuse_out, n_out, out_w,
-                              out_b, out, st);
 }
 
 }  // namespace mst

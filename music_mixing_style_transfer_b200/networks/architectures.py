@@ -115,6 +115,19 @@ class _HParams(dict):
             raise AttributeError(k)
 
 
+_PRECISIONS = {"f16f8": _cabi.TCN_F16F8, "bf16x3": _cabi.TCN_BF16X3}
+
+
+def _precision_code(precision: str) -> int:
+    """'auto' starts in f16f8 (the caller then checks the range flag); the other names map to the C-ABI constants."""
+    if precision == "auto":
+        return _cabi.TCN_F16F8
+    try:
+        return _PRECISIONS[precision]
+    except KeyError:
+        raise ValueError(f"TCN precision must be 'auto', 'f16f8' or 'bf16x3', got {precision!r}") from None
+
+
 class _TcnEngine:
     """Packed weights + scratch for one list of TCN blocks (a whole TCNModel, or a stand-alone TCNBlock)."""
 
@@ -235,6 +248,11 @@ class TCNModel(nn.Module):
                               kernel_size=kernel_size, dilation_growth=dilation_growth, stack_size=stack_size,
                               cond_dim=cond_dim)
         self._engine = _TcnEngine(cfg)
+        # Operand format of the dilated blocks (include/mst_b200.h): "f16f8" (2 tensor units per MMA, activations must
+        # stay inside +-448), "bf16x3" (3 units, fp32 range) or "auto" = f16f8 with the range flag read back after the
+        # forward and one repeat in bf16x3 when it fired (FiLM's gamma is unbounded, network_utils.py:180-182).
+        self.precision = "auto"
+        self.last_range_excess = 0.0      # largest |activation| of the last forward that left the f16f8 range (0 = none)
         for n, blk in enumerate(self.blocks):
             blk._bind(self, n)
 
@@ -248,7 +266,12 @@ class TCNModel(nn.Module):
     def _packed(self, device):
         return self._engine.pack(self._raw(), _param_signature(self), device)
 
-    def forward(self, x, cond):
+    def forward(self, x, cond, out=None, range_flag=None):
+        """x [B, ninputs, T], cond [1 or B, cond_dim] (or one tensor per block) -> [B, noutputs, T].
+
+        Additions to the reference signature (both optional): `out` = preallocated output; `range_flag` = int32[1] CUDA
+        tensor that receives the f16f8 range flag WITHOUT a host read-back (for pipelined callers: check it later with
+        `flag.view(torch.float32).item() > 0` and call `rerun_bf16x3`)."""
         x = _cabi.require_cuda_f32(x, "TCNModel input")
         hp = self.hparams
         if x.dim() != 3 or x.shape[1] != hp.ninputs:
@@ -261,11 +284,35 @@ class TCNModel(nn.Module):
         if n_cond not in (1, B):
             raise RuntimeError(f"TCNModel: condition batch {n_cond} does not broadcast against input batch {B}")
         ws = eng.workspace(B, L, x.device)
-        out = torch.empty(B, hp.noutputs, L, dtype=torch.float32, device=x.device)
-        _cabi.check(_cabi.lib().mst_tcn_forward(ctypes.byref(eng.cfg), _cabi.ptr(eng.packed), _cabi.ptr(x),
-                                                _cabi.ptr(film), n_cond, _cabi.ptr(out), B, L, _cabi.ptr(ws),
-                                                ws.numel(), _cabi.current_stream()), "tcn_forward")
+        out = torch.empty(B, hp.noutputs, L, dtype=torch.float32, device=x.device) if out is None else out
+        code = _precision_code(self.precision)
+        flag = None
+        if code == _cabi.TCN_F16F8 and (self.precision == "auto" or range_flag is not None):
+            flag = torch.empty(1, dtype=torch.int32, device=x.device) if range_flag is None else range_flag
+
+        def run(precision_code, flag_t):
+            _cabi.check(_cabi.lib().mst_tcn_forward(ctypes.byref(eng.cfg), _cabi.ptr(eng.packed), _cabi.ptr(x),
+                                                    _cabi.ptr(film), n_cond, _cabi.ptr(out), B, L, _cabi.ptr(ws),
+                                                    ws.numel(), precision_code, _cabi.ptr(flag_t),
+                                                    _cabi.current_stream()), "tcn_forward")
+
+        run(code, flag)
+        if self.precision == "auto" and range_flag is None:
+            # 4-byte read-back (synchronises the stream): did an inter-block activation leave the f16f8 range?
+            excess = float(flag.view(torch.float32).item())
+            self.last_range_excess = excess
+            if excess > 0.0:
+                run(_cabi.TCN_BF16X3, None)
         return out
+
+    def rerun_bf16x3(self, x, cond, out):
+        """Repeat a forward whose deferred `range_flag` fired (see forward): same arguments, fp32-range operands."""
+        saved = self.precision
+        self.precision = "bf16x3"
+        try:
+            return self.forward(x, cond, out=out)
+        finally:
+            self.precision = saved
 
     def forward_layers(self, x, cond, on_launch=None):
         """Same computation as forward(), one C-ABI call per kernel launch.  `on_launch(name, phase)` is called with
@@ -282,10 +329,11 @@ class TCNModel(nn.Module):
         act = [ws[:half], ws[half:]]
         out = torch.empty(B, hp.noutputs, L, dtype=torch.float32, device=x.device)
         lib, cfg, st = _cabi.lib(), ctypes.byref(eng.cfg), _cabi.current_stream()
+        code = _precision_code(self.precision)
         note = on_launch if on_launch is not None else (lambda name, phase: None)
         note("tcn_block0_kernel", "begin")
         _cabi.check(lib.mst_tcn_block0_forward(cfg, _cabi.ptr(eng.packed), _cabi.ptr(x), _cabi.ptr(film), n_cond,
-                                               _cabi.ptr(act[0]), B, L, st), "tcn_block0_forward")
+                                               _cabi.ptr(act[0]), B, L, code, None, st), "tcn_block0_forward")
         note("tcn_block0_kernel", "end")
         cur = 0
         for n in range(1, hp.nblocks):
@@ -293,7 +341,7 @@ class TCNModel(nn.Module):
             note("tcn_block_umma_kernel", "begin")
             _cabi.check(lib.mst_tcn_layer_forward(cfg, _cabi.ptr(eng.packed), n, _cabi.ptr(act[cur]),
                                                   _cabi.ptr(act[cur ^ 1]), _cabi.ptr(film), n_cond, B, L,
-                                                  1 if last else 0, _cabi.ptr(out), st), "tcn_layer_forward")
+                                                  1 if last else 0, _cabi.ptr(out), code, None, st), "tcn_layer_forward")
             note("tcn_block_umma_kernel", "end")
             cur ^= 1
         return out
@@ -348,6 +396,7 @@ class TCNBlock(torch.nn.Module):
                                    groups=in_ch,
                                    bias=False)
         self._cond_dim = cond_dim
+        self.precision = "f16f8"     # stand-alone use only; inside a TCNModel the model's `precision` applies
         # owner = (TCNModel, index) when built by a TCNModel; a stand-alone block gets a private 2-block engine
         self.__dict__["_owner"] = None
         self.__dict__["_own_engine"] = None
@@ -391,9 +440,11 @@ class TCNBlock(torch.nn.Module):
             eng = model._engine
             eng.pack(model._raw(), _param_signature(model), x.device)
             nblocks = model.hparams.nblocks
+            code = _precision_code(model.precision)
         else:
             eng, idx = self._standalone_engine(x.device)
             nblocks = 2
+            code = _precision_code(self.precision)
         film = eng.film(p, nblocks)
         n_cond = film.shape[1]
         if n_cond not in (1, B):
@@ -402,5 +453,5 @@ class TCNBlock(torch.nn.Module):
         y = torch.empty(B, self.out_ch, L, dtype=torch.float32, device=x.device)
         _cabi.check(_cabi.lib().mst_tcn_block_forward(ctypes.byref(eng.cfg), _cabi.ptr(eng.packed), idx, _cabi.ptr(x),
                                                       _cabi.ptr(film), n_cond, _cabi.ptr(y), B, L, _cabi.ptr(ws),
-                                                      ws.numel(), _cabi.current_stream()), "tcn_block_forward")
+                                                      ws.numel(), code, _cabi.current_stream()), "tcn_block_forward")
         return y

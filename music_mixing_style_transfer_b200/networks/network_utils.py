@@ -25,15 +25,23 @@ def _param_signature(module: nn.Module):
 
 
 class _Workspace:
-    """Grow-only device scratch buffer owned by a module (torch-allocated; the library never allocates)."""
+    """Grow-only device scratch buffers owned by a module (torch-allocated; the library never allocates).
+
+    One buffer per (device, CUDA stream): two forwards of the same module issued on different streams must not share
+    their activation ping-pong buffers (the FX path keys its workspace the same way)."""
 
     def __init__(self):
-        self.buf = None
+        self.bufs = {}
 
     def get(self, nbytes: int, device) -> torch.Tensor:
-        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
-            self.buf = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
-        return self.buf
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = None
+            self.bufs.pop(key, None)     # release the old buffer before growing
+            buf = torch.empty(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
+            self.bufs[key] = buf
+        return buf
 
 
 # 1-dimensional convolutional layer, in the order of conv -> norm -> activation

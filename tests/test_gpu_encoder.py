@@ -74,6 +74,38 @@ def test_full_encoder_matches_oracle(B, L):
     print("encoder parity", B, L, e)
 
 
+@pytest.mark.parametrize("B,L", [(2, 262144), (3, 262144), (2, 441000), (1, 524288)])
+def test_full_encoder_at_benchmark_lengths(B, L):
+    """The headline workload's shapes: L = 262144 (BASELINE configs[1]; T = 64 ... 65536 per block, i.e. the M-tiling of
+    enc_conv_umma_kernel at its benchmark geometry), 441000 (configs[0], feature_extraction.py's 10 s clip) and 2^19 (the
+    reference's default segment).  Rows of a batch of 32 are covered by the batch-permutation property in
+    test_gpu_fullsize.py; here every row is compared against the CPU oracle."""
+    oracle_threads()
+    enc, _ = models()
+    esd, _ = state_dicts()
+    x = W.synthetic_audio(B, L, seed=60 + B)
+    with torch.no_grad():
+        ref = O.fxencoder_forward(x, esd, W.ENC_KERNELS, W.ENC_STRIDES)
+        got = enc(x.cuda()).cpu()
+    e = err_stats(got, ref)
+    assert got.shape == (B, 2048)
+    assert e["max"] <= 1e-4 and e["rel"] <= 2e-5, (B, L, e)
+    print("encoder parity (benchmark length)", B, L, e)
+
+
+def test_full_encoder_batch32_rows_match_small_batches():
+    """B = 32 at L = 262144 (NB segments x TT steps tiles differ from B = 2): rows must equal the same rows run as B = 2,
+    which test_full_encoder_at_benchmark_lengths pins to the oracle."""
+    enc, _ = models()
+    x = W.synthetic_audio(32, 262144, seed=62).cuda()
+    with torch.no_grad():
+        big = enc(x)
+        for i in (0, 13, 30):
+            small = enc(x[i:i + 2].contiguous())
+            d = (big[i:i + 2] - small).abs().max().item()
+            assert d <= 2e-6, (i, d)     # same arithmetic per row; only the tile a row lands in differs
+
+
 def test_encoder_golden_vector():
     enc, _ = models()
     x = W.synthetic_audio(2, 32768, seed=11)

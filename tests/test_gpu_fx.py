@@ -93,17 +93,6 @@ def test_edge_cases_silence_and_mono():
     assert e["rms"] <= RMS_TOL, e
 
 
-def test_v1_kernels_still_match_oracle():
-    """MST_FX_IMPL=v1 keeps the first-generation kernels (fx.cu) selectable for A/B timing: they must stay parity-green.
-    The switch is read once per process, so run a child."""
-    import os, subprocess, sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, MST_FX_IMPL="v1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_fx.py"), "-m", "gpu", "-x", "-q",
-                        "-k", "not v1_kernels"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-
-
 @pytest.mark.parametrize("L", [8192, 8192 * 3 + 4, 8191, 12289])
 def test_tile_boundaries(L):
     """fx2.cu tiles: EQ 8192 frames, compressor 4096 frames; lengths at / around the tile size, with L % 4 != 0 (scalar staging

@@ -43,6 +43,24 @@ def test_golden_tcn_small_and_percond():
     assert np.abs(y2 - fixtures.load_golden("tcn_percond.npz")["y"]).max() <= 2e-6
 
 
+def test_golden_real_audio_windows():
+    """The oracle on REAL audio (windows of samples/style_transfer/#0 decoded by the reference's loader) against the
+    reference's outputs on the same windows (tests/golden/real_audio.npz, oracle/make_golden_real.py)."""
+    esd, tsd = sds()
+    g = fixtures.load_golden("real_audio.npz")
+    x = torch.from_numpy((g["x_vocals"].astype(np.float64).T / 32768.0).astype(np.float32))[None]
+    with torch.no_grad():
+        emb = O.fxencoder_forward(x, esd, W.ENC_KERNELS, W.ENC_STRIDES)[0].numpy()
+        y = O.tcn_forward(x, torch.from_numpy(g["cond_vocals"])[None], tsd)[0].numpy()
+    assert np.abs(emb - g["emb_vocals"]).max() <= 1e-6 * max(1.0, np.abs(g["emb_vocals"]).max())
+    assert np.abs(y - g["y_vocals"]).max() <= 2e-6
+    P = g["fx_params"]
+    for i in range(2):
+        xi = (g[f"fx_x{i}"].astype(np.float64) / 32768.0).astype(np.float32)
+        yi = fx_oracle.fx_chain(xi, P[i])
+        assert np.sqrt(np.mean((yi - g[f"fx_y{i}"]) ** 2)) <= 1e-7, i
+
+
 def test_golden_tcn_blocks():
     _, tsd = sds()
     g = fixtures.load_golden("tcn_blocks.npz")
