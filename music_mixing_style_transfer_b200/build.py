@@ -46,15 +46,21 @@ def needs_build() -> bool:
         return fh.read().strip() != _digest()
 
 
-def build_variant(tag: str, defines) -> str:
-    """Development builds with extra -D switches (ablation studies): build/<tag>/libmst_b200.so, never the product path."""
+def build_variant(tag: str, defines, csrc: str = None) -> str:
+    """Development builds with extra -D switches (ablation studies) or from another source directory (A/B against an older
+    commit: `git archive <rev> music_mixing_style_transfer_b200/csrc include | tar -x -C /tmp/rev`): build/<tag>/libmst_b200.so,
+    never the product path."""
+    csrc = CSRC if csrc is None else csrc
     out_dir = os.path.join(PKG_DIR, "build", tag)
     os.makedirs(out_dir, exist_ok=True)
     objs, procs = [], []
     for src in SOURCES:
         obj = os.path.join(out_dir, src.replace(".cu", ".o"))
+        if not os.path.exists(os.path.join(csrc, src)):
+            continue
         procs.append(subprocess.Popen([_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-c",
-                                       os.path.join(CSRC, src), "-o", obj]))
+                                       os.path.join(csrc, src), "-o", obj], stdout=subprocess.DEVNULL,
+                                      stderr=subprocess.DEVNULL))
         objs.append(obj)
     if any(p.wait() != 0 for p in procs):
         raise RuntimeError("nvcc failed")
@@ -100,5 +106,6 @@ if __name__ == "__main__":
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--variant", nargs="+", metavar=("TAG", "DEFINE"), help="development build: TAG then -D defines")
+    ap.add_argument("--csrc", default=None, help="with --variant: compile the sources of this directory instead")
     a = ap.parse_args()
-    print(build_variant(a.variant[0], a.variant[1:]) if a.variant else build(a.force, a.verbose))
+    print(build_variant(a.variant[0], a.variant[1:], a.csrc) if a.variant else build(a.force, a.verbose))

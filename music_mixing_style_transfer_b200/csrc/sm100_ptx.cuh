@@ -104,6 +104,13 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA store source)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// two fp32 -> packed fp16 pair (lo = a, hi = b), round to nearest, clamped to the finite fp16 range (F2FP.SATFINITE)
+__device__ __forceinline__ uint32_t cvt_f16x2_satfinite(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 // ---------------------------------------------------------------- named barriers (sub-CTA sync)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

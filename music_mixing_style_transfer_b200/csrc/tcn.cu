@@ -27,9 +27,10 @@
 //   warp 1   MMA issuer: the whole warp runs the uniform loop, the tcgen05.mma / commit instructions are predicated on the
 //            elected lane -> straight UTCHMMA sequences from uniform registers (8 or 12 MMAs per slot pair)
 //   warp 2   TMEM allocator (512 columns = 2 tiles x 2 sub-tiles x 128 fp32 columns -> double-buffered accumulators)
-//   warps 4-7 epilogue: tcgen05.ld -> +BN bias -> LeakyReLU -> FiLM -> + res*x_in (x_in tile TMA-loaded) -> split to
-//            bf16 hi/lo -> swizzled shared tile -> TMA store;  the LAST block instead fuses Conv1d(128->2,k=1)+clamp
-//            and writes the fp32 [B,2,L] output directly (the 128-channel tensor of block 13 never touches HBM).
+//   warps 4-7 epilogue: tcgen05.ld -> +BN bias -> LeakyReLU -> FiLM -> + res*x_in (x_in tile TMA-loaded, requested one piece
+//            ahead) -> re-split -> swizzled shared tile -> TMA store;
+//            the LAST block instead fuses Conv1d(128->2,k=1)+clamp and writes the fp32 [B,2,L] output directly (the
+//            128-channel tensor of block 13 never touches HBM).
 // Taps whose shifted tile lies entirely in the zero padding are skipped by producer and issuer alike.
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
@@ -380,7 +381,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   constexpr int kKcPerTap = kCh / KCH;                 // 2 or 4 input-channel chunks per tap
   constexpr int kHalf = kSubRows * KCH * 2;            // bytes of one hi (or lo) operand tile: 16 KB / 8 KB
   constexpr int kSlotBytes = 2 * kHalf;
-  constexpr int kNumSlots = kRingBytes / kSlotBytes;   // 6 / 12
+  constexpr int kNumSlots = kRingBytes / kSlotBytes;   // 6
   constexpr int kK16 = KCH / 16;                       // MMA K-steps per slot
   constexpr int kSwz = KCH * 2;                        // swizzle span in bytes (128 / 64)
   extern __shared__ uint8_t smem_raw[];
@@ -609,11 +610,43 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     }
   } else if (warp >= 4) {
     // ============================== epilogue (128 threads, thread <-> one time row) ==============================
+    // Pieces = (sub-tile, channel half).  The residual tile of the NEXT piece is requested as soon as the TMA store of the
+    // current one has read the staging buffer (for the first piece of the next tile: long before its accumulator is ready),
+    // by the same thread that issued the store.  What was tried and measured on top (profiles/r02_tcn_ablation.md): a second
+    // epilogue group with its own staging buffer (sub-tile g drained by group g, 5-slot ring) -- more cycles per launch at a
+    // higher clock, the same milliseconds: the kernel runs AT the 1000 W power cap, only energy per tile moves its time.
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int et = threadIdx.x - 128;       // 0..127
     const int rl = q * 32 + lane;           // row inside the sub-tile == TMEM lane
+    uint64_t* stage_full = &bars->stage_full;
     uint32_t stage_phase = 0;
     float vmax = 0.f;                       // FMT 1: max |activation| this thread re-split (operand-range guard)
+    // residual x_in of channels 64h .. 64h+63, rows ts .. ts+127 of segment b -> staging (issued by thread 0 of the group)
+    auto request_residual = [&](int h, int ts, int b) {
+      if (FMT == 1) {
+        // the fp16 plane h (16 KB, SWIZZLE_128B) and half of the e4m3 remainder plane (64 bytes per row, 8 KB, SWIZZLE_64B)
+        ptx::mbar_expect_tx(stage_full, 16384 + 8192);
+        ptx::tma_load_3d(&tm_xs, stage_full, staging, 128 * h, ts, b);
+        ptx::tma_load_3d(&tm_l8, stage_full, staging + 16384, 256 + 64 * h, ts, b);
+      } else {
+        ptx::mbar_expect_tx(stage_full, kStageBytes);
+        ptx::tma_load_3d(&tm_xs, stage_full, staging, (2 * h) * 64, ts, b);              // x_in hi, ch 64h..
+        ptx::tma_load_3d(&tm_xs, stage_full, staging + 16384, (2 * h + 1) * 64, ts, b);  // x_in lo
+      }
+    };
+    // requests the h = 0 residual tile of the first live sub-tile at or after (tile, sub) in processing order (thread 0 only)
+    auto request_next = [&](int tile, int sub) {
+      if (MST_TCN_ABLATE & 2) return;
+      for (; tile < a.n_tiles; tile += gridDim.x, sub = 0) {
+        const TcnTile c = tcn_tile<PAIRED>(tile, a);
+        if (!c.sub0) continue;
+        for (; sub < 2; ++sub) {
+          const long long ts = sub == 0 ? c.r0 : c.r1;
+          if (ts < a.T) { request_residual(0, (int)ts, c.b); return; }
+        }
+      }
+    };
+    if (et == 0) request_next(blockIdx.x, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
       const TcnTile c = tcn_tile<PAIRED>(tile, a);
@@ -625,32 +658,15 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       ptx::tc_fence_after();
       for (int sub = 0; sub < 2; ++sub) {
         const int ts = (int)(sub == 0 ? c.r0 : c.r1);
-        if (ts >= a.T) break;
-        if (MST_TCN_ABLATE & 2) break;
+        if (ts >= a.T || (MST_TCN_ABLATE & 2)) break;
         float o0 = 0.f, o1 = 0.f;
         for (int h = 0; h < 2; ++h) {
-          // staging is free once the previous TMA store has read it and every thread has left the previous half
-          if (et == 0) ptx::tma_store_wait_read0();
-          ptx::named_bar_sync(1, 128);
-          if (et == 0) {
-            if (FMT == 1) {
-              // x_in of channels 64h .. 64h+63: the fp16 plane h (16 KB, SWIZZLE_128B) and half of the e4m3 remainder plane
-              // (64 bytes per row, 8 KB, SWIZZLE_64B)
-              ptx::mbar_expect_tx(&bars->stage_full, 16384 + 8192);
-              ptx::tma_load_3d(&tm_xs, &bars->stage_full, staging, 128 * h, ts, b);
-              ptx::tma_load_3d(&tm_l8, &bars->stage_full, staging + 16384, 256 + 64 * h, ts, b);
-            } else {
-              ptx::mbar_expect_tx(&bars->stage_full, kStageBytes);
-              ptx::tma_load_3d(&tm_xs, &bars->stage_full, staging, (2 * h) * 64, ts, b);              // x_in hi, ch 64h..
-              ptx::tma_load_3d(&tm_xs, &bars->stage_full, staging + 16384, (2 * h + 1) * 64, ts, b);  // x_in lo
-            }
-          }
           uint32_t acc[64];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * kCh + h * 64);
           ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
           ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
           ptx::tmem_ld_wait();
-          ptx::mbar_wait(&bars->stage_full, stage_phase);
+          ptx::mbar_wait(stage_full, stage_phase);
           stage_phase ^= 1;
           uint8_t* rowp = staging + rl * 128;
           if constexpr (FMT == 1) {
@@ -661,9 +677,9 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             uint8_t* hrow8 = staging + 24576 + rl * 64;
             const int sw64 = (rl >> 1) & 3;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {     // 8 channels per iteration
-              const int off = ((c ^ (rl & 7)) << 4);
-              const int off8 = (((c >> 1) ^ sw64) << 4) + (c & 1) * 8;
+            for (int c8 = 0; c8 < 8; ++c8) {     // 8 channels per iteration
+              const int off = ((c8 ^ (rl & 7)) << 4);
+              const int off8 = (((c8 >> 1) ^ sw64) << 4) + (c8 & 1) * 8;
               const uint4 xh = *reinterpret_cast<const uint4*>(rowp + off);
               const uint2 xl = *reinterpret_cast<const uint2*>(lrow + off8);
               const uint32_t xhw[4] = {xh.x, xh.y, xh.z, xh.w};
@@ -671,7 +687,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
               uint32_t oh[4], ol[2] = {0, 0}, oh8[2] = {0, 0};
 #pragma unroll
               for (int pr = 0; pr < 4; ++pr) {
-                const int cl = c * 8 + 2 * pr;
+                const int cl = c8 * 8 + 2 * pr;
                 const int ch = h * 64 + cl;
                 const float4 P0 = __ldg(film + ch), P1 = __ldg(film + ch + 1);
                 // x_in = fp16 hi + e4m3 lo * 2^-11  (two channels at once)
@@ -682,8 +698,8 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 const float xin0 = fmaf(lof.x, 1.f / 2048.f, hif.x), xin1 = fmaf(lof.y, 1.f / 2048.f, hif.y);
                 float u0 = fmaf(__uint_as_float(acc[cl]), inv_scale, P0.x);
                 float u1 = fmaf(__uint_as_float(acc[cl + 1]), inv_scale, P1.x);
-                u0 = u0 > 0.f ? u0 : 0.01f * u0;
-                u1 = u1 > 0.f ? u1 : 0.01f * u1;
+                u0 = fmaxf(u0, 0.01f * u0);      // LeakyReLU(0.01): max(u, 0.01 u)
+                u1 = fmaxf(u1, 0.01f * u1);
                 u0 = fmaf(P0.y, u0, P0.z) + P0.w * xin0;
                 u1 = fmaf(P1.y, u1, P1.z) + P1.w * xin1;
                 if (a.fuse_out) {
@@ -695,9 +711,9 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                   }
                 } else {
                   vmax = fmaxf(vmax, fmaxf(fabsf(u0), fabsf(u1)));
-                  const __half2 hi2 = __floats2half2_rn(fminf(fmaxf(u0, -65504.f), 65504.f), fminf(fmaxf(u1, -65504.f), 65504.f));
-                  const float2 hb = __half22float2(hi2);
-                  oh[pr] = *reinterpret_cast<const uint32_t*>(&hi2);
+                  const uint32_t hbits = ptx::cvt_f16x2_satfinite(u0, u1);       // fp16 pair, clamped to +-65504
+                  const float2 hb = __half22float2(*reinterpret_cast<const __half2*>(&hbits));
+                  oh[pr] = hbits;
                   const uint32_t l2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((u0 - hb.x) * 2048.f, (u1 - hb.y) * 2048.f),
                                                                         __NV_SATFINITE, __NV_E4M3);
                   const uint32_t h2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(u0, u1), __NV_SATFINITE, __NV_E4M3);
@@ -711,62 +727,62 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 *reinterpret_cast<uint2*>(hrow8 + off8) = make_uint2(oh8[0], oh8[1]);
               }
             }
+          } else {
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+              const int off = ((c8 ^ (rl & 7)) << 4);  // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+              const uint4 xh = *reinterpret_cast<const uint4*>(rowp + off);
+              const uint4 xl = *reinterpret_cast<const uint4*>(rowp + 16384 + off);
+              const uint32_t xhw[4] = {xh.x, xh.y, xh.z, xh.w}, xlw[4] = {xl.x, xl.y, xl.z, xl.w};
+              uint32_t oh[4], ol[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float v[2];
+#pragma unroll
+                for (int sidx = 0; sidx < 2; ++sidx) {
+                  const int cl = c8 * 8 + e * 2 + sidx;
+                  const int ch = h * 64 + cl;
+                  const float4 P = __ldg(film + ch);
+                  const float xin = sidx == 0 ? bf16_lo_f(xhw[e]) + bf16_lo_f(xlw[e]) : bf16_hi_f(xhw[e]) + bf16_hi_f(xlw[e]);
+                  float u = __uint_as_float(acc[cl]) + P.x;
+                  u = fmaxf(u, 0.01f * u);
+                  u = fmaf(P.y, u, P.z) + P.w * xin;
+                  v[sidx] = u;
+                  if (a.fuse_out) {
+                    o0 = fmaf(u, __ldg(a.out_w + ch), o0);
+                    if (a.n_out > 1) o1 = fmaf(u, __ldg(a.out_w + kCh + ch), o1);
+                  }
+                }
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(v[0], h0, l0);
+                split_bf16(v[1], h1, l1);
+                oh[e] = pack_bf16(h0, h1);
+                ol[e] = pack_bf16(l0, l1);
+              }
+              if (!a.fuse_out) {
+                *reinterpret_cast<uint4*>(rowp + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                *reinterpret_cast<uint4*>(rowp + 16384 + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+              }
+            }
+          }
+          // every thread of the group is done with the staging tile (reads, and the in-place rewrite when it is stored)
+          if (!a.fuse_out) ptx::fence_proxy_async_smem();
+          ptx::named_bar_sync(1, 128);
+          if (et == 0) {
             if (!a.fuse_out) {
-              ptx::fence_proxy_async_smem();
-              ptx::named_bar_sync(2, 128);
-              if (et == 0) {
+              if (FMT == 1) {
                 ptx::tma_store_3d(&tm_y, staging, 128 * h, ts, b);
                 ptx::tma_store_3d(&tm_y8, staging + 16384, 256 + 64 * h, ts, b);
                 ptx::tma_store_3d(&tm_y8, staging + 24576, 384 + 64 * h, ts, b);
-                ptx::tma_store_commit();
+              } else {
+                ptx::tma_store_3d(&tm_y, staging, (2 * h) * 64, ts, b);
+                ptx::tma_store_3d(&tm_y, staging + 16384, (2 * h + 1) * 64, ts, b);
               }
-            }
-            continue;
-          }
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int off = ((c ^ (rl & 7)) << 4);  // 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
-            const uint4 xh = *reinterpret_cast<const uint4*>(rowp + off);
-            const uint4 xl = *reinterpret_cast<const uint4*>(rowp + 16384 + off);
-            const uint32_t xhw[4] = {xh.x, xh.y, xh.z, xh.w}, xlw[4] = {xl.x, xl.y, xl.z, xl.w};
-            uint32_t oh[4], ol[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float v[2];
-#pragma unroll
-              for (int s = 0; s < 2; ++s) {
-                const int cl = c * 8 + e * 2 + s;
-                const int ch = h * 64 + cl;
-                const float4 P = __ldg(film + ch);
-                const float xin = s == 0 ? bf16_lo_f(xhw[e]) + bf16_lo_f(xlw[e]) : bf16_hi_f(xhw[e]) + bf16_hi_f(xlw[e]);
-                float u = __uint_as_float(acc[cl]) + P.x;
-                u = u > 0.f ? u : 0.01f * u;
-                u = fmaf(P.y, u, P.z) + P.w * xin;
-                v[s] = u;
-                if (a.fuse_out) {
-                  o0 = fmaf(u, __ldg(a.out_w + ch), o0);
-                  if (a.n_out > 1) o1 = fmaf(u, __ldg(a.out_w + kCh + ch), o1);
-                }
-              }
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(v[0], h0, l0);
-              split_bf16(v[1], h1, l1);
-              oh[e] = pack_bf16(h0, h1);
-              ol[e] = pack_bf16(l0, l1);
-            }
-            if (!a.fuse_out) {
-              *reinterpret_cast<uint4*>(rowp + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-              *reinterpret_cast<uint4*>(rowp + 16384 + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-            }
-          }
-          if (!a.fuse_out) {
-            ptx::fence_proxy_async_smem();
-            ptx::named_bar_sync(2, 128);
-            if (et == 0) {
-              ptx::tma_store_3d(&tm_y, staging, (2 * h) * 64, ts, b);
-              ptx::tma_store_3d(&tm_y, staging + 16384, (2 * h + 1) * 64, ts, b);
               ptx::tma_store_commit();
+              ptx::tma_store_wait_read0();       // the staging tile may be overwritten once the store has read it
             }
+            if (h == 0) request_residual(1, ts, b);
+            else request_next(tile, sub + 1);
           }
         }
         if (a.fuse_out) {

@@ -1,30 +1,41 @@
 """
-    Inference code of music mixing style transfer on the B200 engine -- the entry that mirrors the reference's
-    `inference/style_transfer.py` (class Mixing_Style_Transfer_Inference :27, inference :112, inference_interpolation
-    :181, batchwise_segmentization :274, flags :346-381).
+    Music mixing style transfer on the B200 engine -- drop-in for the reference's `inference/style_transfer.py`
+    (class Mixing_Style_Transfer_Inference :27, inference :112, inference_interpolation :181, batchwise_segmentization
+    :274, flags :346-381): same flags, same directory layout, same output files.
 
-    Process : converts the mixing style of the input music recording to that of the refernce music.
-                files inside the target directory should be organized as follow
-                    "path_to_data_directory"/"song_name_#1"/input.wav
-                    "path_to_data_directory"/"song_name_#1"/reference.wav
-                    ...
-                where the 'input' and 'reference' should share the same names.
+        "path_to_data_directory"/"song_name_#1"/<stem dir>/input/{drums,bass,other,vocals}.wav
+        "path_to_data_directory"/"song_name_#1"/<stem dir>/reference/{...}.wav        (+ reference_B for --interpolation)
+      <stem dir> = `--stem_level_directory_name` with `--do_not_separate True`, else `separated/<separation_model>`
+      (data_loader/data_loader.py:555-556).
 
-    What is the same: flags, directory layout, segmentation (incl. the extra zero segment when the length is an exact
-    multiple, :287-288), per-stem encoder -> mean embedding -> TCN -> concat -> crop -> 4-stem sum -> PCM_16 files,
-    interpolation weights indexed by batch (:250).
-    What differs, on purpose: (a) the networks run on libmst_b200.so (CUDA only, no CPU mode); (b) the embedding is the
-    mean over ALL reference segments also when the last batch is short, where the reference's torch.stack would throw
-    (:152); (c) under torchrun (WORLD_SIZE > 1) input batches are sharded over the ranks (shard.py); (d) the CPU
-    "FX normalisation" pre-step (--normalize_input, data_loader.py:586-587) and the demucs subprocess (:77-90) are outside
-    this engine: pass --normalize_input False --do_not_separate True with stems already separated; (e) the host I/O either
-    side of the forward runs on the device (wav_io.py / csrc/pcm.cu): raw int16 PCM is copied to the GPU and
-    converted / de-interleaved / clamped there, segments are cut from the device-resident stem, the converted stems stay
-    on the device, and remix + PCM_16 quantisation produce ONE int16 mixture that is copied back and written -- bit-identical
-    to the host path (`--device_io False` keeps that path).
+    What is computed is the reference's: every stem is cut into zero-padded segments (a FULL extra zero segment when the
+    length is an exact multiple, :287-288), the reference stem's segments go through the FXencoder and are averaged, the
+    input stem's segments go through the TCN conditioned on that embedding (interpolation: w A + (1 - w) B with w indexed
+    by the reference's BATCH index, :250), segments are concatenated, cropped, the stems summed and written as PCM_16.
+
+    How it is scheduled is not the reference's per-stem / per-batch loop.  A song is one job:
+      1. all stems are decoded on the device from raw PCM (wav_io.py / csrc/pcm.cu); the next song's files are read into
+         pinned memory by a loader thread while this one computes;
+      2. the segments of ALL stems form one row table [n_stems * n_segments, 2, segment]; under torchrun the rows are
+         sharded over the ranks -- reference rows and input rows alike, so no GPU idles behind rank 0 and the result does
+         not depend on `--batch_size` being large enough to shard (the reference's default is 1);
+      3. encoder: per-stem embedding sums of the local rows, ONE all-reduce of [n_refs, n_stems, 2048] floats;
+      4. TCN: local rows in launches bounded by activation memory, per-row conditioning (FiLM broadcasts per row,
+         network_utils.py:180-182); the f16f8 range flags of all launches are read back once, flagged launches repeat in
+         bf16x3; ONE all-gather of the output rows;
+      5. rank 0 crops, remixes and quantises on the device; the int16 mixture is copied back asynchronously and a writer
+         thread puts it on disk while the next song computes.
+    `--batch_size` therefore only carries its reference semantics (the interpolation weight index) -- not memory, not speed.
+
+    Outside this engine (raise, never silently skipped): the demucs subprocess (:77-90; pass --do_not_separate True with
+    stems already separated) and the normalisation effects that mixing_manipulator/data_normalization.py does not yet run
+    on the GPU (see Audio_Effects_Normalizer there).  CUDA only.
 """
 import os
+import queue
 import sys
+import threading
+import time
 import wave
 from glob import glob
 
@@ -33,90 +44,169 @@ import torch
 
 currentdir = os.path.dirname(os.path.realpath(__file__))
 sys.path.append(os.path.dirname(os.path.dirname(currentdir)))
-from music_mixing_style_transfer_b200.networks import FXencoder, TCNModel  # noqa: E402
 from music_mixing_style_transfer_b200 import shard, wav_io  # noqa: E402
+from music_mixing_style_transfer_b200.inference._common import (checkpoint_state_dict, dump_arguments,  # noqa: E402
+                                                                 segment_into_batches)
+from music_mixing_style_transfer_b200.networks import FXencoder, TCNModel  # noqa: E402
+
+# time rows (segments x samples) one TCN launch chain may hold: 2 activation buffers of 512 B per row -> 8.6 GB
+MAX_ROWS_PER_LAUNCH = 1 << 23
 
 
-# ---- WAV I/O with the reference loader's semantics (mixing_style_transfer/data_loader/loader_utils.py:47-70) ----
 def load_wav_segment(audio_path, start_point=None, duration=None, axis=1, sample_rate=44100):
-    start_point = 0 if start_point is None else start_point
-    pt_wav = wave.open(audio_path, 'r')
-    duration = pt_wav.getnframes() if duration is None else duration
-    if pt_wav.getframerate() != sample_rate:
-        raise ValueError(f"ValueError: input audio's sample rate should be {sample_rate}")
-    pt_wav.setpos(start_point)
-    x = pt_wav.readframes(duration)
-    if pt_wav.getsampwidth() == 2:
-        x = np.frombuffer(x, dtype=np.int16)
-        X = x / float(2 ** 15)    # needs to be 16 bit format
-    elif pt_wav.getsampwidth() == 4:
-        x = np.frombuffer(x, dtype=np.int32)
-        X = x / float(2 ** 31)    # needs to be 32 bit format
-    else:
-        raise ValueError("ValueError: input audio's bit depth should be 16 or 32-bit")
-    # exception for stereo channels
-    if pt_wav.getnchannels() == 2:
-        X_l = np.expand_dims(X[::2], axis=axis)
-        X_r = np.expand_dims(X[1::2], axis=axis)
-        X = np.concatenate((X_l, X_r), axis=axis)
-    return X
+    """Host decode with the reference loader's result (data_loader/loader_utils.py:47-70): float64 in [-1, 1), channels
+    along `axis`.  Only the host-I/O mode and the tests use it; the engine decodes on the device."""
+    pcm = wav_io.read_wav_pcm(audio_path, start_point, duration, sample_rate)          # [n, ch] int16 / int32
+    x = pcm / float(2 ** (8 * pcm.dtype.itemsize - 1))
+    if pcm.shape[1] == 1:
+        return x[:, 0]
+    return x if axis == 1 else np.ascontiguousarray(x.T)
 
 
 def write_wav_pcm16(path, data, sample_rate):
-    """data: float [n, 2]; PCM_16 like `sf.write(..., 'PCM_16')` (scale 2^15, round, clip)."""
+    """float [n, 2] -> PCM_16 file like `sf.write(..., 'PCM_16')`: scale 2^15, round half to even, clip."""
     pcm = np.clip(np.rint(np.asarray(data, dtype=np.float64) * 32768.0), -32768, 32767).astype('<i2')
+    _write_riff(path, pcm, sample_rate)
+
+
+def _write_riff(path, pcm_i16, sample_rate):
     with wave.open(path, 'wb') as w:
-        w.setnchannels(pcm.shape[1])
+        w.setnchannels(pcm_i16.shape[1])
         w.setsampwidth(2)
         w.setframerate(sample_rate)
-        w.writeframes(pcm.tobytes())
+        w.writeframes(pcm_i16.astype('<i2', copy=False).tobytes())
 
 
 class Song_Dataset_Inference:
-    """Stems of every song directory (mixing_style_transfer/data_loader/data_loader.py:545-603), without the CPU FX
-    normaliser.  Items: (input_stems [4,2,T], reference_stems [4,2,T'][, reference_B], dir_name)."""
+    """The songs under `target_dir` and where their stems live (data_loader/data_loader.py:545-603).  `raw(idx)` reads the
+    files (host work, done by the loader thread), `to_device(raw)` decodes them: {role: float32 [n_stems, 2, T]}."""
 
-    def __init__(self, args):
+    def __init__(self, args, normalizer=None):
         self.args = args
-        self.data_dir = args.target_dir
-        self.interpolate = args.interpolation
         self.instruments = args.instruments
-        self.data_dir_paths = sorted(glob(f"{self.data_dir}*/"))
-        self.input_name = args.input_file_name
-        self.reference_name = args.reference_file_name
-        self.stem_level_directory_name = args.stem_level_directory_name
-        if args.normalize_input:
-            raise NotImplementedError(
-                "--normalize_input True: the CPU FX-normalisation pre-step (mixing_manipulator/data_normalization.py) is "
-                "outside this engine's hot path (SURVEY.md 8f-2); run with --normalize_input False")
+        self.data_dir_paths = sorted(glob(f"{args.target_dir}*/"))
+        # with --do_not_separate the reference drops the separation-model component (data_loader.py:555-556)
+        self.stem_level_directory_name = args.stem_level_directory_name if args.do_not_separate \
+            else os.path.join(args.stem_level_directory_name, args.separation_model)
+        self.roles = [("input", args.input_file_name), ("reference", args.reference_file_name)]
+        if args.interpolation:
+            self.roles.append(("reference_B", args.reference_file_name_2interpolate))
+        self.normalizer = normalizer
+        self.device_io = bool(getattr(args, "device_io", True))
 
     def __len__(self):
         return len(self.data_dir_paths)
 
-    def load_stems(self, dir_path, name):
-        stems = []
-        for inst in self.instruments:
-            p = os.path.join(dir_path, self.stem_level_directory_name, self.args.separation_model, name, inst + '.wav')
-            if getattr(self.args, "device_io", True):
-                # raw PCM -> GPU, int -> float / de-interleave / clamp there (csrc/pcm.cu); same values as the host path
-                stems.append(wav_io.load_wav_to_device(p, sample_rate=self.args.sample_rate))
-            else:
-                x = load_wav_segment(p, axis=0, sample_rate=self.args.sample_rate)       # [2, T]
-                stems.append(torch.from_numpy(np.clip(x, -1.0, 1.0)).float())             # data_loader.py:589-590
-        return torch.stack(stems, dim=0)
+    def stem_path(self, idx, name, inst):
+        return os.path.join(self.data_dir_paths[idx], self.stem_level_directory_name, name, inst + '.wav')
 
-    def __getitem__(self, idx):
-        d = self.data_dir_paths[idx]
-        items = [self.load_stems(d, self.input_name), self.load_stems(d, self.reference_name)]
-        if self.interpolate:
-            items.append(self.load_stems(d, self.args.reference_file_name_2interpolate))
-        return (*items, d)
+    def raw(self, idx):
+        out = {"dir_name": os.path.dirname(self.data_dir_paths[idx])}
+        for role, name in self.roles:
+            stems = []
+            for inst in self.instruments:
+                pcm = wav_io.read_wav_pcm(self.stem_path(idx, name, inst), sample_rate=self.args.sample_rate)
+                stems.append(wav_io.pin_pcm(pcm) if self.device_io else pcm)
+            if len({s.shape[0] for s in stems}) != 1:
+                # the reference's torch.stack(input_stems) (data_loader.py:598-600) raises here as well
+                raise RuntimeError(f"stems of {out['dir_name']}/{name} differ in length: {[s.shape[0] for s in stems]}")
+            out[role] = stems
+        return out
+
+    def to_device(self, raw, device):
+        songs = {"dir_name": raw["dir_name"]}
+        for role, _ in self.roles:
+            T = raw[role][0].shape[0]
+            stems = torch.empty(len(self.instruments), 2, T, dtype=torch.float32, device=device)
+            for i, pcm in enumerate(raw[role]):
+                if self.device_io:
+                    wav_io.decode_pcm(pcm, device, out=stems[i])
+                else:   # host numpy path, same values: x / 2^15, de-interleave, clamp (data_loader.py:589-590)
+                    x = pcm / float(2 ** (8 * pcm.dtype.itemsize - 1))
+                    x = np.repeat(x, 2, axis=1) if x.shape[1] == 1 else x
+                    stems[i].copy_(torch.from_numpy(np.clip(x.T, -1.0, 1.0)).float())
+            if role == "input" and self.normalizer is not None:
+                # FX normalisation of the INPUT stems only (data_loader.py:586-587), then the same clamp
+                stems = torch.stack([self.normalizer.normalize_audio(stems[i], src=inst)
+                                     for i, inst in enumerate(self.instruments)], dim=0).clamp_(-1.0, 1.0)
+            songs[role] = stems
+        return songs
+
+
+class _Prefetcher:
+    """Reads song idx + 1 from disk into pinned memory while song idx is on the GPU."""
+
+    def __init__(self, dataset, device):
+        self.dataset, self.device, self.q = dataset, device, queue.Queue(maxsize=1)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        torch.cuda.set_device(self.device)      # pinned allocations of this thread belong to this rank's context
+        for idx in range(len(self.dataset)):
+            try:
+                self.q.put(("ok", self.dataset.raw(idx)))
+            except BaseException as exc:  # surfaced in the consumer, in order
+                self.q.put(("error", exc))
+                return
+        self.q.put(("done", None))
 
     def __iter__(self):
-        for i in range(len(self)):
-            item = self[i]
-            # batch_size=1 DataLoader collation of the reference: leading batch dim, dir name in a list
-            yield tuple(t.unsqueeze(0) for t in item[:-1]) + ([item[-1]],)
+        while True:
+            kind, item = self.q.get()
+            if kind == "done":
+                return
+            if kind == "error":
+                raise item
+            yield item
+
+
+class _Writer:
+    """Writes finished PCM to disk off the critical path: (path, pinned int16 tensor, CUDA event of its D2H copy)."""
+
+    def __init__(self, sample_rate):
+        self.sample_rate, self.q, self.error = sample_rate, queue.Queue(), None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        while True:
+            job = self.q.get()
+            if job is None:
+                return
+            path, host, event = job
+            try:
+                event.synchronize()
+                _write_riff(path, host.numpy(), self.sample_rate)
+            except BaseException as exc:
+                self.error = exc
+
+    def submit(self, path, pcm_dev):
+        host = torch.empty(pcm_dev.shape, dtype=torch.int16, pin_memory=pcm_dev.numel() > 0)
+        host.copy_(pcm_dev, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record()
+        self.q.put((path, host, event))
+
+    def close(self):
+        self.q.put(None)
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+
+
+def cut_rows(stems, seg_len, n_seg):
+    """[n_stems, 2, T] -> rows [n_stems * n_seg, 2, seg_len] (stem-major), zero-padded to n_seg * seg_len; one copy."""
+    n_stems, _, T = stems.shape
+    if n_seg * seg_len != T:
+        stems = torch.cat((stems, stems.new_zeros(n_stems, 2, n_seg * seg_len - T)), dim=-1)
+    return stems.view(n_stems, 2, n_seg, seg_len).permute(0, 2, 1, 3).reshape(n_stems * n_seg, 2, seg_len)
+
+
+def join_rows(rows, n_stems, T):
+    """inverse of cut_rows: rows [n_stems * n_seg, 2, seg] -> [n_stems, 2, T] (concatenate on time, crop; :165-169)."""
+    n_seg, seg = rows.shape[0] // n_stems, rows.shape[-1]
+    return rows.view(n_stems, n_seg, 2, seg).permute(0, 2, 1, 3).reshape(n_stems, 2, n_seg * seg)[..., :T]
 
 
 class Mixing_Style_Transfer_Inference:
@@ -124,263 +214,215 @@ class Mixing_Style_Transfer_Inference:
         if not torch.cuda.is_available() or args.inference_device == 'cpu':
             raise RuntimeError("Mixing_Style_Transfer_Inference (B200 engine) needs a CUDA device: there is no CPU path "
                                "(the reference's own CPU forward is only used as the parity oracle)")
+        if not args.do_not_separate:
+            raise NotImplementedError("source separation runs the external `demucs` CLI (style_transfer.py:77-90), which is "
+                                      "outside this engine: separate the stems first and pass --do_not_separate True")
         self.rank, self.world_size = shard.world()
         self.device = torch.device("cuda", torch.cuda.current_device())
-
-        # inference computational hyperparameters
         self.args = args
         self.device_io = bool(getattr(args, "device_io", True))
         self.segment_length = args.segment_length
         self.batch_size = args.batch_size
         self.sample_rate = 44100    # sampling rate should be 44100
         self.time_in_seconds = int(args.segment_length // self.sample_rate)
-
-        # directory configuration
         self.output_dir = args.target_dir if args.output_dir is None else args.output_dir
         self.target_dir = args.target_dir
 
-        # load model and its checkpoint weights
-        self.models = {}
-        self.models['effects_encoder'] = FXencoder(args.cfg_encoder).to(self.device)
-        self.models['mixing_converter'] = TCNModel(nparams=args.cfg_converter["condition_dimension"],
-                                                   ninputs=2,
-                                                   noutputs=2,
-                                                   nblocks=args.cfg_converter["nblocks"],
-                                                   dilation_growth=args.cfg_converter["dilation_growth"],
-                                                   kernel_size=args.cfg_converter["kernel_size"],
-                                                   channel_width=args.cfg_converter["channel_width"],
-                                                   stack_size=args.cfg_converter["stack_size"],
-                                                   cond_dim=args.cfg_converter["condition_dimension"],
-                                                   causal=args.cfg_converter["causal"]).to(self.device)
+        conv = args.cfg_converter
+        self.models = {
+            'effects_encoder': FXencoder(args.cfg_encoder).to(self.device),
+            'mixing_converter': TCNModel(nparams=conv["condition_dimension"], ninputs=2, noutputs=2,
+                                         nblocks=conv["nblocks"], dilation_growth=conv["dilation_growth"],
+                                         kernel_size=conv["kernel_size"], channel_width=conv["channel_width"],
+                                         stack_size=conv["stack_size"], cond_dim=conv["condition_dimension"],
+                                         causal=conv["causal"]).to(self.device)}
+        self.reload_weights({'effects_encoder': args.ckpt_path_enc, 'mixing_converter': args.ckpt_path_conv},
+                            ddp=trained_w_ddp)
 
-        ckpt_paths = {'effects_encoder': args.ckpt_path_enc,
-                      'mixing_converter': args.ckpt_path_conv}
-        # reload saved model weights
-        self.reload_weights(ckpt_paths, ddp=trained_w_ddp)
-
-        # load data loader for the inference procedure
-        self.data_loader = Song_Dataset_Inference(args)
-
-        # save current arguments
+        normalizer = None
+        if args.normalize_input:
+            from music_mixing_style_transfer_b200.mixing_manipulator.data_normalization import Audio_Effects_Normalizer
+            normalizer = Audio_Effects_Normalizer(precomputed_feature_path=args.precomputed_normalization_feature,
+                                                  STEMS=args.instruments, EFFECTS=args.normalization_order)
+        self.data_loader = Song_Dataset_Inference(args, normalizer)
+        self.stats = {"audio_seconds": 0.0, "wall_seconds": 0.0, "songs": 0}
         if self.rank == 0:
             self.save_args(args)
-        if not self.args.do_not_separate:
-            raise NotImplementedError("source separation runs the external `demucs` CLI (style_transfer.py:77-90), which is "
-                                      "outside this engine: separate the stems first and pass --do_not_separate True")
 
-    # reload model weights from the target checkpoint path
     def reload_weights(self, ckpt_paths, ddp=True):
-        for cur_model_name in self.models.keys():
-            checkpoint = torch.load(ckpt_paths[cur_model_name], map_location=self.device)
-            from collections import OrderedDict
-            new_state_dict = OrderedDict()
-            for k, v in checkpoint["model"].items():
-                # remove `module.` if the model was trained with DDP
-                name = k[7:] if ddp else k
-                new_state_dict[name] = v
-            # load params
-            self.models[cur_model_name].load_state_dict(new_state_dict)
-            print(f"---reloaded checkpoint weights : {cur_model_name} ---")
+        """`{"model": state_dict}` checkpoints, `module.` prefix of DDP training stripped (:94-108)."""
+        for name, model in self.models.items():
+            model.load_state_dict(checkpoint_state_dict(ckpt_paths[name], self.device, ddp=ddp))
+            print(f"---reloaded checkpoint weights : {name} ---")
 
-    # ---- device-side pieces ----
-    def encode_reference(self, ref_batches):
-        """Mean embedding over every reference segment (style_transfer.py:144-153)."""
-        feats = []
-        with torch.no_grad():
-            for cur_ref_data in ref_batches:
-                cur_ref_data = cur_ref_data.to(self.device, non_blocking=True)
-                feats.append(self.models["effects_encoder"].eval()(cur_ref_data))
-        return torch.cat(feats, dim=0).mean(dim=0)
+    # ---- planning: how a stem of T samples is cut (pure host logic, tests/test_host_logic.py) ----
+    def plan_cut(self, T, segment_length, cut_above, song_name="<song>"):
+        """(segment length, segment count).  Stems longer than `cut_above` samples are cut into `segment_length` pieces with
+        the zero-padded tail of batchwise_segmentization (:281-301, which asserts T >= args.segment_length); shorter ones
+        go through as one segment of their own length (:131-132, :139-140)."""
+        if T <= cut_above:
+            return T, 1
+        assert T >= self.args.segment_length, (
+            "Error : Insufficient duration!\n\t Target song's length is shorter than segment length.\n\t "
+            f"Song name : {song_name}\n\t Consider changing the 'segment_length' or song with sufficient duration")
+        return segment_length, T // segment_length + 1          # pad = seg - T % seg in (0, seg]  ->  floor(T / seg) + 1
 
-    def convert(self, in_batches, cond_of_batch):
-        """TCN over the input batches; under torchrun each rank takes a contiguous slice of every batch and the
-        results are all-gathered (shard.py).  cond_of_batch(idx) -> [2048] embedding for batch idx."""
-        outs = []
-        with torch.no_grad():
-            for idx, cur_data in enumerate(in_batches):
-                cond = cond_of_batch(idx).unsqueeze(0)
-                n = cur_data.shape[0]
-                lo, hi = shard.shard_bounds(n, self.world_size, self.rank)
-                local = cur_data[lo:hi].to(self.device, non_blocking=True)
-                if hi > lo:
-                    y = self.models["mixing_converter"].eval()(local, cond)
-                else:
-                    y = torch.empty(0, 2, cur_data.shape[-1], device=self.device)
-                if self.world_size > 1:
-                    y = shard.allgather_segments(y, shard.shard_counts(n, self.world_size))
-                outs.append(y.detach() if self.device_io else y.cpu().detach())
-        return outs
+    # ---- device stages ----
+    def _local(self, n_rows):
+        return shard.shard_bounds(n_rows, self.world_size, self.rank)
 
-    def combine(self, infered_data_list, length):
-        # combine back to whole song (:165-169); a device tensor under --device_io, a numpy array otherwise
-        seq = [torch.cat(torch.unbind(b, dim=0), dim=-1) for b in infered_data_list]
-        whole = torch.cat(seq, dim=-1)[:, :length]
-        return whole if self.device_io else whole.numpy()
+    def embed_stems(self, ref_sets):
+        """ref_sets: list of (stems [n_stems, 2, T], seg_len, n_seg) -> [len(ref_sets), n_stems, 2048]: per stem the mean
+        FXencoder embedding over all its segments (:144-153), rows sharded over the ranks, one all-reduce of the sums."""
+        encoder = self.models["effects_encoder"].eval()
+        n_stems = ref_sets[0][0].shape[0]
+        sums = torch.zeros(len(ref_sets), n_stems, encoder.config["channels"][-1], device=self.device)
+        for k, (stems, seg_len, n_seg) in enumerate(ref_sets):
+            lo, hi = self._local(n_stems * n_seg)
+            if hi == lo:
+                continue
+            rows = cut_rows(stems, seg_len, n_seg)[lo:hi]
+            step = max(1, MAX_ROWS_PER_LAUNCH // seg_len)
+            for s in range(0, hi - lo, step):
+                emb = encoder(rows[s:s + step].contiguous())
+                first = lo + s                      # global row of emb[0]; rows are stem-major
+                for st in range(first // n_seg, (first + emb.shape[0] - 1) // n_seg + 1):
+                    a, b = max(st * n_seg, first) - first, min((st + 1) * n_seg, first + emb.shape[0]) - first
+                    sums[k, st] += emb[a:b].sum(dim=0)      # per-stem partial sums in a fixed order: bit-reproducible
+        if self.world_size > 1:
+            torch.distributed.all_reduce(sums)
+        counts = torch.tensor([n for _, _, n in ref_sets], dtype=torch.float32, device=self.device)
+        return sums / counts.view(-1, 1, 1)
 
-    def write_outputs(self, cur_out_dir, inst_outputs, output_name_tag):
-        """Per-instrument files (--save_each_inst) and the remix `sum(inst_outputs)` as PCM_16 (:170-177)."""
+    def convert_rows(self, rows, cond):
+        """rows [R, 2, seg] (all stems of the song), cond [R, 2048] -> converted rows [R, 2, seg] on every rank."""
+        converter = self.models["mixing_converter"].eval()
+        R, _, seg = rows.shape
+        lo, hi = self._local(R)
+        local = torch.empty(hi - lo, 2, seg, dtype=torch.float32, device=self.device)
+        step = max(1, MAX_ROWS_PER_LAUNCH // seg)
+        auto = converter.precision == "auto"
+        launches = []
+        if auto:
+            converter.precision = "f16f8"
+        try:
+            for s in range(lo, hi, step):
+                e = min(hi, s + step)
+                flag = torch.zeros(1, dtype=torch.int32, device=self.device) if auto else None
+                x, c = rows[s:e].contiguous(), cond[s:e].contiguous()
+                converter(x, c, out=local[s - lo:e - lo], range_flag=flag)
+                launches.append((x, c, s, e, flag))
+            if auto and launches:
+                # one read-back for all launches: did any activation leave the f16f8 operand range?  (TCNModel.forward)
+                excess = torch.cat([l[4] for l in launches]).view(torch.float32).cpu()
+                for (x, c, s, e, _), v in zip(launches, excess.tolist()):
+                    if v > 0.0:
+                        converter.rerun_bf16x3(x, c, local[s - lo:e - lo])
+        finally:
+            if auto:
+                converter.precision = "auto"
+        if self.world_size > 1:
+            return shard.allgather_segments(local, shard.shard_counts(R, self.world_size))
+        return local
+
+    def _emit(self, writer, cur_out_dir, stems_out, tag):
+        """Per-instrument files (--save_each_inst) and the remix `sum(inst_outputs)` as PCM_16 (:170-177); rank 0 only."""
         if self.rank != 0:
             return
-        if self.device_io:
-            if self.args.save_each_inst:
-                for name, y in zip(self.args.instruments, inst_outputs):
-                    wav_io.write_wav_pcm16_from_device(os.path.join(cur_out_dir, f"{name}_{output_name_tag}.wav"), y,
-                                                       self.args.sample_rate)
-            wav_io.write_wav_pcm16_from_device(os.path.join(cur_out_dir, f"mixture_{output_name_tag}.wav"),
-                                               torch.stack(inst_outputs, dim=0), self.args.sample_rate)
-        else:
-            if self.args.save_each_inst:
-                for name, y in zip(self.args.instruments, inst_outputs):
-                    write_wav_pcm16(os.path.join(cur_out_dir, f"{name}_{output_name_tag}.wav"), y.transpose(-1, -2),
-                                    self.args.sample_rate)
-            write_wav_pcm16(os.path.join(cur_out_dir, f"mixture_{output_name_tag}.wav"),
-                            sum(inst_outputs).transpose(-1, -2), self.args.sample_rate)
+        jobs = [(f"mixture_{tag}.wav", stems_out)]
+        if self.args.save_each_inst:
+            jobs = [(f"{name}_{tag}.wav", stems_out[i]) for i, name in enumerate(self.args.instruments)] + jobs
+        for fname, y in jobs:
+            path = os.path.join(cur_out_dir, fname)
+            if self.device_io:
+                writer.submit(path, wav_io.encode_mix_pcm16(y))
+            else:
+                y = y.cpu().numpy()
+                write_wav_pcm16(path, (y if y.ndim == 2 else y.sum(axis=0, dtype=np.float32)).T, self.args.sample_rate)
+
+    def _run(self, tag, plan_song):
+        """Shared song loop.  plan_song(songs) -> (input cut, [reference cut, ...], cond_fn(embs, stem_of_row, seg_of_row))."""
+        writer = _Writer(self.args.sample_rate)
+        t0 = time.perf_counter()
+        try:
+            with torch.no_grad():
+                for raw in _Prefetcher(self.data_loader, self.device):
+                    songs = self.data_loader.to_device(raw, self.device)
+                    dir_name = songs["dir_name"]
+                    print(f"---inference file name : {dir_name}---")
+                    cur_out_dir = dir_name.replace(self.target_dir, self.output_dir)
+                    if self.rank == 0:
+                        os.makedirs(cur_out_dir, exist_ok=True)
+                    (seg, n_seg), ref_sets, cond_fn = plan_song(songs)
+                    inp = songs["input"]
+                    n_stems, _, T = inp.shape
+                    embs = self.embed_stems(ref_sets)
+                    row = torch.arange(n_stems * n_seg, device=self.device)
+                    cond = cond_fn(embs, row // n_seg, row % n_seg)
+                    out_rows = self.convert_rows(cut_rows(inp, seg, n_seg), cond)
+                    self._emit(writer, cur_out_dir, join_rows(out_rows, n_stems, T).contiguous(), tag)
+                    self.stats["audio_seconds"] += T / self.sample_rate
+                    self.stats["songs"] += 1
+        finally:
+            writer.close()
+        torch.cuda.synchronize()
+        self.stats["wall_seconds"] += time.perf_counter() - t0
+        return self.stats
 
     # Inference whole song
-    def inference(self, ):
+    def inference(self):
         print("\n======= Start to inference music mixing style transfer =======")
-        # normalized input
-        output_name_tag = 'output' if self.args.normalize_input else 'output_notnormed'
+        a = self.args
+        tag = 'output' if a.normalize_input else 'output_notnormed'
 
-        for step, (input_stems, reference_stems, dir_name) in enumerate(self.data_loader):
-            print(f"---inference file name : {dir_name[0]}---")
-            cur_out_dir = dir_name[0].replace(self.target_dir, self.output_dir)
-            os.makedirs(cur_out_dir, exist_ok=True)
-            ''' stem-level inference '''
-            inst_outputs = []
-            for cur_inst_idx, cur_inst_name in enumerate(self.args.instruments):
-                print(f'\t{cur_inst_name}...')
-                ''' segmentize whole songs into batch '''
-                if len(input_stems[0][cur_inst_idx][0]) > self.args.segment_length:
-                    cur_inst_input_stem = self.batchwise_segmentization(input_stems[0][cur_inst_idx],
-                                                                        dir_name[0],
-                                                                        segment_length=self.args.segment_length,
-                                                                        discard_last=False)
-                else:
-                    cur_inst_input_stem = [input_stems[:, cur_inst_idx]]
-                if len(reference_stems[0][cur_inst_idx][0]) > self.args.segment_length * 2:
-                    cur_inst_reference_stem = self.batchwise_segmentization(reference_stems[0][cur_inst_idx],
-                                                                            dir_name[0],
-                                                                            segment_length=self.args.segment_length_ref,
-                                                                            discard_last=False)
-                else:
-                    cur_inst_reference_stem = [reference_stems[:, cur_inst_idx]]
+        def plan_song(songs):
+            name = songs["dir_name"]
+            cut_in = self.plan_cut(songs["input"].shape[-1], a.segment_length, a.segment_length, name)
+            # the reference cuts the style reference at `segment_length_ref` but only when it is longer than TWICE
+            # `segment_length` (:133-136, quirk q5)
+            Tr = songs["reference"].shape[-1]
+            ref_sets = [(songs["reference"], *self.plan_cut(Tr, a.segment_length_ref, 2 * a.segment_length, name))]
+            return cut_in, ref_sets, lambda embs, stem, seg_idx: embs[0][stem]
 
-                ''' inference '''
-                # first extract reference style embedding (every rank computes it: 1 % of the work, no broadcast needed
-                # for file-level inference; the benchmark path uses shard.sharded_style_transfer with the broadcast)
-                infered_ref_data_avg = self.encode_reference(cur_inst_reference_stem)
-                # mixing style converter
-                infered_data_list = self.convert(cur_inst_input_stem, lambda idx: infered_ref_data_avg)
-                # final output of current instrument
-                fin_data_out_inst = self.combine(infered_data_list, input_stems[0][cur_inst_idx].shape[-1])
+        return self._run(tag, plan_song)
 
-                inst_outputs.append(fin_data_out_inst)
-            # per-instrument outputs (--save_each_inst) and the remix
-            self.write_outputs(cur_out_dir, inst_outputs, output_name_tag)
-
-    # Inference whole song
-    def inference_interpolation(self, ):
+    # Inference whole song, interpolating between two reference styles
+    def inference_interpolation(self):
         print("\n======= Start to inference interpolation examples =======")
-        # normalized input
-        output_name_tag = 'output_interpolation' if self.args.normalize_input else 'output_notnormed_interpolation'
+        a = self.args
+        tag = 'output_interpolation' if a.normalize_input else 'output_notnormed_interpolation'
+        S = a.interpolate_segments
 
-        for step, (input_stems, reference_stems_A, reference_stems_B, dir_name) in enumerate(self.data_loader):
-            print(f"---inference file name : {dir_name[0]}---")
-            cur_out_dir = dir_name[0].replace(self.target_dir, self.output_dir)
-            os.makedirs(cur_out_dir, exist_ok=True)
-            ''' stem-level inference '''
-            inst_outputs = []
-            for cur_inst_idx, cur_inst_name in enumerate(self.args.instruments):
-                print(f'\t{cur_inst_name}...')
-                ''' segmentize whole song '''
-                # segmentize input according to number of interpolating segments
-                interpolate_segment_length = input_stems[0][cur_inst_idx].shape[1] // self.args.interpolate_segments + 1
-                cur_inst_input_stem = self.batchwise_segmentization(input_stems[0][cur_inst_idx],
-                                                                    dir_name[0],
-                                                                    segment_length=interpolate_segment_length,
-                                                                    discard_last=False)
-                # batchwise segmentize 2 reference tracks
-                if len(reference_stems_A[0][cur_inst_idx][0]) > self.args.segment_length_ref:
-                    cur_inst_reference_stem_A = self.batchwise_segmentization(reference_stems_A[0][cur_inst_idx],
-                                                                              dir_name[0],
-                                                                              segment_length=self.args.segment_length_ref,
-                                                                              discard_last=False)
-                else:
-                    cur_inst_reference_stem_A = [reference_stems_A[:, cur_inst_idx]]
-                if len(reference_stems_B[0][cur_inst_idx][0]) > self.args.segment_length_ref:
-                    # the reference cuts B with `segment_length`, A with `segment_length_ref` (:205 vs :212)
-                    cur_inst_reference_stem_B = self.batchwise_segmentization(reference_stems_B[0][cur_inst_idx],
-                                                                              dir_name[0],
-                                                                              segment_length=self.args.segment_length,
-                                                                              discard_last=False)
-                else:
-                    cur_inst_reference_stem_B = [reference_stems_B[:, cur_inst_idx]]
+        def plan_song(songs):
+            name = songs["dir_name"]
+            T = songs["input"].shape[-1]
+            # the input is always cut, into pieces of T // S + 1 samples (:196-200)
+            cut_in = self.plan_cut(T, T // S + 1, -1, name)
+            # A is cut at `segment_length_ref`, B at `segment_length`; both only when longer than `segment_length_ref`
+            # (:203-216, quirk q5)
+            ref_sets = [(songs["reference"], *self.plan_cut(songs["reference"].shape[-1], a.segment_length_ref,
+                                                            a.segment_length_ref, name)),
+                        (songs["reference_B"], *self.plan_cut(songs["reference_B"].shape[-1], a.segment_length,
+                                                              a.segment_length_ref, name))]
 
-                ''' inference '''
-                infered_ref_data_avg_A = self.encode_reference(cur_inst_reference_stem_A)
-                infered_ref_data_avg_B = self.encode_reference(cur_inst_reference_stem_B)
+            def cond_fn(embs, stem, seg_idx):
+                # the weight follows the reference's BATCH index (:247-251, quirk q4): segments of one batch share it
+                batch_idx = (seg_idx // self.batch_size).to(torch.float32)
+                w = ((S - 1 - batch_idx) / (S - 1)).unsqueeze(1)
+                return w * embs[0][stem] + (1 - w) * embs[1][stem]
 
-                # perform linear interpolation on embedding space; the weight is indexed by BATCH (:247-251)
-                def cond_of_batch(cur_idx):
-                    cur_weight = (self.args.interpolate_segments - 1 - cur_idx) / (self.args.interpolate_segments - 1)
-                    return cur_weight * infered_ref_data_avg_A + (1 - cur_weight) * infered_ref_data_avg_B
+            return cut_in, ref_sets, cond_fn
 
-                infered_data_list = self.convert(cur_inst_input_stem, cond_of_batch)
-                fin_data_out_inst = self.combine(infered_data_list, input_stems[0][cur_inst_idx].shape[-1])
-                inst_outputs.append(fin_data_out_inst)
-            # per-instrument outputs (--save_each_inst) and the remix
-            self.write_outputs(cur_out_dir, inst_outputs, output_name_tag)
+        return self._run(tag, plan_song)
 
-    # function that segmentize an entire song into batch
+    # function that segmentize an entire song into batch (kept for callers of the reference's method, :274-301)
     def batchwise_segmentization(self, target_song, song_name, segment_length, discard_last=False):
-        assert target_song.shape[-1] >= self.args.segment_length, \
-            f"Error : Insufficient duration!\n\t \
-                Target song's length is shorter than segment length.\n\t \
-                Song name : {song_name}\n\t \
-                Consider changing the 'segment_length' or song with sufficient duration"
-
-        # discard restovers (last segment)
-        if discard_last:
-            target_length = target_song.shape[-1] - target_song.shape[-1] % segment_length
-            target_song = target_song[:, :target_length]
-        # pad last segment
-        else:
-            pad_length = segment_length - target_song.shape[-1] % segment_length
-            target_song = torch.cat((target_song, torch.zeros(2, pad_length, device=target_song.device)), axis=-1)
-
-        # segmentize according to the given segment_length
-        whole_batch_data = []
-        batch_wise_data = []
-        for cur_segment_idx in range(target_song.shape[-1] // segment_length):
-            batch_wise_data.append(target_song[..., cur_segment_idx * segment_length:(cur_segment_idx + 1) * segment_length])
-            if len(batch_wise_data) == self.args.batch_size:
-                whole_batch_data.append(torch.stack(batch_wise_data, dim=0))
-                batch_wise_data = []
-        if batch_wise_data:
-            whole_batch_data.append(torch.stack(batch_wise_data, dim=0))
-
-        return whole_batch_data
+        return segment_into_batches(target_song, segment_length, self.args.batch_size, min_length=self.args.segment_length,
+                                    name=song_name, discard_last=discard_last)
 
     # save current inference arguments
     def save_args(self, params):
-        info = '\n[args]\n'
-        parser = getattr(params, "_parser", None)
-        groups = parser._action_groups if parser is not None else []
-        for sub_args in groups:
-            if sub_args.title in ['positional arguments', 'optional arguments', 'options']:
-                continue
-            size_sub = len(sub_args._group_actions)
-            info += f'  {sub_args.title} ({size_sub})\n'
-            for i, arg in enumerate(sub_args._group_actions):
-                prefix = '-'
-                info += f'      {prefix} {arg.dest:20s}: {getattr(params, arg.dest)}\n'
-        info += '\n'
-
-        os.makedirs(self.output_dir, exist_ok=True)
-        record_path = f"{self.output_dir}style_transfer_inference_configurations.txt"
-        with open(record_path, 'w') as f:
-            np.savetxt(f, [info], delimiter=" ", fmt="%s")
+        dump_arguments(params, f"{self.output_dir}style_transfer_inference_configurations.txt")
 
 
 def build_parser():
@@ -451,7 +493,8 @@ def main(argv=None):
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-        dist.init_process_group("nccl")
+        if not dist.is_initialized():
+            dist.init_process_group("nccl")
 
     # load network configurations
     with open(os.path.join(currentdir, 'configs.yaml'), 'r') as f:
@@ -460,11 +503,8 @@ def main(argv=None):
     args.cfg_converter = configs['TCN']['default']
 
     # Perform music mixing style transfer
-    inference_style_transfer = Mixing_Style_Transfer_Inference(args)
-    if args.interpolation:
-        inference_style_transfer.inference_interpolation()
-    else:
-        inference_style_transfer.inference()
+    engine = Mixing_Style_Transfer_Inference(args)
+    return engine.inference_interpolation() if args.interpolation else engine.inference()
 
 
 if __name__ == '__main__':

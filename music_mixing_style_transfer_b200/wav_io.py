@@ -41,6 +41,18 @@ def read_wav_pcm(audio_path, start_point=None, duration=None, sample_rate=44100)
     return x.reshape(-1, n_ch)
 
 
+def pin_pcm(pcm):
+    """numpy int16 / int32 [n_frames, n_channels] (the read-only file buffer) -> the same samples in a pinned torch tensor,
+    ready for an asynchronous H2D copy.  Safe to call from a loader thread."""
+    if pcm.dtype not in (np.dtype('<i2'), np.dtype('<i4')):
+        raise ValueError("ValueError: input audio's bit depth should be 16 or 32-bit")
+    tdt = torch.int16 if pcm.dtype == np.dtype('<i2') else torch.int32
+    host = torch.empty(pcm.shape, dtype=tdt, pin_memory=bool(pcm.size) and torch.cuda.is_available())
+    if pcm.size:
+        np.copyto(host.numpy(), pcm)
+    return host
+
+
 def decode_pcm(pcm, device=None, out=None):
     """pcm: numpy or torch int16 / int32 [n_frames, n_channels] (host or device) -> float32 [2, n_frames] on the GPU:
     x / 2^15 (or 2^31), clamped to [-1, 1], de-interleaved; mono is duplicated into both channels."""
@@ -51,18 +63,12 @@ def decode_pcm(pcm, device=None, out=None):
         if pcm.dtype not in (np.dtype('<i2'), np.dtype('<i4')):
             raise ValueError("ValueError: input audio's bit depth should be 16 or 32-bit")
         # one host copy: the (read-only) file buffer straight into a pinned staging tensor, then an async H2D copy
-        tdt = torch.int16 if pcm.dtype == np.dtype('<i2') else torch.int32
-        if pcm.size:
-            host = torch.empty(pcm.shape, dtype=tdt).pin_memory()
-            np.copyto(host.numpy(), pcm)
-            pcm = host.to(device, non_blocking=True)
-        else:
-            pcm = torch.empty(pcm.shape, dtype=tdt, device=device)
+        pcm = pin_pcm(pcm)
     if pcm.dtype not in (torch.int16, torch.int32):
         raise ValueError("ValueError: input audio's bit depth should be 16 or 32-bit")
     if pcm.dim() == 1:
         pcm = pcm.unsqueeze(1)
-    pcm = pcm.to(device).contiguous()
+    pcm = pcm.to(device, non_blocking=True).contiguous()
     n_frames, n_ch = int(pcm.shape[0]), int(pcm.shape[1])
     if out is None:
         out = torch.empty(2, n_frames, dtype=torch.float32, device=device)

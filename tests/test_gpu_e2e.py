@@ -58,7 +58,7 @@ def test_public_entry_on_wav_files(tmp_path, interp):
             x = W.synthetic_audio(1, L, seed=500 + 10 * len(name) + i)[0].numpy()
             x = np.clip(np.rint(x * 32768.0), -32768, 32767) / 32768.0        # what survives PCM_16
             audio[(name, inst)] = torch.from_numpy(x).float()
-            _write_wav(str(song / "separated" / "mdx_extra" / name / f"{inst}.wav"), x)
+            _write_wav(str(song / "separated" / name / f"{inst}.wav"), x)
     argv = ["--target_dir", str(tmp_path / "data") + "/", "--output_dir", str(tmp_path / "out") + "/",
             "--ckpt_path_enc", str(tmp_path / "enc.pt"), "--ckpt_path_conv", str(tmp_path / "tcn.pt"),
             "--segment_length", str(seg), "--segment_length_ref", str(seg), "--batch_size", "2",
@@ -114,7 +114,7 @@ def test_device_io_is_bit_identical_to_host_io(tmp_path):
     for name, L in (("input", 2 * seg + 77), ("reference", 3 * seg + 1)):
         for i, inst in enumerate(insts):
             x = W.synthetic_audio(1, L, seed=900 + 10 * len(name) + i)[0].numpy() * 3.0   # loud: the remix clips
-            _write_wav(str(song / "separated" / "mdx_extra" / name / f"{inst}.wav"), x)
+            _write_wav(str(song / "separated" / name / f"{inst}.wav"), x)
     outs = {}
     for mode in ("True", "False"):
         out_dir = tmp_path / f"out_{mode}"

@@ -90,6 +90,40 @@ def test_entry_point_segmentation_matches_oracle():
         obj.batchwise_segmentization(torch.randn(2, 100), "s", segment_length=250)
 
 
+def test_song_row_table_equals_reference_segmentation():
+    """The engine cuts ALL stems of a song into one row table (inference/style_transfer.py: plan_cut / cut_rows / join_rows):
+    the rows must be the reference's segments (oracle restatement of batchwise_segmentization, incl. the extra all-zero
+    segment of an exact multiple), in stem-major order, and join_rows must undo the cut."""
+    from music_mixing_style_transfer_b200.inference.style_transfer import (Mixing_Style_Transfer_Inference, build_parser,
+                                                                           cut_rows, join_rows)
+    from oracle import networks_oracle as O
+    obj = Mixing_Style_Transfer_Inference.__new__(Mixing_Style_Transfer_Inference)
+    obj.args = build_parser().parse_args(["--segment_length", "250", "--segment_length_ref", "300"])
+    for T in (1000, 1001, 777, 251):
+        stems = torch.randn(4, 2, T)
+        seg, n = obj.plan_cut(T, 250, 250)
+        rows = cut_rows(stems, seg, n)
+        ref = torch.cat([torch.cat(O.batchwise_segmentization(stems[i], 250, 3), 0) for i in range(4)], 0)
+        assert (seg, n) == (250, T // 250 + 1) and torch.equal(rows, ref), T
+        assert torch.equal(join_rows(rows, 4, T), stems)
+    # short stems pass through as one odd-length segment (style_transfer.py:131-132); the style reference is only cut above
+    # TWICE the segment length (:133) and then at segment_length_ref (:136)
+    assert obj.plan_cut(250, 250, 250) == (250, 1) and obj.plan_cut(199, 250, 250) == (199, 1)
+    assert obj.plan_cut(500, 300, 500) == (500, 1) and obj.plan_cut(501, 300, 500) == (300, 2)
+    assert torch.equal(cut_rows(torch.ones(3, 2, 199), 199, 1), torch.ones(3, 2, 199))
+    with pytest.raises(AssertionError):     # cut requested but shorter than args.segment_length (:275-279)
+        obj.plan_cut(200, 100, -1)
+
+
+def test_stem_directory_layout_follows_do_not_separate():
+    """data_loader/data_loader.py:555-556: --do_not_separate True drops the separation-model path component."""
+    from music_mixing_style_transfer_b200.inference.style_transfer import Song_Dataset_Inference, build_parser
+    a = build_parser().parse_args(["--target_dir", "/data/", "--do_not_separate", "True"])
+    assert Song_Dataset_Inference(a).stem_level_directory_name == "separated"
+    a = build_parser().parse_args(["--target_dir", "/data/"])
+    assert Song_Dataset_Inference(a).stem_level_directory_name == os.path.join("separated", "mdx_extra")
+
+
 def test_shard_bounds_cover_everything_once():
     for n in (0, 1, 7, 32, 33, 512):
         for ws in (1, 2, 3, 4, 8):
