@@ -8,11 +8,17 @@
 Workload (BASELINE.json configs[1], per GPU): reference batch [32, 2, 262144] -> FXencoder -> mean embedding;
 input batch [32, 2, 262144] -> MixFXcloner TCN conditioned on it -> clamp.  Synthetic seeded stereo 44.1 kHz audio,
 seeded random weights loaded through the reference's state_dict layout (no checkpoints ship with the reference).
-N > 1 (weak scaling): every rank converts its own 32 input segments (32*N in total); rank 0 encodes the reference
-batch, the embedding is broadcast (NCCL) and the output segments are all-gathered (NCCL) -- shard.py.
-One "step" = one full forward over that batch.  `value` = audio seconds of input converted by ALL ranks per second,
-inputs resident in HBM; `e2e` = same through the public module API with pinned-host inputs, H2D of inputs and D2H of
-the output waveforms inside the timed region.
+N > 1 (weak scaling): every rank converts its own 32 input segments (32*N in total).  The reference batch is sharded too
+(every rank encodes 32/N of its segments, ONE 8 KiB all-reduce of the partial sums -- SURVEY.md 8e; `--ref-mode broadcast`
+selects rank-0 encode + broadcast instead) and the output segments are all-gathered in sub-batches that overlap the TCN of
+the next sub-batch (shard.py).  One "step" = one full forward over that batch.  `value` = audio seconds of input converted
+by ALL ranks per second, inputs resident in HBM; `e2e` = same through the public host-to-host call
+(pipeline.StyleTransferPipeline): pinned-host inputs, H2D of every step's inputs and D2H of its output waveforms inside the
+timed region, copies on side streams.
+`extra` carries the other BASELINE configs as short legs: configs[2] (FX chain), configs[3]'s 64 segments per GPU, configs[4]
+(interpolation, per-row conditioning, one odd length), the sample-format kernels, a file-to-file run of the inference entry,
+and -- at N = 1 -- the reference's own modules on this GPU through cuDNN (what inference/style_transfer.py:29-32 runs as
+shipped) as a secondary baseline.
 
 --impl reference: the reference's own CPU implementation of the path (oracle port of its torch modules -- a Python
 reference cannot travel to the GPU box as source) on the host cores, a bounded sample per step.
@@ -39,6 +45,7 @@ UNIT = "audio_s/s"
 FLOP_PER_ROW_UMMA = 2 * 128 * 128 * 15
 TCN_FLOP_PER_SAMPLE = 6397952        # whole TCN, SURVEY.md 8d
 ENC_FLOP_PER_SEG = 28.59e9           # encoder at L = 2^18
+TRAFFIC_PER_LAUNCH = 9.03e9          # dram bytes per tcn_block_umma_kernel launch at configs[1], from the committed ncu capture
 
 
 def peaks():
@@ -129,6 +136,7 @@ def cpu_reference_step(state, n_seg=1, length=SEG_LEN):
         emb = O.fxencoder_forward(state["ref"], esd, W.ENC_KERNELS, W.ENC_STRIDES).mean(dim=0)
         out = O.tcn_forward(state["inp"], emb.unsqueeze(0), tsd)
     state["last"] = float(out.abs().mean())
+    state["out"] = out
     return n_seg * length / SR
 
 
@@ -184,6 +192,90 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def reference_modules_on_gpu(device, B, L, cpu_out=None, cpu_in=None):
+    """Secondary baseline (N = 1, rank 0): the oracle port of the reference's torch modules on THIS GPU through cuDNN -- what
+    inference/style_transfer.py:29-32 runs as shipped when CUDA is available.  Twice: fp32 with TF32 off, and with torch's
+    defaults for convolutions (TF32 on).  Its error against the CPU forward is measured on the cpu_baseline sample."""
+    import torch
+    from oracle import networks_oracle as O, weights as W
+    esd = {k: v.to(device) for k, v in W.make_encoder_state_dict(0).items()}
+    tsd = {k: v.to(device) for k, v in W.make_tcn_state_dict(0).items()}
+    B = min(B, 8)            # bounded: throughput is per audio second, eager fp32 keeps ~5 activation tensors of B x 134 MB alive
+    ref = W.synthetic_audio(B, L, seed=1234).to(device)
+    inp = W.synthetic_audio(B, L, seed=2000).to(device)
+    out = {"batch": B}
+    for name, tf32 in (("fp32", False), ("tf32_default", True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+
+        def step(r, x):
+            with torch.no_grad():
+                emb = O.fxencoder_forward(r, esd, W.ENC_KERNELS, W.ENC_STRIDES).mean(dim=0)
+                return O.tcn_forward(x, emb.unsqueeze(0), tsd)
+        try:
+            step(ref[:2], inp[:2])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            step(ref, inp)                      # warm (cuDNN algorithm selection)
+            e0.record()
+            for _ in range(2):
+                y = step(ref, inp)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 2
+            rec = {"ms_per_step": ms, "audio_s_per_s": B * L / SR / (ms * 1e-3)}
+            if cpu_out is not None:
+                y1 = step(cpu_in[0].to(device), cpu_in[1].to(device)).cpu()
+                rec["rms_err_vs_cpu_forward"] = float((y1 - cpu_out).pow(2).mean().sqrt())
+            del y
+            out[name] = rec
+        except Exception as exc:
+            out[name] = {"error": repr(exc)}
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = True
+    return out
+
+
+def file_to_file_leg(device, tmp_root):
+    """The inference entry on a synthetic song directory in the reference's layout (2 songs x 4 stems x 60 s, PCM_16):
+    WAV files in, mixture WAV out; audio seconds of song per wall second, file reads and writes included."""
+    import shutil
+    import wave
+    import numpy as np
+    import torch
+    from music_mixing_style_transfer_b200 import synthetic as W
+    from music_mixing_style_transfer_b200.inference import style_transfer as st
+    root = os.path.join(tmp_root, "mst_bench_songs")
+    shutil.rmtree(root, ignore_errors=True)
+    n_frames = 60 * SR
+    for song in ("song0", "song1"):
+        for name in ("input", "reference"):
+            d = os.path.join(root, "data", song, "separated", name)
+            os.makedirs(d)
+            for i, inst in enumerate(("drums", "bass", "other", "vocals")):
+                x = W.synthetic_audio(1, n_frames, seed=100 * int(song[-1]) + 10 * len(name) + i)[0].numpy()
+                with wave.open(os.path.join(d, inst + ".wav"), "wb") as w:
+                    w.setnchannels(2); w.setsampwidth(2); w.setframerate(SR)
+                    w.writeframes(np.clip(np.rint(x.T * 32768.0), -32768, 32767).astype("<i2").tobytes())
+    torch.save({"model": {"module." + k: v for k, v in W.make_encoder_state_dict(0).items()}}, os.path.join(root, "enc.pt"))
+    torch.save({"model": {"module." + k: v for k, v in W.make_tcn_state_dict(0).items()}}, os.path.join(root, "tcn.pt"))
+    argv = ["--target_dir", os.path.join(root, "data") + "/", "--output_dir", os.path.join(root, "out") + "/",
+            "--ckpt_path_enc", os.path.join(root, "enc.pt"), "--ckpt_path_conv", os.path.join(root, "tcn.pt"),
+            "--segment_length", str(SEG_LEN), "--segment_length_ref", str(SEG_LEN), "--normalize_input", "False",
+            "--do_not_separate", "True"]
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        st.main(argv)                       # warm: weight packing, allocator
+        stats = dict(st.main(argv))
+    shutil.rmtree(root, ignore_errors=True)
+    return {"workload": "inference/style_transfer.py entry, 2 songs x 4 stems x 60 s PCM_16 WAV in -> mixture WAV out, "
+                        f"segment_length {SEG_LEN}, default batch_size 1",
+            "audio_s_per_s": stats["audio_seconds"] / stats["wall_seconds"], "wall_s": stats["wall_seconds"],
+            "song_seconds": stats["audio_seconds"],
+            "note": "song seconds (4 stems each) per wall second, file reads / decode / remix / PCM_16 / file writes included"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,8 +284,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="segments per GPU (default: BASELINE config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the `extra` legs (profiling runs)")
     ap.add_argument("--precision", default="auto", choices=["auto", "f16f8", "bf16x3"],
                     help="TCN operand format (auto = f16f8 with the range guard and a bf16x3 repeat when it fires)")
+    ap.add_argument("--ref-mode", default="allreduce", choices=["allreduce", "broadcast"],
+                    help="N > 1: shard the reference batch (all-reduce of partial sums) or encode on rank 0 and broadcast")
+    ap.add_argument("--gather-chunks", type=int, default=4, help="N > 1: sub-batches whose all-gather overlaps the next TCN")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -207,6 +303,7 @@ def main():
     import torch
     import torch.distributed as dist
     from music_mixing_style_transfer_b200 import _cabi, shard
+    from music_mixing_style_transfer_b200.pipeline import StyleTransferPipeline
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
@@ -221,11 +318,16 @@ def main():
     enc, tcn = build_models(device)
     tcn.precision = args.precision
     from music_mixing_style_transfer_b200 import synthetic as W
-    ref_host = W.synthetic_audio(B, L, seed=1234).pin_memory() if rank == 0 else None
+    shard_ref = world > 1 and args.ref_mode == "allreduce"
+    ref_lo, ref_hi = shard.shard_bounds(B, world, rank) if shard_ref else (0, B)
+    holds_ref = shard_ref or rank == 0
+    # the reference batch is the same seeded [B, 2, L] everywhere; a rank keeps the segments it encodes
+    ref_host = W.synthetic_audio(B, L, seed=1234)[ref_lo:ref_hi].contiguous().pin_memory() if holds_ref else None
     inp_host = W.synthetic_audio(B, L, seed=2000 + rank).pin_memory()
-    out_host = torch.empty(B, 2, L, dtype=torch.float32).pin_memory()
-    ref_dev = ref_host.to(device) if rank == 0 else None
+    ref_dev = ref_host.to(device) if holds_ref else None
     inp_dev = inp_host.to(device)
+    chunks = args.gather_chunks if (world > 1 and B % max(1, args.gather_chunks) == 0) else 1
+    step_kw = dict(gather=True, shard_reference=shard_ref, n_reference=B, gather_chunks=chunks)
 
     def barrier():
         if world > 1:
@@ -234,25 +336,29 @@ def main():
 
     def step_resident():
         with torch.no_grad():
-            return shard.sharded_style_transfer(enc, tcn, ref_dev, inp_dev, total, gather=True)
+            return shard.sharded_style_transfer(enc, tcn, ref_dev, inp_dev, total, **step_kw)
 
-    def step_e2e():
-        with torch.no_grad():
-            r = ref_host.to(device, non_blocking=True) if rank == 0 else None
-            x = inp_host.to(device, non_blocking=True)
-            _, out = shard.sharded_style_transfer(enc, tcn, r, x, total, gather=True)
-            lo = rank * B
-            out_host.copy_(out[lo:lo + B] if world > 1 else out, non_blocking=True)   # this rank's waveforms -> host
-            torch.cuda.current_stream().synchronize()
-            return out_host
+    pipe = StyleTransferPipeline(enc, tcn, device, total, depth=2, **step_kw)
 
-    def timed(fn, steps):
+    def run_e2e(steps):
+        """`steps` host-to-host steps through the public pipeline; every step's inputs come from pinned host memory and its
+        waveforms end in pinned host memory before this returns."""
+        for i in range(steps):
+            if i >= pipe.depth:
+                pipe.collect()
+            pipe.submit(ref_host, inp_host)
+        pipe.drain()
+
+    def timed(fn, steps, whole=False):
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         ev0.record()
-        for _ in range(steps):
-            fn()
+        if whole:
+            fn(steps)
+        else:
+            for _ in range(steps):
+                fn()
         ev1.record()
         barrier()
         t1 = time.time()
@@ -271,11 +377,10 @@ def main():
     ms_step = ms_total / args.steps
     value = total * L / SR / (ms_step / 1e3)
 
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    run_e2e(3)
+    ms_e2e, _, _ = timed(run_e2e, args.steps, whole=True)
     e2e_value = total * L / SR / (ms_e2e / args.steps / 1e3)
-    h2d = B * 2 * L * 4 * (2 if rank == 0 else 1)
+    h2d = (inp_host.numel() + (ref_host.numel() if holds_ref else 0)) * 4
     d2h = B * 2 * L * 4
 
     # ---- roofline leg: per-launch CUDA events around the dominant kernel (tcn_block_umma_kernel) ----
@@ -291,12 +396,11 @@ def main():
         events.append((phase, ev))
 
     with torch.no_grad():
-        emb = enc(ref_dev).mean(dim=0) if rank == 0 else cond[0]
-        tcn.forward_layers(inp_dev, emb.unsqueeze(0))        # warm
+        tcn.forward_layers(inp_dev, cond)                    # warm
         events.clear()
         n_prof = 3
         for _ in range(n_prof):
-            tcn.forward_layers(inp_dev, emb.unsqueeze(0), on_launch)
+            tcn.forward_layers(inp_dev, cond, on_launch)
     torch.cuda.synchronize()
     durs = [events[i][1].elapsed_time(events[i + 1][1]) for i in range(0, len(events), 2)]
     umma_ms = sum(durs) / max(1, len(durs))
@@ -309,24 +413,64 @@ def main():
     roofline = {"kernel": "tcn_block_umma_kernel", "bound": "tensor", "achieved": achieved,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
                 "peak_source": f"{pk['source']} bf16 dense (sustained: kernel timed inside a long step)",
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of
-                # this command (profiles/r01_summary.md section 2); = 1.00x the algorithmic activation bytes
-                # dram__bytes_read.sum + dram__bytes_write.sum, mean over the 13 launches of a step, from the committed ncu
-                # captures of this workload (profiles/r01g_tcn_ncu.csv for blocks 1-6, r01g_tcn_ncu_blkfast.csv for blocks 7-13):
-                # 5.10 GB read + 3.93 GB written = 1.05x the algorithmic activation bytes
-                "traffic": 9.03e9 if (B == BATCH_PER_GPU and L == SEG_LEN and f8) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum, mean over the 13 launches of a step, from the committed ncu capture
+                # of this workload (profiles/r02_tcn_ncu.csv; r01g: 5.10 GB read + 3.93 GB written = 1.05x the algorithmic bytes)
+                "traffic": TRAFFIC_PER_LAUNCH if (B == BATCH_PER_GPU and L == SEG_LEN and f8) else None,
                 "traffic_algorithmic": 2.0 * B * L * 512, "ms_per_launch": umma_ms, "launches_per_step": n_umma, "share_of_step": share,
                 "algorithmic_flop_per_launch": flops_per_launch,
                 "note": ("fp32-grade parity needs split operands: fp16 main product + two e4m3 correction products (each at twice "
                          "the bf16 rate) = 2 bf16-MMA equivalents per algorithmic MMA, so frac <= 0.5 by construction; "
-                         "tensor_pipe_frac = 2*frac") if f8 else
+                         "tensor_pipe_frac = 2*frac.  The kernel runs at the board's 1000 W cap: its time is energy per "
+                         "launch / cap (profiles/r02_tcn_ablation.md)") if f8 else
                         ("fp32-grade parity needs the 3-product bf16 split: tensor-pipe work is 3x the algorithmic FLOPs, "
                          "so frac <= 0.333 by construction; tensor_pipe_frac = 3*frac"),
                 "tensor_pipe_frac": units * achieved / pk["bf16_tflops_sustained"]}
 
+    extra = {}
+    if not args.no_extra:
+        # ---- configs[3]: 64 input segments per GPU (512 over 8 GPUs), same reference batch, a few steps on every rank ----
+        try:
+            x64 = torch.cat([inp_dev, inp_dev.flip(0)], dim=0) if B == BATCH_PER_GPU else None
+            if x64 is not None:
+                def step64():
+                    with torch.no_grad():
+                        return shard.sharded_style_transfer(enc, tcn, ref_dev, x64, 2 * total, gather=True,
+                                                            shard_reference=shard_ref, n_reference=B, gather_chunks=chunks)
+                step64()
+                ms64, _, _ = timed(step64, 3)
+                extra["config4_64_per_gpu"] = {
+                    "workload": f"configs[3]: full forward, {2 * total} input segments of 262144 sharded 64 per GPU over {world} GPU(s), "
+                                "reference batch 32", "ms_per_step": ms64 / 3, "audio_s_per_s": 2 * total * L / SR / (ms64 / 3 / 1e3)}
+            del x64
+        except Exception as exc:
+            extra["config4_64_per_gpu"] = {"error": repr(exc)}
+        torch.cuda.empty_cache()
+        # ---- configs[4]: interpolation, two reference embeddings, per-ROW conditioning, 16 rows per GPU; L = 2^18 and 82,412 ----
+        try:
+            rows, S = 16, 16
+            legs = {}
+            for L5 in (SEG_LEN, 82412):
+                xi = inp_dev[:rows, :, :L5].contiguous()
+                ra = ref_dev[:2] if (rank == 0 and ref_dev is not None) else (W.synthetic_audio(2, L, seed=1234).to(device) if rank == 0 else None)
+                rb = W.synthetic_audio(2, L, seed=1300).to(device) if rank == 0 else None
+                wts = shard.interpolation_weights(rows * world, S, device=device)
+
+                def step5():
+                    with torch.no_grad():
+                        return shard.sharded_interpolation(enc, tcn, ra, rb, xi, rows * world, wts, gather=True)
+                step5()
+                ms5, _, _ = timed(step5, 3)
+                legs[str(L5)] = {"ms_per_step": ms5 / 3, "audio_s_per_s": rows * world * L5 / SR / (ms5 / 3 / 1e3)}
+            extra["config5_interpolation"] = {
+                "workload": f"configs[4]: interpolation mode, 2 reference embeddings (1 broadcast of [2, 2048]), interpolate_segments {S}, "
+                            f"{rows} rows per GPU x {world} GPU(s), cond [rows, 2048] per row; segment lengths 262144 and 82412",
+                "by_segment_length": legs}
+        except Exception as exc:
+            extra["config5_interpolation"] = {"error": repr(exc)}
+        torch.cuda.empty_cache()
+
     # ---- extra: BASELINE config 3 (FX chain only, B=256 random-parameter segments) on rank 0 ----
-    fx_extra = None
-    if rank == 0:
+    if rank == 0 and not args.no_extra:
         try:
             import numpy as np
             from music_mixing_style_transfer_b200.mixing_manipulator import fx_chain_forward
@@ -350,17 +494,19 @@ def main():
             torch.cuda.synchronize()
             fx_ms = f0.elapsed_time(f1) / 10
             fx_gbs = 16.0 * fb * L / (fx_ms * 1e-3) / 1e9
-            fx_extra = {"workload": "configs[2]: FX chain (EQ+comp+imager+gain), batch=256 random-param segments of 262144",
-                        "ms": fx_ms, "audio_s_per_s": fb * L / SR / (fx_ms * 1e-3),
-                        "roofline": {"bound": "hbm", "achieved": fx_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                     "frac": fx_gbs / pk["hbm_gbs"], "algorithmic_bytes": 16.0 * fb * L}}
+            extra["fx_chain_config3"] = {
+                "workload": "configs[2]: FX chain (EQ+comp+imager+gain), batch=256 random-param segments of 262144",
+                "ms": fx_ms, "audio_s_per_s": fb * L / SR / (fx_ms * 1e-3),
+                "roofline": {"bound": "hbm", "achieved": fx_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                             "frac": fx_gbs / pk["hbm_gbs"], "algorithmic_bytes": 16.0 * fb * L,
+                             "traffic": 3.06e9, "traffic_source": "profiles/r01f_fx_v2_2_ncu_full.csv: three passes "
+                             "(two whole-segment RMS barriers), the EQ and compressor passes are instruction-bound"}}
             del fx_x, fx_y
         except Exception as exc:  # the headline line must survive a failure of the extra leg
-            fx_extra = {"error": repr(exc)}
+            extra["fx_chain_config3"] = {"error": repr(exc)}
 
     # ---- extra: the sample-format kernels either side of the forward, HBM-bound streams, on rank 0 ----
-    io_extra = None
-    if rank == 0:
+    if rank == 0 and not args.no_extra:
         try:
             from music_mixing_style_transfer_b200 import wav_io
             n_fr = 2 * B * L                                     # two batches worth of stereo frames: every buffer set > the 126 MB L2
@@ -384,15 +530,24 @@ def main():
             dec_ms, enc_ms = g0.elapsed_time(g1) / 10, g1.elapsed_time(g2) / 10
             dec_bytes = n_fr * (4 + 8)                           # int16 stereo in, fp32 planar out
             enc_bytes = (n_fr // 2) * (4 * 8 + 4)                # 4 fp32 stereo stems in, int16 stereo out
-            io_extra = {"workload": "8f-1: PCM16 decode of 2 batches of stereo frames (201 MB in + out); remix of 4 stems of one batch "
-                                    "+ PCM_16 quantise (302 MB); buffers exceed the L2",
-                        "decode": {"ms": dec_ms, "GB/s": dec_bytes / (dec_ms * 1e-3) / 1e9,
-                                   "frac_of_hbm_peak": dec_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
-                        "encode_mix": {"ms": enc_ms, "GB/s": enc_bytes / (enc_ms * 1e-3) / 1e9,
-                                       "frac_of_hbm_peak": enc_bytes / (enc_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}}
+            extra["wav_io"] = {
+                "workload": "8f-1: PCM16 decode of 2 batches of stereo frames (201 MB in + out); remix of 4 stems of one batch "
+                            "+ PCM_16 quantise (302 MB); buffers exceed the L2",
+                "decode": {"ms": dec_ms, "GB/s": dec_bytes / (dec_ms * 1e-3) / 1e9,
+                           "frac_of_hbm_peak": dec_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
+                "encode_mix": {"ms": enc_ms, "GB/s": enc_bytes / (enc_ms * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": enc_bytes / (enc_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}}
             del pcm, dec, stems
         except Exception as exc:
-            io_extra = {"error": repr(exc)}
+            extra["wav_io"] = {"error": repr(exc)}
+        torch.cuda.empty_cache()
+
+    # ---- extra: file -> file through the inference entry (single process only: the entry would start its own group) ----
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            extra["file_to_file"] = file_to_file_leg(device, os.environ.get("TMPDIR", "/tmp"))
+        except Exception as exc:
+            extra["file_to_file"] = {"error": repr(exc)}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -408,8 +563,20 @@ def main():
         cpu_baseline = {"value": secs / dt, "unit": UNIT, "cores": cores, "host_cores": os.cpu_count(), "kind": "port",
                         "sample": f"1 reference + 1 input segment of {SEG_LEN} stereo samples through the oracle port of "
                                   f"the reference torch modules, {dt:.1f} s wall", "torch": torch.__version__}
+        if world == 1 and not args.no_extra:
+            # the same modules on this GPU through cuDNN, next to the CPU number (secondary baseline, not the target)
+            try:
+                extra["reference_modules_on_gpu"] = dict(
+                    reference_modules_on_gpu(device, B, L, state.get("out"), (state["ref"], state["inp"])),
+                    workload="oracle port of the reference torch modules on this GPU (cuDNN), configs[1] segments, batch 8",
+                    note="what inference/style_transfer.py:29-32 runs when CUDA is available; rms_err_vs_cpu_forward on the "
+                         "cpu_baseline sample (1 segment)")
+            except Exception as exc:
+                extra["reference_modules_on_gpu"] = {"error": repr(exc)}
 
     if rank == 0:
+        n_enc = 27                                           # 24 conv + split + pool + batch reduction (ranks that encode)
+        n_tcn = 15 * chunks                                  # film + block 0 + 13 tcgen05 launches per converted sub-batch
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None,
@@ -419,16 +586,21 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": "configs[1]: FXencoder+MixFXcloner full forward, batch=32 segments of 262144 "
                                        "stereo samples per GPU", "segment_length": L, "batch_per_gpu": B,
-                           "global_batch": total, "reference_batch": B, "parallelism": f"dp{world} (segments sharded; "
-                           "1 NCCL broadcast of the embedding + 1 all-gather of outputs)" if world > 1 else "single GPU",
+                           "global_batch": total, "reference_batch": B, "tcn_precision": args.precision,
+                           "parallelism": (f"dp{world} (input segments sharded; reference batch sharded, 1 NCCL all-reduce of the "
+                                           f"embedding sums; output all-gather in {chunks} sub-batches overlapping the TCN)"
+                                           if shard_ref else f"dp{world} (segments sharded; 1 NCCL broadcast of the embedding + "
+                                           f"all-gather of outputs in {chunks} sub-batches)") if world > 1 else "single GPU",
                            "l2": "inputs and activations (>= 67 MB per tensor, 4.3 GB per TCN activation) exceed the 126 MB L2",
                            "weights": "seeded random, reference state_dict layout"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": args.steps * (25 + 15) if rank == 0 else args.steps * 15,
-                "gpu_launches_per_step": {"encoder (24 conv + 1 pool, rank 0)": 25, "tcn (film + block0 + 13 umma)": 15},
-                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": {"fx_chain_config3": fx_extra, "wav_io": io_extra},
-                "tflops_algorithmic": (TCN_FLOP_PER_SAMPLE * L * B + ENC_FLOP_PER_SEG * B) / (ms_step * 1e-3) / 1e12}
+                        "ms_per_step": ms_e2e / args.steps,
+                        "api": "pipeline.StyleTransferPipeline.submit / collect (copies on side streams, 2 buffer sets)"},
+                "gpu_launches": args.steps * (n_enc + n_tcn),
+                "gpu_launches_per_step": {"encoder (24 conv + split + pool + batch mean)": n_enc,
+                                          f"tcn (film + block0 + 13 umma) x {chunks} sub-batch(es)": n_tcn},
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": extra,
+                "tflops_algorithmic": (TCN_FLOP_PER_SAMPLE * L * B + ENC_FLOP_PER_SEG * (ref_hi - ref_lo)) / (ms_step * 1e-3) / 1e12}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -59,6 +59,10 @@ int mst_enc_conv1d(const float* x, const float* w_folded, const float* b_folded,
 /* AdaptiveAvgPool1d(1).squeeze(-1) (architectures.py:62,67): y[B,C] = mean_t x[B,C,T] */
 int mst_enc_mean_pool(const float* x, float* y, int B, int C, int T, void* stream);
 
+/* out[c] = scale * sum over rows of x[rows, cols] (rows added in order): `stack -> reshape -> mean(0)` over the reference
+ * segments' embeddings (inference/style_transfer.py:152-153) with scale = 1/rows, or a rank's partial sum with scale = 1 */
+int mst_rows_reduce(const float* x, int rows, int cols, float scale, float* out, void* stream);
+
 size_t mst_enc_packed_bytes(const mst_enc_config* cfg);
 /* raw: host array of 12*n_blocks device pointers, per block: conv1 {w,b,bn_w,bn_b,bn_mean,bn_var}, conv2 {...} */
 int mst_enc_pack(const mst_enc_config* cfg, const float* const* raw, float* packed, void* stream);
@@ -143,6 +147,26 @@ size_t mst_fx_workspace_bytes(int B, int L);
 /* x,y: fp32 [B,2,L] (channel-major; the reference's arrays are [L,2]); params: fp32 [B,20]; stages: MST_FX_* mask */
 int mst_fx_chain_forward(const float* x, const float* params, float* y, int B, int L, float sample_rate, int stages,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- stereo building blocks of the input FX normaliser and the remaining processors ----------
+ * Reference paths relative to mixing_style_transfer/mixing_manipulator/.
+ * mst_biquad_cascade: up to 5 cascaded biquads with explicit coefficients coef[B][n_sections][5] = (b0, b1, b2, a1, a2), a0 = 1,
+ *   device float64, zero initial state, on x[B,2,L] -> y (the EQ kernel's time-parallel scan).  Replaces the K-weighting
+ *   `IIRfilter.apply_filter` pair of the BS.1770 meter behind fx_utils.lufs_normalize (fx_utils.py:220-238; pyloudnorm).
+ * mst_stereo_stats: stats[B][4] = (sum L^2, sum R^2, sum L*R, max|x|) in float64: the reductions of normalize_imager /
+ *   process_balance (normalization_imager.py:34-36,94-99) and the peak of lufs_normalize (fx_utils.py:231).
+ * mst_stereo_mix: y = M x per frame, matrices[B][4] = (m0 m1; m2 m3) device float32: mid/side gains and L/R balance of
+ *   normalize_imager (normalization_imager.py:31-76), Panner.process (common_audioeffects.py:935), the loudness gain.
+ * mst_block_energy: z[c][j] = sum of squares of x[c][lo[j]:hi[j]] (float64): the gating blocks of the loudness meter.
+ * mst_haas: y = x, y[ch] += feedback * roll(x[ch], delay) per segment (haas_process, common_audioeffects.py:767-787); x != y. */
+int mst_biquad_cascade(const float* x, const double* coef, int n_sections, float* y, int B, int L, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int mst_stereo_stats(const float* x, int B, long long L, double* stats, void* stream);
+int mst_stereo_mix(const float* x, const float* matrices, float* y, int B, long long L, void* stream);
+int mst_block_energy(const float* x, int n_channels, long long T, const long long* lo, const long long* hi, int n_blocks,
+                     double* z, void* stream);
+int mst_haas(const float* x, float* y, int B, long long L, const int* delay, const float* feedback, const int* channel,
+             void* stream);
 
 /* ---- WAV sample formats on the device: the steps either side of the forward -------------------
  * mst_pcm_decode replaces load_wav_segment's int -> float conversion and de-interleave

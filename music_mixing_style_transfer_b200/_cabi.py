@@ -39,6 +39,7 @@ SIGNATURES = {
     "mst_conv1d_fold_bn": (c_int, [c_void_p] * 6 + [c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "mst_enc_conv1d": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
     "mst_enc_mean_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "mst_rows_reduce": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
     "mst_enc_packed_bytes": (c_size_t, [POINTER(EncConfig)]),
     "mst_enc_pack": (c_int, [POINTER(EncConfig), POINTER(c_void_p), c_void_p, c_void_p]),
     "mst_enc_workspace_bytes": (c_size_t, [POINTER(EncConfig), c_int, c_int]),
@@ -59,6 +60,11 @@ SIGNATURES = {
     "mst_fx_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mst_fx_chain_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_size_t,
                                      c_void_p]),
+    "mst_biquad_cascade": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "mst_stereo_stats": (c_int, [c_void_p, c_int, ctypes.c_longlong, c_void_p, c_void_p]),
+    "mst_stereo_mix": (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.c_longlong, c_void_p]),
+    "mst_block_energy": (c_int, [c_void_p, c_int, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "mst_haas": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mst_pcm_decode": (c_int, [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, ctypes.c_longlong, c_void_p]),
     "mst_pcm_encode_mix": (c_int, [c_void_p, c_int, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_void_p]),
 }

@@ -473,6 +473,19 @@ static size_t enc_max_act_split(const mst_enc_config* cfg, const EncOffsets& o, 
 
 using namespace mst;
 
+namespace mst {
+// out[c] = scale * sum_r x[r][c], rows added in order (bit-reproducible): the mean over the reference segments' embeddings
+// (inference/style_transfer.py:152-153) without an eager torch reduction on the path
+__global__ void __launch_bounds__(256) rows_reduce_kernel(const float* __restrict__ x, int rows, int cols, float scale,
+                                                           float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int r = 0; r < rows; ++r) s += __ldg(x + (size_t)r * cols + c);
+  out[c] = s * scale;
+}
+}  // namespace mst
+
 extern "C" {
 
 int mst_conv1d_fold_bn(const float* w, const float* b, const float* bn_w, const float* bn_b, const float* bn_mean,
@@ -498,6 +511,12 @@ int mst_enc_mean_pool(const float* x, float* y, int B, int C, int T, void* strea
   const int rows = B * C;
   mean_pool_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, y, rows, T);
   return launch_ok("mean_pool_kernel");
+}
+
+int mst_rows_reduce(const float* x, int rows, int cols, float scale, float* out, void* stream) {
+  MST_CHECK(x && out && rows > 0 && cols > 0, "rows_reduce: bad arguments");
+  rows_reduce_kernel<<<cdiv(cols, 256), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, scale, out);
+  return launch_ok("rows_reduce_kernel");
 }
 
 size_t mst_enc_packed_bytes(const mst_enc_config* cfg) {

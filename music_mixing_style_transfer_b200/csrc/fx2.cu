@@ -256,19 +256,27 @@ struct EqShared {
 __device__ __forceinline__ u64 shfl_up2(u64 v, int off) { return __shfl_up_sync(0xffffffffu, v, off); }
 __global__ void __launch_bounds__(kThreads, 2)
 eq_kernel(const float* __restrict__ x, const float* __restrict__ params, float* __restrict__ y, double* __restrict__ stats,
-          int L, float sample_rate, int enable, int vec) {
+          int L, float sample_rate, int enable, int vec, const double* __restrict__ coef, int n_coef_sections) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EqShared& sh = *reinterpret_cast<EqShared*>(smem_raw);
   float* stg_all = reinterpret_cast<float*>(smem_raw + ((sizeof(EqShared) + 15) / 16) * 16);
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   float* stg = stg_all + wid * (2 * 32 * kEqRow);
-  const float* p = params + (size_t)b * MST_FX_NPARAMS;
+  const float* p = params != nullptr ? params + (size_t)b * MST_FX_NPARAMS : nullptr;
 
   if (tid < 5) {
     // dict order low_shelf, first, second, third, high_shelf (:391); shelves Q = 0.707 (:454)
     const int gi[5] = {0, 2, 5, 8, 11}, fi[5] = {1, 3, 6, 9, 12}, qi[5] = {-1, 4, 7, 10, -1}, ty[5] = {0, 1, 1, 1, 2};
-    const double Q = qi[tid] < 0 ? 0.707 : (double)p[qi[tid]];
-    const Biquad q = rbj((double)p[gi[tid]], Q, (double)p[fi[tid]], (double)sample_rate, ty[tid]);
+    Biquad q;
+    if (coef != nullptr) {
+      // explicit sections (mst_biquad_cascade): (b0, b1, b2, a1, a2) per section, a0 = 1; the unused ones are identities
+      const double* c5 = coef + ((size_t)b * n_coef_sections + tid) * 5;
+      if (tid < n_coef_sections) { q.b0 = c5[0]; q.b1 = c5[1]; q.b2 = c5[2]; q.a1 = c5[3]; q.a2 = c5[4]; }
+      else { q.b0 = 1.0; q.b1 = 0.0; q.b2 = 0.0; q.a1 = 0.0; q.a2 = 0.0; }
+    } else {
+      const double Q = qi[tid] < 0 ? 0.707 : (double)p[qi[tid]];
+      q = rbj((double)p[gi[tid]], Q, (double)p[fi[tid]], (double)sample_rate, ty[tid]);
+    }
     const double Bc = q.b0 + q.b1 + q.b2, dl = 1.0 + q.a1 + q.a2, cy = -(1.0 + q.a1), cx = q.b0 + q.b1;
     sh.cf[tid][0] = (float)q.b0;
     sh.cf[tid][1] = (float)Bc;
@@ -819,8 +827,7 @@ static size_t comp_smem_bytes() { return align_up(sizeof(CompShared), 16) + (siz
 
 }  // namespace fx2
 
-static int fx2_chain_forward(const float* x, const float* params, float* y, int B, int L, float sample_rate, int stages, double* stats,
-                             cudaStream_t st) {
+static int fx2_set_attributes() {
   using namespace fx2;
   static bool attr_done[64] = {false};
   int dev = 0;
@@ -830,8 +837,15 @@ static int fx2_chain_forward(const float* x, const float* params, float* y, int 
     MST_CUDA_OK(cudaFuncSetAttribute(comp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)comp_smem_bytes()));
     attr_done[dev] = true;
   }
+  return 0;
+}
+
+static int fx2_chain_forward(const float* x, const float* params, float* y, int B, int L, float sample_rate, int stages, double* stats,
+                             cudaStream_t st) {
+  using namespace fx2;
+  if (fx2_set_attributes()) return 1;
   const int vec = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) % 16 == 0) ? 1 : 0;
-  eq_kernel<<<B, kThreads, eq_smem_bytes(), st>>>(x, params, y, stats, L, sample_rate, (stages & MST_FX_EQ) ? 1 : 0, vec);
+  eq_kernel<<<B, kThreads, eq_smem_bytes(), st>>>(x, params, y, stats, L, sample_rate, (stages & MST_FX_EQ) ? 1 : 0, vec, nullptr, 0);
   if (launch_ok("fx2::eq_kernel")) return 1;
   comp_kernel<<<B, kThreads, comp_smem_bytes(), st>>>(params, y, stats, L, sample_rate, stages, vec);
   if (launch_ok("fx2::comp_kernel")) return 1;
@@ -858,6 +872,18 @@ int mst_fx_chain_forward(const float* x, const float* params, float* y, int B, i
   MST_CHECK(workspace_bytes >= mst_fx_workspace_bytes(B, L), "fx_chain_forward: workspace too small");
   MST_CHECK(sample_rate > 0.f, "fx_chain_forward: bad sample rate");
   return fx2_chain_forward(x, params, y, B, L, sample_rate, stages, reinterpret_cast<double*>(workspace), (cudaStream_t)stream);
+}
+
+int mst_biquad_cascade(const float* x, const double* coef, int n_sections, float* y, int B, int L, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  MST_CHECK(x && coef && y && workspace, "biquad_cascade: null pointer");
+  MST_CHECK(B > 0 && L > 0 && n_sections >= 1 && n_sections <= 5, "biquad_cascade: bad shape B=%d L=%d sections=%d", B, L, n_sections);
+  MST_CHECK(workspace_bytes >= mst_fx_workspace_bytes(B, L), "biquad_cascade: workspace too small");
+  if (fx2_set_attributes()) return 1;
+  const int vec = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) % 16 == 0) ? 1 : 0;
+  fx2::eq_kernel<<<B, fx2::kThreads, fx2::eq_smem_bytes(), (cudaStream_t)stream>>>(x, nullptr, y, reinterpret_cast<double*>(workspace), L,
+                                                                                  44100.f, 1, vec, coef, n_sections);
+  return launch_ok("fx2::eq_kernel (biquad cascade)");
 }
 
 }  // extern "C"

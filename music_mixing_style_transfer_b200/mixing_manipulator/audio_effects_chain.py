@@ -1,7 +1,7 @@
-"""Effects-chain factory -- same surface as the reference's `mixing_manipulator/audio_effects_chain.py:17-95` for the
-four effects on the hot path.  Other effect names of the reference (pan, reverb, expander ...) raise
-NotImplementedError: they are outside BASELINE's FX chain."""
-from .common_audioeffects import (AugmentationChain, Compressor, Equaliser, Gain, MidSideImager, Processor)
+"""Effects-chain factory -- same surface as the reference's `mixing_manipulator/audio_effects_chain.py:17-95`: the four
+effects of BASELINE's FX chain (eq, comp, imager, gain) plus the panner.  The expander and the reverbs
+(algorithmic: pymixconsole comb / all-pass components; convolutional: impulse-response data sets) raise NotImplementedError."""
+from .common_audioeffects import (AugmentationChain, Compressor, Equaliser, Gain, MidSideImager, Panner, Processor)
 
 
 # create augmentation effects chain according to targeted effects with their applying probability
@@ -40,10 +40,14 @@ def create_effects_augmentation_chain(effects,
             fx_list.append(Equaliser(n_channels=2, sample_rate=sample_rate))
         elif 'comp' in cur_fx.lower():
             fx_list.append(Compressor(sample_rate=sample_rate))
+        elif 'expand' in cur_fx.lower():
+            raise NotImplementedError(f"effect {cur_fx!r}: the expander has no B200 kernel yet (SURVEY.md 8f-4)")
+        elif 'pan' in cur_fx.lower():
+            fx_list.append(Panner())
         elif 'image' in cur_fx.lower():
             fx_list.append(MidSideImager())
-        elif any(k in cur_fx.lower() for k in ('expand', 'pan', 'algorithmic', 'reverb')):
-            raise NotImplementedError(f"effect {cur_fx!r} is outside the B200 FX chain (eq, comp, imager, gain)")
+        elif any(k in cur_fx.lower() for k in ('algorithmic', 'reverb')):
+            raise NotImplementedError(f"effect {cur_fx!r}: the reverbs have no B200 kernel yet (SURVEY.md 8f-4)")
         else:
             raise ValueError(f"make sure the target effects are in the Augment FX chain : received fx called {cur_fx}")
 

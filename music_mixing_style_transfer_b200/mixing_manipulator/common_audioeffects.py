@@ -97,6 +97,8 @@ class Parameter:
         elif self.kind in ('float', 'int') and self.min is not None and self.max is not None:
             v = self.min + np.random.rand() * (self.max - self.min)
             self.value = int(round(v)) if self.kind == 'int' else float(v)
+        elif self.kind == 'string' and self.options:
+            self.value = self.options[np.random.randint(len(self.options))]
 
     def __repr__(self):
         return f"Parameter({self.name}={self.value})"
@@ -262,6 +264,126 @@ class Gain(Processor):
         return v
 
 
+# %%%%%%%%%%%%%%%%%%%%%%%%%%%%% HAAS EFFECT %%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%
+class Haas(Processor):
+    """Haas Effect Processor (common_audioeffects.py:790-850): one channel gets a delayed copy of itself added,
+    y[:, ch] += feedback * roll(x[:, ch], delay) (:767-787); kernel mst_haas."""
+    STAGE = 0
+
+    def __init__(self, sample_rate, delay_range=(-0.040, 0.040), name='Haas', parameters=None):
+        super().__init__(name=name, parameters=parameters, block_size=None, sample_rate=sample_rate)
+        if not parameters:
+            self.parameters = ParameterList()
+            self.parameters.add(Parameter('delay', int(delay_range[1] * sample_rate), 'int', units='samples',
+                                          minimum=int(delay_range[0] * sample_rate),
+                                          maximum=int(delay_range[1] * sample_rate)))
+            self.parameters.add(Parameter('feedback', 0.35, 'float', minimum=0.33, maximum=0.66))
+            self.parameters.add(Parameter('wet_channel', 'left', 'string', options=['left', 'right']))
+
+    def process(self, x):
+        from .data_normalization import haas
+        x = np.asarray(x)
+        assert x.shape[1] == 1 or x.shape[1] == 2, 'Haas effect only works with monaural or stereo audio.'
+        if x.shape[1] < 2:
+            x = np.repeat(x, 2, axis=1)
+        xt = _to_device(x)
+        ch = {'left': 0, 'right': 1}.get(self.parameters.wet_channel.value, -1)     # any other string: no wet channel (:781-784)
+        y = haas(xt, [int(self.parameters.delay.value)], [float(self.parameters.feedback.value)], [ch])
+        return np.ascontiguousarray(y[0].cpu().numpy().T)
+
+
+# %%%%%%%%%%%%%%%%%%%%%%%%%%%%%% PANNER %%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%
+class Panner(Processor):
+    """Simple stereo panner (common_audioeffects.py:854-952): per-channel gains from the pan law; kernel mst_stereo_mix."""
+    STAGE = 0
+
+    def __init__(self, name='Panner', parameters=None):
+        super().__init__(name=name, parameters=parameters, block_size=None, sample_rate=None)
+        if not parameters:
+            self.parameters = ParameterList()
+            self.parameters.add(Parameter('pan', 0.5, 'float', minimum=0., maximum=1.))
+            self.parameters.add(Parameter('pan_law', '-4.5dB', 'string', options=['-4.5dB', 'linear', 'constant_power']))
+        self.update()
+
+    def _calculate_pan_coefficents(self):
+        self.gains = np.zeros(2, dtype=self.dtype)
+        theta = self.parameters.pan.value * (np.pi / 2)         # [0, 1] -> [0, pi/2]
+        law = self.parameters.pan_law.value
+        if law == 'linear':
+            self.gains[0] = ((np.pi / 2) - theta) * (2 / np.pi)
+            self.gains[1] = theta * (2 / np.pi)
+        elif law == 'constant_power':
+            self.gains[0] = np.cos(theta)
+            self.gains[1] = np.sin(theta)
+        elif law == '-4.5dB':
+            self.gains[0] = np.sqrt(((np.pi / 2) - theta) * (2 / np.pi) * np.cos(theta))
+            self.gains[1] = np.sqrt(theta * (2 / np.pi) * np.sin(theta))
+        else:
+            raise ValueError(f'Invalid pan_law {law}.')
+
+    def update(self, parameter_name=None):
+        self._calculate_pan_coefficents()
+
+    def process(self, x):
+        from .data_normalization import stereo_mix
+        x = np.asarray(x)
+        assert x.shape[1] == 1 or x.shape[1] == 2, 'Panner only works with monaural or stereo audio.'
+        if x.shape[1] < 2:
+            x = np.repeat(x, 2, axis=1)
+        y = stereo_mix(_to_device(x), [[float(self.gains[0]), 0.0, 0.0, float(self.gains[1])]])
+        return np.ascontiguousarray(y[0].cpu().numpy().T)
+
+
+def _to_device(x):
+    """float [n, 2] numpy (time-major, as the reference passes audio) -> float32 CUDA [1, 2, n]."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("mixing_manipulator (B200 engine): no CUDA device; there is no CPU fallback")
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x).T, dtype=np.float32)).unsqueeze(0).cuda()
+
+
+_STAGE_SLICE = {FX_EQ: slice(0, 13), FX_COMP: slice(13, 17), FX_IMAGER: slice(17, 18), FX_GAIN: slice(18, 20)}
+
+
+def _top_stage(mask):
+    return max(s for s in (FX_EQ, FX_COMP, FX_IMAGER, FX_GAIN) if mask & s) if mask else 0
+
+
+class _DeviceList:
+    """The chain's list of [n, 2] arrays, either on the host (numpy) or on the device (float32 [2, n] tensors)."""
+
+    def __init__(self, x_list):
+        self._host, self._dev = list(x_list), None
+
+    def host(self):
+        if self._dev is not None:
+            self._host = [np.ascontiguousarray(t.cpu().numpy().T) for t in self._dev]
+            self._dev = None
+        return self._host
+
+    def set_host(self, y_list):
+        self._host, self._dev = list(y_list), None
+
+    def run_stages(self, stages, rms_normalize, params, *sample_rates):
+        if self._dev is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("mixing_manipulator (B200 engine): no CUDA device; there is no CPU fallback")
+            for x in self._host:
+                if np.asarray(x).ndim != 2 or np.asarray(x).shape[1] != 2:
+                    raise ValueError(f"expected audio of shape [n_samples, 2], got {np.asarray(x).shape}")
+            self._dev = [torch.from_numpy(np.ascontiguousarray(np.asarray(x).T, dtype=np.float32)).cuda() for x in self._host]
+        mask = stages | (FX_RMSNORM if rms_normalize else 0)
+        sr = float(sample_rates[0]) if sample_rates else 44100.0
+        by_len = {}
+        for i, t in enumerate(self._dev):
+            by_len.setdefault(t.shape[-1], []).append(i)
+        for idx in by_len.values():
+            batch = torch.stack([self._dev[i] for i in idx], dim=0)
+            p = torch.from_numpy(np.tile(np.asarray(params, np.float32), (len(idx), 1))).to(batch.device)
+            y = fx_chain_forward(batch, p, mask, sr)
+            for k, i in enumerate(idx):
+                self._dev[i] = y[k]
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 class AugmentationChain:
     """Basic audio Fx chain which is used for data augmentation (common_audioeffects.py:91-201)."""
@@ -280,7 +402,7 @@ class AugmentationChain:
 
     def apply_processor(self, x, processor: Processor, rms_normalize):
         """One effect (+ RMS re-normalisation, :142-145) on one [n, 2] array; the normalisation is fused in the kernel."""
-        unfused = (rms_normalize and processor.STAGE == FX_GAIN) or getattr(processor, "hard_clip", False)
+        unfused = (rms_normalize and processor.STAGE == FX_GAIN) or getattr(processor, "hard_clip", False) or processor.STAGE == 0
         if unfused:
             # Gain is never normalised by the factory (audio_effects_chain.py:92) and hard_clip is off by default:
             # rare combinations take the effect kernel, then the reference's own normalisation arithmetic on the host
@@ -297,11 +419,15 @@ class AugmentationChain:
         return x_list
 
     def __call__(self, x_list):
+        """Same semantics and the same order of `np.random` draws as the reference (:156-192): per effect a Bernoulli gate,
+        then the randomisation of its parameters.  The DSP is batched: the gated EQ / compressor / imager / gain stages that
+        follow each other in the kernel's stage order are ONE `fx_chain_forward` launch chain over the whole list (arrays of
+        equal length share a batch), and the list crosses PCIe once in each direction instead of once per effect and array."""
         # randomly shuffle effect order if `self.shuffle` is True
         if self.shuffle:
             shuffle(self.fxs)
-        # apply effects with probabilities given in `self.fxs`
-        y_list = x_list.copy()
+        state = _DeviceList(x_list)
+        run = None                                   # pending fused run: [stage mask, rms flag of its normalised stages, params]
         for fx, p, rms_normalize in self.fxs:
             if np.random.rand() < p:
                 if isinstance(fx, Processor):
@@ -310,9 +436,31 @@ class AugmentationChain:
                         fx.randomize()
                     else:
                         fx.update(None)
-                    y_list = self.apply_same_processor(y_list, fx, rms_normalize)
+                    fusable = fx.STAGE != 0 and not getattr(fx, "hard_clip", False) and not (fx.STAGE == FX_GAIN and rms_normalize)
+                    if fusable:
+                        norm = None if fx.STAGE == FX_GAIN else bool(rms_normalize)     # the gain stage is never normalised
+                        if run is not None and (fx.STAGE <= _top_stage(run[0]) or (norm is not None and run[1] not in (None, norm))):
+                            state.run_stages(*run)
+                            run = None
+                        if run is None:
+                            run = [0, None, _NEUTRAL.copy()]
+                        run[0] |= fx.STAGE
+                        run[1] = norm if norm is not None else run[1]
+                        run[2][_STAGE_SLICE[fx.STAGE]] = fx.param_vector()[_STAGE_SLICE[fx.STAGE]]
+                        run.append(fx.sample_rate) if fx.sample_rate else None
+                    else:
+                        if run is not None:
+                            state.run_stages(*run)
+                            run = None
+                        state.set_host(self.apply_same_processor(state.host(), fx, rms_normalize))
                 else:
-                    y_list = fx(y_list)
+                    if run is not None:
+                        state.run_stages(*run)
+                        run = None
+                    state.set_host(fx(state.host()))
+        if run is not None:
+            state.run_stages(*run)
+        y_list = state.host()
         if self.parallel:
             # weighting factor of input signal in the range of (0.0 ~ 0.5)
             weight_in = self.parallel_weight_factor if self.parallel_weight_factor else np.random.rand() / 2.
@@ -324,10 +472,9 @@ class AugmentationChain:
         """Current parameter values of the chain's processors as a [batch, 20] float32 tensor (host)."""
         v = _NEUTRAL.copy()
         for fx, _, _ in self.fxs:
-            if isinstance(fx, Processor):
+            if isinstance(fx, Processor) and fx.STAGE:
                 pv = fx.param_vector()
-                sl = {FX_EQ: slice(0, 13), FX_COMP: slice(13, 17), FX_IMAGER: slice(17, 18), FX_GAIN: slice(18, 20)}[fx.STAGE]
-                v[sl] = pv[sl]
+                v[_STAGE_SLICE[fx.STAGE]] = pv[_STAGE_SLICE[fx.STAGE]]
         return torch.from_numpy(np.tile(v, (batch, 1)))
 
     def __repr__(self):

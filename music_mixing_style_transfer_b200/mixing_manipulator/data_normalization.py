@@ -1,0 +1,237 @@
+"""Audio effects chain normalisation on the GPU -- same surface as the reference's
+`mixing_manipulator/data_normalization.py` (class Audio_Effects_Normalizer :19-175).
+
+  normalize_audio(audio, src)             :77-85     the effects of `EFFECTS` in order
+  normalize_audio_per_effect(...)         :88-155    pad by FFT_SIZE zeros, skip below -40 dB peak, effect, crop
+    'loudness'  fx_utils.lufs_normalize (fx_utils.py:220-238): BS.1770 integrated loudness of the padded stem (the meter is
+                pyloudnorm's, a third-party package: K-weighting biquads -> 400 ms / 75 % gating blocks -> absolute and
+                relative gates), gain to the stem's target LUFS, then division by max(1, peak)
+    'imager'    normalize_imager (normalization_imager.py:22-81): mid/side balance to the stem's target, left/right balance
+                50-50, mid/side balance again; a Haas effect first when the stem is almost mono
+    'eq', 'compression': NOT on the GPU yet -> NotImplementedError (EQ matching = 65,536-point STFT average -> firwin2 ->
+                filtfilt, utils_data_normalization.py:65-107; compression matching = a data-dependent search over aubio onsets,
+                :357-429, which SURVEY.md leaves on the CPU)
+
+Device work per effect: one reduction pass (mst_stereo_stats, and for loudness mst_biquad_cascade + mst_block_energy), a few
+dozen float64 operations on the host with the reference's own formulas, one 2x2 mix pass (mst_stereo_mix).  The three
+process_balance steps of the imager collapse into ONE 2x2 matrix: every step is linear in (L, R), so the energies each step
+needs follow from (sum L^2, sum R^2, sum LR) of the input.  `audio` may be a float32 CUDA tensor [2, T] (the engine's stems)
+or a numpy array [n, 2] / [n, 1] (the reference's call, :77); the result has the same kind.  No CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _cabi
+
+FFT_SIZE = 2 ** 16
+_G = np.array([1.0, 1.0, 1.0, 1.41, 1.41])     # BS.1770 channel weights
+
+
+def _rbj(kind, G, Q, fc, rate):
+    A = 10 ** (G / 40.0)
+    w0 = 2.0 * np.pi * (fc / rate)
+    alpha, c = np.sin(w0) / (2.0 * Q), np.cos(w0)
+    if kind == 'high_shelf':
+        s = 2 * np.sqrt(A) * alpha
+        b = [A * ((A + 1) + (A - 1) * c + s), -2 * A * ((A - 1) + (A + 1) * c), A * ((A + 1) + (A - 1) * c - s)]
+        a = [(A + 1) - (A - 1) * c + s, 2 * ((A - 1) - (A + 1) * c), (A + 1) - (A - 1) * c - s]
+    else:   # high_pass
+        b = [(1 + c) / 2, -(1 + c), (1 + c) / 2]
+        a = [1 + alpha, -2 * c, 1 - alpha]
+    return [b[0] / a[0], b[1] / a[0], b[2] / a[0], a[1] / a[0], a[2] / a[0]]
+
+
+def _stream():
+    return _cabi.current_stream()
+
+
+def stereo_stats(x):
+    """x float32 CUDA [B, 2, L] -> float64 numpy [B, 4] = (sum L^2, sum R^2, sum LR, max |x|)."""
+    B, _, L = x.shape
+    out = torch.empty(B, 4, dtype=torch.float64, device=x.device)
+    _cabi.check(_cabi.lib().mst_stereo_stats(_cabi.ptr(x), B, L, out.data_ptr(), _stream()), "stereo_stats")
+    return out.cpu().numpy()
+
+
+def stereo_mix(x, matrices, out=None):
+    """y = M x per frame; x float32 CUDA [B, 2, L], matrices [B, 4] = (m0, m1, m2, m3) (numpy or tensor)."""
+    B, _, L = x.shape
+    m = torch.as_tensor(np.asarray(matrices, dtype=np.float32).reshape(B, 4)).to(x.device) \
+        if not isinstance(matrices, torch.Tensor) else matrices.to(device=x.device, dtype=torch.float32).contiguous()
+    y = torch.empty_like(x) if out is None else out
+    _cabi.check(_cabi.lib().mst_stereo_mix(_cabi.ptr(x), _cabi.ptr(m), _cabi.ptr(y), B, L, _stream()), "stereo_mix")
+    return y
+
+
+def haas(x, delay, feedback, channel):
+    """haas_process (common_audioeffects.py:767-787) on x float32 CUDA [B, 2, L]; per-segment delay (samples, may be negative:
+    np.roll wraps), feedback and wet channel (0 = left, 1 = right)."""
+    B, _, L = x.shape
+    dev = x.device
+    d = torch.as_tensor(np.asarray(delay, dtype=np.int32).reshape(B)).to(dev)
+    f = torch.as_tensor(np.asarray(feedback, dtype=np.float32).reshape(B)).to(dev)
+    c = torch.as_tensor(np.asarray(channel, dtype=np.int32).reshape(B)).to(dev)
+    y = torch.empty_like(x)
+    _cabi.check(_cabi.lib().mst_haas(_cabi.ptr(x), _cabi.ptr(y), B, L, d.data_ptr(), _cabi.ptr(f), c.data_ptr(), _stream()), "haas")
+    return y
+
+
+def gating_block_bounds(num_samples, rate=44100, block_size=0.400, overlap=0.75):
+    """Sample bounds of the loudness meter's gating blocks, in the float arithmetic of the meter the reference uses."""
+    T_g, step = block_size, 1.0 - overlap
+    num_blocks = int(np.round(((num_samples / rate - T_g) / (T_g * step))) + 1)
+    j = range(max(num_blocks, 0))
+    return (np.array([int(T_g * (jj * step) * rate) for jj in j], dtype=np.int64),
+            np.array([int(T_g * (jj * step + 1) * rate) for jj in j], dtype=np.int64))
+
+
+def gated_loudness(z_sums, rate=44100, block_size=0.400):
+    """[channels, blocks] block sums of squares of the K-weighted signal -> integrated loudness in LUFS (BS.1770-4: absolute
+    gate -70 LUFS, relative gate 10 LU below the mean of the blocks that passed it)."""
+    z = np.asarray(z_sums, dtype=np.float64) / (block_size * rate)
+    g = _G[:z.shape[0], None]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        l = -0.691 + 10.0 * np.log10(np.sum(g * z, axis=0))
+        keep = l >= -70.0
+        gamma_r = -0.691 + 10.0 * np.log10(np.sum(g[:, 0] * z[:, keep].mean(axis=1))) - 10.0 if keep.any() else np.nan
+        keep = (l > gamma_r) & (l > -70.0)
+        z_avg = np.nan_to_num(z[:, keep].mean(axis=1)) if keep.any() else np.zeros(z.shape[0])
+        return float(-0.691 + 10.0 * np.log10(np.sum(g[:, 0] * z_avg)))
+
+
+def integrated_loudness(x, rate=44100):
+    """x float32 CUDA [2, T] -> LUFS of (x + 1e-10), as fx_utils.lufs_normalize measures it (fx_utils.py:224)."""
+    lib = _cabi.lib()
+    T = x.shape[-1]
+    xe = (x + 1e-10).unsqueeze(0).contiguous()
+    coef = torch.tensor([[_rbj('high_shelf', 4.0, 1 / np.sqrt(2), 1500.0, rate), _rbj('high_pass', 0.0, 0.5, 38.0, rate)]],
+                        dtype=torch.float64, device=x.device)
+    ws = torch.empty(max(lib.mst_fx_workspace_bytes(1, T), 4096), dtype=torch.uint8, device=x.device)
+    y = torch.empty_like(xe)
+    _cabi.check(lib.mst_biquad_cascade(_cabi.ptr(xe), coef.data_ptr(), 2, _cabi.ptr(y), 1, T, _cabi.ptr(ws), ws.numel(),
+                                       _stream()), "biquad_cascade")
+    lo, hi = gating_block_bounds(T, rate)
+    if len(lo) == 0:
+        return float('-inf')
+    lo_d, hi_d = torch.from_numpy(lo).to(x.device), torch.from_numpy(hi).to(x.device)
+    z = torch.empty(2, len(lo), dtype=torch.float64, device=x.device)
+    _cabi.check(lib.mst_block_energy(_cabi.ptr(y), 2, T, lo_d.data_ptr(), hi_d.data_ptr(), len(lo), z.data_ptr(), _stream()),
+                "block_energy")
+    return gated_loudness(z.cpu().numpy(), rate)
+
+
+def lufs_normalize(x, sr, lufs):
+    """fx_utils.lufs_normalize (fx_utils.py:220-238) on x float32 CUDA [2, T]: gain to `lufs`, then / max(1, 1e-6 + peak)."""
+    loudness = integrated_loudness(x, sr)
+    gain = float(np.power(10.0, (float(np.asarray(lufs).reshape(-1)[0]) - loudness) / 20.0))
+    peak = gain * float(stereo_stats(x.unsqueeze(0))[0, 3])
+    k = gain / max(1.0, 1e-6 + peak)
+    return stereo_mix(x.unsqueeze(0), [[k, 0.0, 0.0, k]])[0]
+
+
+def _balance_gains(e1, e2, tgt_e1_bal, eps):
+    """process_balance (normalization_imager.py:84-99) on energies: gains for the two signals."""
+    total = e1 + e2
+    g1 = np.sqrt(tgt_e1_bal * total / (e1 + eps))
+    g2 = np.sqrt((total - e1 * g1 ** 2) / (e2 + 1e-3))
+    return g1, g2
+
+
+def imager_matrix(ll, rr, lr, target_side_mid_bal, eps=1e-4):
+    """The three balance steps of normalize_imager (normalization_imager.py:54-76) as ONE 2x2 matrix on (L, R), from the input's
+    (sum L^2, sum R^2, sum LR).  Energy of a linear combination a L + b R = a^2 ll + 2 a b lr + b^2 rr."""
+    def energy(row):
+        return row[0] ** 2 * ll + 2 * row[0] * row[1] * lr + row[1] ** 2 * rr
+    to_ms = np.array([[1.0, 1.0], [1.0, -1.0]])
+    to_lr = np.array([[0.5, 0.5], [0.5, -0.5]])
+    M = np.eye(2)
+    for basis, back, bal in ((to_ms, to_lr, float(target_side_mid_bal)), (np.eye(2), np.eye(2), 0.5), (to_ms, to_lr, float(target_side_mid_bal))):
+        A = basis @ M                                   # the two signals this step balances, as rows over (L, R)
+        g1, g2 = _balance_gains(energy(A[0]), energy(A[1]), bal, eps)
+        M = back @ (np.diag([g1, g2]) @ A)
+    return M
+
+
+class Audio_Effects_Normalizer:
+    def __init__(self, precomputed_feature_path, STEMS=['drums', 'bass', 'other', 'vocals'],
+                 EFFECTS=['eq', 'compression', 'imager', 'loudness']):
+        self.STEMS = STEMS          # Stems to be normalized
+        self.EFFECTS = EFFECTS      # Effects to be normalized, order matters
+        unsupported = [e for e in EFFECTS if e not in ('loudness', 'imager')]
+        if unsupported:
+            raise NotImplementedError(
+                f"Audio_Effects_Normalizer (B200 engine): effects {unsupported} are not on the GPU yet -- 'loudness' and 'imager' are "
+                "(SURVEY.md 8f-2).  Pass normalization_order with those only, or --normalize_input False")
+        # Audio settings
+        self.SR = 44100
+        self.SUBTYPE = 'PCM_16'
+        # General Settings
+        self.FFT_SIZE = FFT_SIZE
+        self.HOP_LENGTH = self.FFT_SIZE // 4
+        # Loudness
+        self.NTAPS = 1001
+        self.LUFS = -30
+        self.MIN_DB = -40           # Min amplitude to apply the effects
+        # Load Pre-computed Audio Effects Features
+        if isinstance(precomputed_feature_path, dict):
+            self.features_mean = precomputed_feature_path
+        else:
+            self.features_mean = np.load(precomputed_feature_path, allow_pickle='TRUE')[()]
+        self.haas_rng = np.random.RandomState()
+
+    # normalize current audio input with the order of designed audio FX
+    def normalize_audio(self, audio, src):
+        assert src in self.STEMS
+        as_numpy = not isinstance(audio, torch.Tensor)
+        if as_numpy:
+            if not torch.cuda.is_available():
+                raise RuntimeError("Audio_Effects_Normalizer (B200 engine): no CUDA device; there is no CPU fallback")
+            a = np.asarray(audio)
+            assert len(a.shape) == 2    # Always expects two dimensions
+            if a.shape[1] == 1:         # Converts mono to stereo with repeated channels
+                a = np.repeat(a, 2, axis=-1)
+            x = torch.from_numpy(np.ascontiguousarray(a.T, dtype=np.float32)).cuda()
+        else:
+            x = _cabi.require_cuda_f32(audio, "normalizer input")
+        for cur_effect in self.EFFECTS:
+            x = self.normalize_audio_per_effect(x, src=src, effect=cur_effect)
+        return np.ascontiguousarray(x.cpu().numpy().T) if as_numpy else x
+
+    # normalize current audio input with current targeted audio FX; audio: float32 CUDA [2, T]
+    def normalize_audio_per_effect(self, audio, src, effect):
+        T = audio.shape[-1]
+        track = torch.nn.functional.pad(audio, (self.FFT_SIZE, self.FFT_SIZE))
+        peak = float(stereo_stats(track.unsqueeze(0))[0, 3])
+        with np.errstate(divide='ignore'):
+            max_db = 20 * np.log10(peak + 1e-30)
+        if max_db > self.MIN_DB:
+            if effect == 'loudness':
+                track = lufs_normalize(track, self.SR, self.features_mean[effect][src])
+            elif effect == 'imager':
+                # threshold of applying Haas effects
+                mono_threshold = 0.99 if src == 'bass' else 0.975
+                track = self.normalize_imager(track, self.features_mean[effect][src], mono_threshold)
+            else:
+                raise NotImplementedError(effect)
+        return track[:, self.FFT_SIZE:self.FFT_SIZE + T].contiguous()
+
+    def normalize_imager(self, data, target_side_mid_bal, mono_threshold, eps=1e-4):
+        """normalization_imager.normalize_imager on data float32 CUDA [2, T]."""
+        ll, rr, lr, _ = stereo_stats(data.unsqueeze(0))[0]
+        mid_e, side_e = ll + rr + 2 * lr, max(ll + rr - 2 * lr, 0.0)
+        # apply haas effect to almost-mono signal (:39-42); the reference draws delay / feedback / channel from its
+        # Processor.randomize() (third-party distributions): uniform over the documented ranges here
+        if mid_e / (mid_e + side_e) > mono_threshold:
+            delay = int(self.haas_rng.randint(int(-0.040 * self.SR), int(0.040 * self.SR) + 1))
+            feedback = float(self.haas_rng.uniform(0.33, 0.66))
+            n = 2.0 * data.shape[-1]
+            data = haas(data.unsqueeze(0), [delay], [feedback], [int(self.haas_rng.randint(2))])[0]
+            hl, hr, hlr, _ = stereo_stats(data.unsqueeze(0))[0]
+            # the chain applies it with RMS re-normalisation (AugmentationChain fxs=[(Haas, 1, True)], common_audioeffects.py:142-145)
+            k = float(np.sqrt(((ll + rr) / n) / np.maximum(1e-7, (hl + hr) / n)))
+            data = stereo_mix(data.unsqueeze(0), [[k, 0.0, 0.0, k]])[0]
+            ll, rr, lr = hl * k * k, hr * k * k, hlr * k * k
+        M = imager_matrix(ll, rr, lr, target_side_mid_bal, eps)
+        return stereo_mix(data.unsqueeze(0), [[M[0, 0], M[0, 1], M[1, 0], M[1, 1]]])[0]

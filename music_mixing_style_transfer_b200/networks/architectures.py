@@ -90,6 +90,16 @@ class FXencoder(nn.Module):
             self._packed, self._packed_sig = packed, sig
         return self._packed
 
+    def embed_mean(self, input, scale=None):
+        """forward(input) reduced over the batch in the same stream: `scale * sum_b emb[b]`, scale = 1/B by default -- the mean
+        embedding of a batch of reference segments (inference/style_transfer.py:152-153); scale=1.0 gives a partial sum."""
+        emb = self.forward(input)
+        out = torch.empty(emb.shape[1], dtype=torch.float32, device=emb.device)
+        _cabi.check(_cabi.lib().mst_rows_reduce(_cabi.ptr(emb), emb.shape[0], emb.shape[1],
+                                                float(1.0 / emb.shape[0] if scale is None else scale), _cabi.ptr(out),
+                                                _cabi.current_stream()), "rows_reduce")
+        return out
+
     # network forward operation
     def forward(self, input):
         x = _cabi.require_cuda_f32(input, "FXencoder input")

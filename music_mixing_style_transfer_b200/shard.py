@@ -76,21 +76,79 @@ def allgather_segments(local: torch.Tensor, counts: List[int], group=None) -> to
     return torch.cat([out[r * mx:r * mx + counts[r]] for r in range(ws)], dim=0)
 
 
+def _embed(encoder, batch, mean=True):
+    """Mean (or sum) of the batch's embeddings: the encoder's fused reduction when it has one (FXencoder.embed_mean)."""
+    if hasattr(encoder, "embed_mean"):
+        return encoder.embed_mean(batch, None if mean else 1.0)
+    emb = encoder(batch)
+    return emb.mean(dim=0) if mean else emb.sum(dim=0)
+
+
+def mean_embedding(encoder, reference_batch: Optional[torch.Tensor], n_reference: int, device, cond_dim: int = 2048,
+                   shard_reference: bool = False, group=None) -> torch.Tensor:
+    """Mean FXencoder embedding of the reference batch on every rank (inference/style_transfer.py:144-153).
+      shard_reference = False: rank 0 holds the batch, encodes it and the [cond_dim] mean is BROADCAST (the exchange
+                               BASELINE's north_star names); the other ranks wait for it.
+      shard_reference = True:  every rank holds the batch (or at least its own contiguous slice of it, passed as the slice),
+                               encodes n_reference / world segments and the partial sums are ALL-REDUCED (8 KiB) -- no rank
+                               idles behind rank 0's encoder pass."""
+    rank, ws = world(group)
+    if ws == 1:
+        return _embed(encoder, reference_batch)
+    if not shard_reference:
+        emb = _embed(encoder, reference_batch) if rank == 0 else None
+        return broadcast_embedding(emb, (cond_dim,), device, src=0, group=group)
+    lo, hi = shard_bounds(n_reference, ws, rank)
+    part = torch.zeros(cond_dim, dtype=torch.float32, device=device)
+    if hi > lo:
+        mine = reference_batch if reference_batch.shape[0] == hi - lo else reference_batch[lo:hi]
+        part = _embed(encoder, mine.contiguous(), mean=False)
+    dist.all_reduce(part, group=group)
+    return part / float(n_reference)
+
+
+def convert_and_gather(converter, input_shard: torch.Tensor, cond: torch.Tensor, total_segments: int, gather: bool = True,
+                       chunks: int = 1, group=None) -> torch.Tensor:
+    """TCN over this rank's shard and the all-gather of the output segments, overlapped: the shard is converted in `chunks`
+    sub-batches and the NCCL all-gather of sub-batch k runs (on NCCL's own stream) while sub-batch k + 1 is being converted,
+    so only the last sub-batch's gather is exposed.  cond: [1, cond_dim] or one row per local segment.
+    Returns [total_segments, 2, L] in rank order (or the local shard when gather is False / single rank)."""
+    rank, ws = world(group)
+    n_local = input_shard.shape[0]
+    counts = shard_counts(total_segments, ws)
+    even = all(c == counts[0] for c in counts)
+    overlapped = gather and ws > 1 and chunks > 1 and even and n_local % chunks == 0 and dist.get_backend(group) == "nccl"
+    if not overlapped:
+        out = converter(input_shard, cond)
+        return allgather_segments(out, counts, group=group) if (gather and ws > 1) else out
+    sb = n_local // chunks
+    tail = tuple(input_shard.shape[1:-1]) + (input_shard.shape[-1],)
+    gathered = input_shard.new_empty((chunks, ws, sb) + tail)          # [k][rank][row of sub-batch k]
+    works, keep = [], []
+    for k in range(chunks):
+        c = cond if cond.shape[0] == 1 else cond[k * sb:(k + 1) * sb].contiguous()
+        y = converter(input_shard[k * sb:(k + 1) * sb].contiguous(), c)
+        keep.append(y)                                   # alive until its gather has completed
+        works.append(dist.all_gather_into_tensor(gathered[k].view((ws * sb,) + tail), y, group=group, async_op=True))
+    for w in works:
+        w.wait()
+    # rank-major order: out[r * n_local + k * sb + i] = gathered[k][r][i]   (one device copy of the gathered batch)
+    return gathered.permute(1, 0, 2, *range(3, gathered.dim())).reshape((total_segments,) + tail)
+
+
 def sharded_style_transfer(encoder, converter, reference_batch: Optional[torch.Tensor], input_shard: torch.Tensor,
-                           total_segments: int, cond_dim: int = 2048, gather: bool = True, group=None):
+                           total_segments: int, cond_dim: int = 2048, gather: bool = True, group=None,
+                           shard_reference: bool = False, n_reference: Optional[int] = None, gather_chunks: int = 1):
     """One sharded forward step.
-      reference_batch: [B_ref, 2, L_ref] on rank 0 (ignored elsewhere)  -> encoder -> mean embedding -> broadcast
+      reference_batch: [B_ref, 2, L_ref] on rank 0 (ignored elsewhere)  -> encoder -> mean embedding -> broadcast;
+                       with shard_reference=True every rank passes the batch (or its slice) and the sums are all-reduced
       input_shard:     this rank's contiguous [B_local, 2, L] slice of the `total_segments` input segments
     Returns (embedding [cond_dim], output) where output is the gathered [total_segments, 2, L] (gather=True) or the
     local shard.  `encoder` / `converter` are callables with the FXencoder / TCNModel forward signatures."""
-    rank, ws = world(group)
-    emb = None
-    if rank == 0:
-        emb = encoder(reference_batch).mean(dim=0)       # inference/style_transfer.py:152-153
-    emb = broadcast_embedding(emb, (cond_dim,), input_shard.device, src=0, group=group)
-    out = converter(input_shard, emb.unsqueeze(0))       # :161 (cond broadcast over the batch)
-    if gather and ws > 1:
-        out = allgather_segments(out, shard_counts(total_segments, ws), group=group)
+    if n_reference is None:
+        n_reference = 0 if reference_batch is None else int(reference_batch.shape[0])
+    emb = mean_embedding(encoder, reference_batch, n_reference, input_shard.device, cond_dim, shard_reference, group)
+    out = convert_and_gather(converter, input_shard, emb.unsqueeze(0), total_segments, gather, gather_chunks, group)  # :161
     return emb, out
 
 
@@ -107,7 +165,7 @@ def interpolation_weights(total_segments: int, interpolate_segments: int, device
 
 def sharded_interpolation(encoder, converter, reference_a: Optional[torch.Tensor], reference_b: Optional[torch.Tensor],
                           input_shard: torch.Tensor, total_segments: int, weights: torch.Tensor, cond_dim: int = 2048,
-                          gather: bool = True, group=None):
+                          gather: bool = True, group=None, gather_chunks: int = 1):
     """Interpolation mode (inference/style_transfer.py:181-270) sharded over the ranks.
       reference_a / reference_b: [B_ref, 2, L_ref] on rank 0 -> two mean embeddings -> ONE broadcast of [2, cond_dim]
       input_shard: this rank's contiguous slice of the `total_segments` input segments
@@ -117,14 +175,13 @@ def sharded_interpolation(encoder, converter, reference_a: Optional[torch.Tensor
     rank, ws = world(group)
     embs = None
     if rank == 0:
-        embs = torch.stack([encoder(reference_a).mean(dim=0), encoder(reference_b).mean(dim=0)], dim=0)
+        embs = torch.stack([_embed(encoder, reference_a),
+                            _embed(encoder, reference_b)], dim=0)
     embs = broadcast_embedding(embs, (2, cond_dim), input_shard.device, src=0, group=group)
     lo, hi = shard_bounds(total_segments, ws, rank)
     if hi - lo != input_shard.shape[0]:
         raise RuntimeError(f"rank {rank}: input shard has {input_shard.shape[0]} segments, expected {hi - lo}")
     w = weights[lo:hi].to(device=input_shard.device, dtype=torch.float32).unsqueeze(1)
     cond = w * embs[0].unsqueeze(0) + (1.0 - w) * embs[1].unsqueeze(0)
-    out = converter(input_shard, cond)
-    if gather and ws > 1:
-        out = allgather_segments(out, shard_counts(total_segments, ws), group=group)
+    out = convert_and_gather(converter, input_shard, cond, total_segments, gather, gather_chunks, group)
     return embs, out

@@ -1,0 +1,186 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU (numpy / scipy float64) restatement of the input FX normaliser's loudness and imager
+effects.  Paths relative to /root/reference/mixing_style_transfer/mixing_manipulator/.
+
+  normalize_audio / normalize_audio_per_effect   data_normalization.py:77-155   (pad by FFT_SIZE, -40 dB gate, crop)
+  lufs_normalize                                  fx_utils.py:220-238
+  normalize_imager / process_balance              normalization_imager.py:22-118 (Haas branch excluded: it draws random
+                                                  parameters through pymixconsole's Processor.randomize)
+  Meter / loudness_gain_apply                     pyloudnorm==0.1.0 (requirements.txt:9), third-party, NOT in the reference
+                                                  tree: restated from the published BS.1770-4 algorithm -> PARITY UNPINNED
+
+Pinned where the reference's own code can run here: tests/test_oracle_pinned.py imports the reference's fx_utils,
+normalization_imager and data_normalization on the shims of oracle/shims/ (whose `pyloudnorm` is THIS file's Meter) and
+compares lufs_normalize / normalize_imager / Audio_Effects_Normalizer.normalize_audio_per_effect with the functions below.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+"""
+import numpy as np
+import scipy.signal
+
+FFT_SIZE = 2 ** 16          # data_normalization.py:31
+MIN_DB = -40                # :37
+SR = 44100
+
+
+def rbj_high_shelf(G, Q, fc, rate):
+    A = 10 ** (G / 40.0)
+    w0 = 2.0 * np.pi * (fc / rate)
+    alpha = np.sin(w0) / (2.0 * Q)
+    c, s = np.cos(w0), 2 * np.sqrt(A) * alpha
+    b = np.array([A * ((A + 1) + (A - 1) * c + s), -2 * A * ((A - 1) + (A + 1) * c), A * ((A + 1) + (A - 1) * c - s)])
+    a = np.array([(A + 1) - (A - 1) * c + s, 2 * ((A - 1) - (A + 1) * c), (A + 1) - (A - 1) * c - s])
+    return b / a[0], a / a[0]
+
+
+def rbj_high_pass(Q, fc, rate):
+    w0 = 2.0 * np.pi * (fc / rate)
+    alpha = np.sin(w0) / (2.0 * Q)
+    c = np.cos(w0)
+    b = np.array([(1 + c) / 2, -(1 + c), (1 + c) / 2])
+    a = np.array([1 + alpha, -2 * c, 1 - alpha])
+    return b / a[0], a / a[0]
+
+
+def k_weighting(rate=SR):
+    """The two K-weighting stages of pyloudnorm's default meter, in application order."""
+    return [rbj_high_shelf(4.0, 1 / np.sqrt(2), 1500.0, rate), rbj_high_pass(0.5, 38.0, rate)]
+
+
+def gating_block_bounds(num_samples, rate=SR, block_size=0.400, overlap=0.75):
+    """(lower, upper) sample bounds of every gating block, with pyloudnorm's float arithmetic."""
+    T_g, step = block_size, 1.0 - overlap
+    T = num_samples / rate
+    num_blocks = int(np.round(((T - T_g) / (T_g * step))) + 1)
+    j = np.arange(0, max(num_blocks, 0))
+    lo = np.array([int(T_g * (jj * step) * rate) for jj in j], dtype=np.int64)
+    hi = np.array([int(T_g * (jj * step + 1) * rate) for jj in j], dtype=np.int64)
+    return lo, hi
+
+
+def gated_loudness(z, block_size=0.400, rate=SR):
+    """z[channel][block] = SUM of squares of the K-weighted signal per gating block -> integrated loudness (LUFS)."""
+    G = [1.0, 1.0, 1.0, 1.41, 1.41]
+    z = np.asarray(z, dtype=np.float64) * (1.0 / (block_size * rate))
+    n_ch, n_blocks = z.shape
+    with np.errstate(divide='ignore', invalid='ignore'):
+        l = np.array([-0.691 + 10.0 * np.log10(np.sum([G[i] * z[i, j] for i in range(n_ch)])) for j in range(n_blocks)])
+        J_g = [j for j in range(n_blocks) if l[j] >= -70.0]
+        z_avg = [np.mean([z[i, j] for j in J_g]) for i in range(n_ch)]
+        gamma_r = -0.691 + 10.0 * np.log10(np.sum([G[i] * z_avg[i] for i in range(n_ch)])) - 10.0
+        J_g = [j for j in range(n_blocks) if (l[j] > gamma_r and l[j] > -70.0)]
+        z_avg = np.nan_to_num(np.array([np.mean([z[i, j] for j in J_g]) for i in range(n_ch)]))
+        return float(-0.691 + 10.0 * np.log10(np.sum([G[i] * z_avg[i] for i in range(n_ch)])))
+
+
+class Meter:
+    """pyloudnorm.Meter(rate) with the default K-weighting filters and 400 ms blocks."""
+
+    def __init__(self, rate, filter_class="K-weighting", block_size=0.400):
+        self.rate, self.block_size = rate, block_size
+        self._filters = k_weighting(rate)
+
+    def integrated_loudness(self, data):
+        x = np.array(data, copy=True)
+        if x.ndim == 1:
+            x = x.reshape(-1, 1)
+        for b, a in self._filters:
+            for ch in range(x.shape[1]):
+                x[:, ch] = scipy.signal.lfilter(b, a, x[:, ch])          # stored back in the data's dtype
+        lo, hi = gating_block_bounds(x.shape[0], self.rate, self.block_size)
+        z = np.array([[np.sum(np.square(x[l:u, ch])) for l, u in zip(lo, hi)] for ch in range(x.shape[1])], dtype=np.float64)
+        return gated_loudness(z.reshape(x.shape[1], len(lo)), self.block_size, self.rate)
+
+
+def loudness_gain_apply(data, input_loudness, target_loudness):
+    """pyloudnorm.normalize.loudness: gain = 10^((target - input) / 20) as a numpy float64 scalar -> float64 output."""
+    gain = np.power(10.0, (target_loudness - input_loudness) / 20.0)
+    return gain * data
+
+
+def lufs_normalize(x, sr, lufs):
+    """fx_utils.py:220-238 (log=False)."""
+    meter = Meter(sr)
+    loudness = meter.integrated_loudness(x + 1e-10)
+    y = loudness_gain_apply(x, loudness, lufs)
+    y = y / np.maximum(1.0, 1e-6 + np.max(np.abs(y)))
+    return y
+
+
+def process_balance(d1, d2, tgt_e1_bal=0.5, eps=1e-04):
+    """normalization_imager.py:84-99."""
+    e1, e2 = np.sum(d1 ** 2), np.sum(d2 ** 2)
+    total = e1 + e2
+    g1 = np.sqrt(tgt_e1_bal * total / (e1 + eps))
+    left = total - e1 * (g1 ** 2)
+    g2 = np.sqrt(left / (e2 + 1e-3))
+    return d1 * g1, d2 * g2
+
+
+def imager_is_almost_mono(data, mono_threshold):
+    mid, side = data[:, 0] + data[:, 1], data[:, 0] - data[:, 1]
+    mid_e, side_e = np.sum(mid ** 2), np.sum(side ** 2)
+    return bool(mid_e / (mid_e + side_e) > mono_threshold)
+
+
+def normalize_imager(data, target_side_mid_bal=0.9, mono_threshold=0.95, eps=1e-04):
+    """normalization_imager.py:22-81 for inputs that are NOT almost mono (no Haas)."""
+    if imager_is_almost_mono(data, mono_threshold):
+        raise ValueError("almost-mono input: the reference applies a randomised Haas effect here (no deterministic oracle)")
+    mid, side = data[:, 0] + data[:, 1], data[:, 0] - data[:, 1]
+    mid, side = process_balance(mid, side, target_side_mid_bal, eps)
+    left, right = (mid + side) / 2, (mid - side) / 2
+    left, right = process_balance(left, right, 0.5, eps)
+    mid, side = left + right, left - right
+    mid, side = process_balance(mid, side, target_side_mid_bal, eps)
+    return np.stack([(mid + side) / 2, (mid - side) / 2], 1)
+
+
+def normalize_audio_per_effect(audio, effect, feature, src="drums"):
+    """data_normalization.py:88-155 for effect in ('loudness', 'imager').  audio: [n, 2]; feature = features_mean[effect][src]."""
+    audio = audio.astype(np.float32)
+    track = np.pad(audio, ((FFT_SIZE, FFT_SIZE), (0, 0)), mode='constant')
+    out = track.copy()
+    with np.errstate(divide='ignore'):
+        max_db = 20.0 * np.log10(np.max(np.abs(out)) + 1e-30)       # amp_to_db, utils_data_normalization.py:35-36
+    if max_db > MIN_DB:
+        if effect == 'loudness':
+            out = lufs_normalize(out, SR, feature)
+        elif effect == 'imager':
+            np.copyto(out, normalize_imager(out, target_side_mid_bal=feature,
+                                            mono_threshold=0.99 if src == 'bass' else 0.975))
+        else:
+            raise NotImplementedError(effect)
+    return out[FFT_SIZE:FFT_SIZE + audio.shape[0]]
+
+
+def normalize_audio(audio, effects, features, src="drums"):
+    """data_normalization.py:77-85."""
+    y = audio
+    for e in effects:
+        y = normalize_audio_per_effect(y, e, features[e][src], src)
+    return y
+
+
+def haas_process(x, delay, feedback, wet_channel):
+    """common_audioeffects.py:767-787.  x: [n, 2]."""
+    y = np.copy(x)
+    if wet_channel == 'left':
+        y[:, 0] += feedback * np.roll(x[:, 0], delay)
+    elif wet_channel == 'right':
+        y[:, 1] += feedback * np.roll(x[:, 1], delay)
+    return y
+
+
+def pan_gains(pan, pan_law='-4.5dB'):
+    """Panner._calculate_pan_coefficents (common_audioeffects.py:877-908), float32 like `self.dtype`."""
+    g = np.zeros(2, dtype=np.float32)
+    theta = pan * (np.pi / 2)
+    if pan_law == 'linear':
+        g[0], g[1] = ((np.pi / 2) - theta) * (2 / np.pi), theta * (2 / np.pi)
+    elif pan_law == 'constant_power':
+        g[0], g[1] = np.cos(theta), np.sin(theta)
+    elif pan_law == '-4.5dB':
+        g[0] = np.sqrt(((np.pi / 2) - theta) * (2 / np.pi) * np.cos(theta))
+        g[1] = np.sqrt(theta * (2 / np.pi) * np.sin(theta))
+    else:
+        raise ValueError(f'Invalid pan_law {pan_law}.')
+    return g

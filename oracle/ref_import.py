@@ -91,3 +91,22 @@ def import_reference_loader_utils():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def import_reference_normalizer():
+    """The reference's mixing_manipulator modules behind the input FX normaliser: (data_normalization, fx_utils,
+    normalization_imager).  librosa / matplotlib / aubio / soundfile are empty stand-ins (oracle/shims/); `pyloudnorm` resolves
+    to the RESTATED meter of oracle/norm_oracle.py, so what this pins is the reference's own arithmetic around it
+    (lufs_normalize, normalize_imager, Audio_Effects_Normalizer.normalize_audio_per_effect)."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    import importlib
+    import types
+
+    _prepend(os.path.join(REFERENCE_ROOT, "mixing_style_transfer", "mixing_manipulator"))
+    _prepend(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))      # `oracle` package for the pyloudnorm shim
+    _prepend(_SHIMS)
+    if "soundfile" not in sys.modules:
+        sys.modules["soundfile"] = types.ModuleType("soundfile")
+    return (importlib.import_module("data_normalization"), importlib.import_module("fx_utils"),
+            importlib.import_module("normalization_imager"))

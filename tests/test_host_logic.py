@@ -157,6 +157,12 @@ def _worker(rank, ws, port, n_total, q):
         emb, out = shard.sharded_style_transfer(enc, conv, ref if rank == 0 else None, full[lo:hi], n_total, cond_dim=16)
         expect_emb = enc(ref).mean(dim=0)
         ok = torch.allclose(emb, expect_emb) and torch.equal(out, full * 2.0 + expect_emb[:1])
+        # sharded reference batch: every rank encodes its slice, one all-reduce of the partial sums
+        rlo, rhi = shard.shard_bounds(ref.shape[0], ws, rank)
+        for batch in (ref, ref[rlo:rhi]):                        # the whole batch, or just this rank's slice of it
+            emb2, out2 = shard.sharded_style_transfer(enc, conv, batch, full[lo:hi], n_total, cond_dim=16,
+                                                      shard_reference=True, n_reference=ref.shape[0], gather_chunks=2)
+            ok = ok and torch.allclose(emb2, expect_emb, atol=1e-6) and torch.allclose(out2, full * 2.0 + expect_emb[:1], atol=1e-6)
         q.put((rank, bool(ok), tuple(out.shape)))
     finally:
         dist.destroy_process_group()

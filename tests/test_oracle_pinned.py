@@ -169,3 +169,26 @@ def test_configs_yaml_equals_reference():
                                             "music_mixing_style_transfer_b200", "inference", "configs.yaml")))
     ref = yaml.full_load(open(os.path.join(ref_import.REFERENCE_ROOT, "inference", "configs.yaml")))
     assert ours == ref
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree not present (GPU box)")
+def test_normalizer_oracle_equals_reference_code(tmp_path):
+    """oracle/norm_oracle.py against the reference's own lufs_normalize, normalize_imager and
+    Audio_Effects_Normalizer.normalize_audio (loudness, imager) on a real stem window.  The BS.1770 meter underneath is the
+    restated pyloudnorm (third-party, absent) on BOTH sides: that part stays unpinned."""
+    from oracle import norm_oracle as N
+    dn, fx_utils, nimg = ref_import.import_reference_normalizer()
+    g = fixtures.load_golden("real_audio.npz")
+    x = (g["x_drums"].astype(np.float64) / 32768.0).astype(np.float32)[:50000]          # [n, 2]
+    x[:, 1] = 0.3 * x[:, 1] + 0.6 * np.roll(x[:, 0], 4410)                             # wide (no Haas branch), unbalanced
+    ref = fx_utils.lufs_normalize(x.copy(), 44100, np.array([-28.9]), log=False)
+    assert np.abs(N.lufs_normalize(x.copy(), 44100, np.array([-28.9])) - ref).max() <= 1e-9
+    ref = nimg.normalize_imager(x.copy(), target_side_mid_bal=0.9447, mono_threshold=0.975, sr=44100)
+    assert np.abs(N.normalize_imager(x.copy(), 0.9447, 0.975) - ref).max() <= 1e-7
+    feats = {"loudness": {"drums": np.array([-28.9674596])}, "imager": {"drums": np.float32(0.94471526)}}
+    np.save(tmp_path / "feats.npy", feats, allow_pickle=True)
+    order = ['loudness', 'imager', 'loudness']
+    norm = dn.Audio_Effects_Normalizer(str(tmp_path / "feats.npy"), STEMS=['drums'], EFFECTS=order)
+    ref = norm.normalize_audio(x.copy(), src='drums')
+    got = N.normalize_audio(x.copy(), order, feats, src='drums')
+    assert ref.shape == got.shape and np.abs(got - ref).max() <= 1e-7
