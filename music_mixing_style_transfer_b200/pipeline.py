@@ -57,6 +57,13 @@ class StyleTransferPipeline:
         flags = []
         with torch.no_grad():
             _, out = shard.sharded_style_transfer(self.encoder, self._converter(flags), ref, x, self.total, **self.kw)
+        fired_dev = None
+        if flags:
+            # did any converter call of this step leave the f16f8 range?  Reduced on the compute stream now and copied out with
+            # the waveforms, so that collect() never waits on the compute stream (which already holds the next step)
+            fired_dev = (torch.cat(flags).view(torch.float32) > 0).any().to(torch.int32).reshape(1)
+            if self.world > 1:      # the repeat in collect() runs collectives: every rank must take the same branch
+                torch.distributed.all_reduce(fired_dev, op=torch.distributed.ReduceOp.MAX, group=self.kw["group"])
         slot["computed"] = torch.cuda.Event()
         slot["computed"].record(compute)
         n_local = x.shape[0]
@@ -67,9 +74,14 @@ class StyleTransferPipeline:
             host = self._buffer(slot, "out", mine, pinned=True)
             host.copy_(mine, non_blocking=True)
             mine.record_stream(self.copy_out)
+            fired_host = None
+            if fired_dev is not None:
+                fired_host = self._buffer(slot, "fired", fired_dev, pinned=True)
+                fired_host.copy_(fired_dev, non_blocking=True)
+                fired_dev.record_stream(self.copy_out)
             done = torch.cuda.Event()
             done.record(self.copy_out)
-        self.pending.append((host, done, out, flags, (ref, x, lo, n_local)))
+        self.pending.append((host, done, out, fired_host, (ref, x, lo, n_local)))
         self.n_submitted += 1
 
     def _converter(self, flags):
@@ -92,15 +104,9 @@ class StyleTransferPipeline:
     def collect(self):
         """Pinned host tensor with this rank's waveforms of the oldest submitted step (blocks until its copy-out is done).
         The buffer is reused by the step submitted `depth` submits later."""
-        host, done, _, flags, (ref, x, lo, n_local) = self.pending.popleft()
+        host, done, _, fired_host, (ref, x, lo, n_local) = self.pending.popleft()
         done.synchronize()
-        fired = False
-        if flags:
-            any_fired = (torch.cat(flags).view(torch.float32) > 0).any().to(torch.int32)
-            if self.world > 1:      # the repeat below runs collectives: every rank must take the same branch
-                torch.distributed.all_reduce(any_fired, op=torch.distributed.ReduceOp.MAX, group=self.kw["group"])
-            fired = bool(any_fired.item())
-        if fired:
+        if fired_host is not None and int(fired_host[0]) != 0:
             # an activation left the f16f8 operand range: repeat this step with fp32-range operands (its inputs are still in
             # their slot: at most depth - 1 later steps have been submitted)
             self.converter.precision = "bf16x3"

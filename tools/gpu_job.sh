@@ -4,7 +4,8 @@
 #   ablate           default build vs the MST_TCN_ABLATE side builds (build.py --variant), tools/tcn_time.py each
 #   tcntests         the TCN parity files only
 #   ab               tools/tcn_time.py for build/base (previous commit), the product library and $MST_AB_VARIANTS side builds
-#   bench [args]     python bench.py args
+#   nccl / benchn    tools/nccl_check.py / bench.py under torchrun with $MST_NPROC ranks (gpurun --gpus N)
+#   bench            python bench.py
 # Everything is written under gpurun_out/.
 set -u
 mkdir -p gpurun_out
@@ -19,6 +20,8 @@ case "$what" in
               lib=""; [ -n "$v" ] && lib=music_mixing_style_transfer_b200/build/$v/libmst_b200.so
               MST_DEV_LIB=$lib timeout 300 python tools/tcn_time.py f16f8 32 ${MST_AB_REPS:-4}
             done; } 2>&1 | grep -v Warning > gpurun_out/ab.log; cat gpurun_out/ab.log ;;
+  nccl)   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${MST_NPROC:-2} --master-addr 127.0.0.1 --master-port 29511 tools/nccl_check.py 2>&1 | grep -E "^rank|Error|error" | tail -20 > gpurun_out/nccl.log; cat gpurun_out/nccl.log ;;
+  benchn) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${MST_NPROC:-2} --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus ${MST_NPROC:-2} --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n${MST_NPROC:-2}.json 2> gpurun_out/bench_n.err; tail -c 2500 gpurun_out/bench_n${MST_NPROC:-2}.json; tail -3 gpurun_out/bench_n.err ;;
   bench)  timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json ;;
 esac
 done
