@@ -64,7 +64,9 @@ enc_conv_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                      const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_y,
                      const ConvUmmaArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET into the shared array (not integer pointer arithmetic): the compiler keeps the shared
+  // state space and emits LDS / STS instead of generic LD / ST for the epilogue's staging accesses
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;
   uint8_t* staging = smem + (size_t)kEncSlots * kEncSlotBytes;
   EncBarriers* bars = reinterpret_cast<EncBarriers*>(staging + kEncSlotBytes);

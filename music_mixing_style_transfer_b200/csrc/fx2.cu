@@ -32,13 +32,14 @@
 //
 // Layout: x, y fp32 [B][2][L]; params fp32 [B][20]; stats double [B][16] (workspace).
 #include "common.cuh"
+#include "f32x2.cuh"
 
 #include <cstdlib>
 
 namespace mst {
 namespace fx2 {
 
-typedef unsigned long long u64;
+using namespace ::mst::f2;   // packed float32 x 2 helpers: lo = left channel, hi = right channel
 
 constexpr int kThreads = 256;
 constexpr int kWarps = 8;
@@ -54,33 +55,6 @@ constexpr int kFxStats = 16;
 // stats slots (doubles per segment); 10..13 = final-pass matrix (out_L = m0 l + m1 r, out_R = m2 l + m3 r)
 enum { S_X2_0 = 0, S_X2_1, S_Y1_0, S_Y1_1, S_U2_0, S_U2_1, S_Y2_0, S_Y2_1, S_LR, S_ROUNDS, S_M0, S_M1, S_M2, S_M3 };
 
-// ---- packed float32 x 2 helpers (lo = left channel, hi = right channel) ----
-__device__ __forceinline__ u64 pk(float lo, float hi) {
-  u64 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ float lo_of(u64 v) {
-  float a, b;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-  return a;
-}
-__device__ __forceinline__ float hi_of(u64 v) {
-  float a, b;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-  return b;
-}
-__device__ __forceinline__ u64 dup(float v) { return pk(v, v); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
-  u64 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 __device__ __forceinline__ float lg2_approx(float x) {
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

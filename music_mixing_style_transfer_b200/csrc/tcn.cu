@@ -36,6 +36,7 @@
 #include <cuda_fp8.h>
 
 #include "common.cuh"
+#include "f32x2.cuh"
 #include "sm100_ptx.cuh"
 
 // Development-only ablation switches (tools/tcn_ablate.sh builds side libraries with -DMST_TCN_ABLATE=<mask>; the shipped
@@ -46,6 +47,8 @@
 #endif
 
 namespace mst {
+
+using namespace f2;
 
 constexpr int kCh = MST_TCN_CH;      // 128
 constexpr int kTaps = MST_TCN_K;     // 15
@@ -151,7 +154,9 @@ __global__ void tcn_pack_vec_kernel(const float* __restrict__ bn_w, const float*
 
 // =====================================================================================================================
 // FiLM precompute: one warp per (block, output row of Linear(2048 -> 256)); weight row kept in registers and reused for
-// every conditioning row.  Emits float4 (bn_bias, gamma, beta, res_scale) per (block, cond row, channel).
+// every conditioning row.  Emits (bn_bias, gamma, beta, res_scale) per (block, cond row, channel), interleaved over channel
+// PAIRS -- film[block][cond row][pair][component][channel & 1], two float4 per pair -- so that the epilogues, which work on
+// two channels at a time with packed fma.rn.f32x2, load their operands as ready-made 64-bit register pairs.
 // =====================================================================================================================
 template <int MAX_PER_LANE>
 __global__ void __launch_bounds__(256)
@@ -178,11 +183,11 @@ tcn_film_kernel(const float* __restrict__ film_w, const float* __restrict__ film
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) {
-      float* q = out + (((size_t)n * n_cond + bc) * kCh + c) * 4;
-      q[comp] = s + bias;
+      float* q = out + (((size_t)n * n_cond + bc) * kCh + (c & ~1)) * 4 + (c & 1);     // pair base + channel parity
+      q[2 * comp] = s + bias;
       if (comp == 1) {
         q[0] = bn_bias[n * kCh + c];
-        q[3] = res[n * kCh + c];
+        q[6] = res[n * kCh + c];
       }
     }
   }
@@ -215,7 +220,13 @@ tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, con
   for (int q = 0; q < 2; ++q) {
 #pragma unroll
     for (int i = 0; i < NIN * kTaps; ++i) wr[q][i] = __ldg(w0 + ch[q] * NIN * kTaps + i);
-    P[q] = __ldg(film + (size_t)(n_cond > 1 ? b : 0) * kCh + ch[q]);
+  }
+  {
+    // (bn_bias, gamma, beta, res) of the channel pair {ch[0], ch[1]}: two float4 of the pair-interleaved table
+    const float4* fp = film + (size_t)(n_cond > 1 ? b : 0) * kCh + ch[0];
+    const float4 A = __ldg(fp), Bq = __ldg(fp + 1);
+    P[0] = make_float4(A.x, A.z, Bq.x, Bq.z);
+    P[1] = make_float4(A.y, A.w, Bq.y, Bq.w);
   }
   // res = Conv1d(in, 128, k=1, groups=in): out channel c reads input channel c / (128/in)  (architectures.py:216-220)
   const int res_ci = ch[0] / (kCh / NIN);
@@ -315,7 +326,6 @@ struct TcnLayerArgs {
   const float* inv_scale;   // FMT 1 (f16f8): 1 / (S * 2^11) of this layer's packed weights (tcn_f8.cu)
   unsigned int* range_flag; // FMT 1: receives max |activation| (float bits, atomicMax) if it exceeds the e4m3 range; may be null
   const float4* film;   // this block's [n_cond][128] (bn_bias, gamma, beta, res)
-  int fuse_out;         // 1 on the last block: Conv1d(128 -> n_out, k=1) + clamp fused, fp32 [B][n_out][T] written
   int n_out;
   const float* out_w;   // [n_out][128]
   const float* out_b;   // [n_out]
@@ -368,7 +378,8 @@ __device__ __forceinline__ TcnTile tcn_tile(int tile, const TcnLayerArgs& a) {
 //        0-127], weights per tap [fp16 W S 2^11 ci 0-63 | ci 64-127 | e4m3 W S | e4m3 lo]; operand group 0 = the two fp16 tiles
 //        (kind::f16), group 1 = the two e4m3 tiles (kind::f8f6f4, tile i of X times tile i of W), all into ONE accumulator; the
 //        epilogue multiplies by 1 / (S 2^11).  Tensor maps are byte-typed in this mode (coordinates in bytes).
-template <int KCH, bool PAIRED, int FMT>
+// FUSE:  the last block -- Conv1d(128 -> n_out, k=1) + clamp in the epilogue, no activation store.
+template <int KCH, bool PAIRED, int FMT, bool FUSE>
 __global__ void __launch_bounds__(256, 1)
 tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                       const __grid_constant__ CUtensorMap tm_xs, const __grid_constant__ CUtensorMap tm_y,
@@ -385,7 +396,9 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   constexpr int kK16 = KCH / 16;                       // MMA K-steps per slot
   constexpr int kSwz = KCH * 2;                        // swizzle span in bytes (128 / 64)
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment as an OFFSET into the shared array (not integer pointer arithmetic): the compiler keeps the shared
+  // state space and emits LDS / STS instead of generic LD / ST for the epilogue's staging accesses
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;                                  // kNumSlots x kSlotBytes, 1024-aligned
   uint8_t* staging = smem + kRingBytes;                  // 32 KB epilogue tile (hi 16 KB | lo 16 KB), SWIZZLE_128B
   TcnBarriers* bars = reinterpret_cast<TcnBarriers*>(staging + kStageBytes);
@@ -620,7 +633,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     const int rl = q * 32 + lane;           // row inside the sub-tile == TMEM lane
     uint64_t* stage_full = &bars->stage_full;
     uint32_t stage_phase = 0;
-    float vmax = 0.f;                       // FMT 1: max |activation| this thread re-split (operand-range guard)
+    __half2 vmax2 = __float2half2_rn(0.f);  // FMT 1: max |activation| this thread re-split (operand-range guard), per pair half
     // residual x_in of channels 64h .. 64h+63, rows ts .. ts+127 of segment b -> staging (issued by thread 0 of the group)
     auto request_residual = [&](int h, int ts, int b) {
       if (FMT == 1) {
@@ -672,7 +685,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           if constexpr (FMT == 1) {
             // f16f8 rows: fp16 hi at staging (128-byte rows, SWIZZLE_128B), e4m3 remainder at +16 KB and e4m3 copy at +24 KB
             // (64-byte rows, SWIZZLE_64B: 16-byte chunk index XOR ((row / 2) mod 4))
-            const float inv_scale = __ldg(a.inv_scale);
+            const u64 inv_scale2 = dup(__ldg(a.inv_scale));
             uint8_t* lrow = staging + 16384 + rl * 64;
             uint8_t* hrow8 = staging + 24576 + rl * 64;
             const int sw64 = (rl >> 1) & 3;
@@ -689,20 +702,22 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
               for (int pr = 0; pr < 4; ++pr) {
                 const int cl = c8 * 8 + 2 * pr;
                 const int ch = h * 64 + cl;
-                const float4 P0 = __ldg(film + ch), P1 = __ldg(film + ch + 1);
-                // x_in = fp16 hi + e4m3 lo * 2^-11  (two channels at once)
+                // two adjacent channels at a time in packed fma.rn.f32x2 (each half rounds like the scalar op): the pair-
+                // interleaved table delivers (bn_bias, gamma) and (beta, res) of the pair as 64-bit operands
+                const ulonglong2 Pa = __ldg(reinterpret_cast<const ulonglong2*>(film + ch));
+                const ulonglong2 Pb = __ldg(reinterpret_cast<const ulonglong2*>(film + ch) + 1);
+                // x_in = fp16 hi + e4m3 lo * 2^-11
                 const float2 hif = __half22float2(*reinterpret_cast<const __half2*>(&xhw[pr]));
                 const unsigned short l8pair = (unsigned short)((xlw[pr >> 1] >> (16 * (pr & 1))) & 0xFFFFu);
                 const __half2_raw lraw = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)l8pair, __NV_E4M3);
                 const float2 lof = __half22float2(__half2(lraw));
-                const float xin0 = fmaf(lof.x, 1.f / 2048.f, hif.x), xin1 = fmaf(lof.y, 1.f / 2048.f, hif.y);
-                float u0 = fmaf(__uint_as_float(acc[cl]), inv_scale, P0.x);
-                float u1 = fmaf(__uint_as_float(acc[cl + 1]), inv_scale, P1.x);
-                u0 = fmaxf(u0, 0.01f * u0);      // LeakyReLU(0.01): max(u, 0.01 u)
-                u1 = fmaxf(u1, 0.01f * u1);
-                u0 = fmaf(P0.y, u0, P0.z) + P0.w * xin0;
-                u1 = fmaf(P1.y, u1, P1.z) + P1.w * xin1;
-                if (a.fuse_out) {
+                const u64 xin = fma2(pk(lof.x, lof.y), dup(1.f / 2048.f), pk(hif.x, hif.y));
+                u64 u = fma2(pk(__uint_as_float(acc[cl]), __uint_as_float(acc[cl + 1])), inv_scale2, Pa.x);
+                const u64 ul = mul2(u, dup(0.01f));                   // LeakyReLU(0.01): max(u, 0.01 u)
+                u = pk(fmaxf(lo_of(u), lo_of(ul)), fmaxf(hi_of(u), hi_of(ul)));
+                u = fma2(Pb.y, xin, fma2(Pa.y, u, Pb.x));             // gamma u + beta + res x_in
+                const float u0 = lo_of(u), u1 = hi_of(u);
+                if (FUSE) {
                   o0 = fmaf(u0, __ldg(a.out_w + ch), o0);
                   o0 = fmaf(u1, __ldg(a.out_w + ch + 1), o0);
                   if (a.n_out > 1) {
@@ -710,18 +725,18 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                     o1 = fmaf(u1, __ldg(a.out_w + kCh + ch + 1), o1);
                   }
                 } else {
-                  vmax = fmaxf(vmax, fmaxf(fabsf(u0), fabsf(u1)));
                   const uint32_t hbits = ptx::cvt_f16x2_satfinite(u0, u1);       // fp16 pair, clamped to +-65504
+                  vmax2 = __hmax2(vmax2, __habs2(*reinterpret_cast<const __half2*>(&hbits)));   // range guard on the packed pair
                   const float2 hb = __half22float2(*reinterpret_cast<const __half2*>(&hbits));
                   oh[pr] = hbits;
-                  const uint32_t l2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2((u0 - hb.x) * 2048.f, (u1 - hb.y) * 2048.f),
-                                                                        __NV_SATFINITE, __NV_E4M3);
+                  const u64 rem = mul2(fma2(pk(hb.x, hb.y), dup(-1.f), u), dup(2048.f));     // (u - fp16 u) 2^11, exact subtraction
+                  const uint32_t l2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(lo_of(rem), hi_of(rem)), __NV_SATFINITE, __NV_E4M3);
                   const uint32_t h2 = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(u0, u1), __NV_SATFINITE, __NV_E4M3);
                   ol[pr >> 1] |= l2 << (16 * (pr & 1));
                   oh8[pr >> 1] |= h2 << (16 * (pr & 1));
                 }
               }
-              if (!a.fuse_out) {
+              if (!FUSE) {
                 *reinterpret_cast<uint4*>(rowp + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
                 *reinterpret_cast<uint2*>(lrow + off8) = make_uint2(ol[0], ol[1]);
                 *reinterpret_cast<uint2*>(hrow8 + off8) = make_uint2(oh8[0], oh8[1]);
@@ -742,13 +757,14 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 for (int sidx = 0; sidx < 2; ++sidx) {
                   const int cl = c8 * 8 + e * 2 + sidx;
                   const int ch = h * 64 + cl;
-                  const float4 P = __ldg(film + ch);
+                  const float* Pp = reinterpret_cast<const float*>(film + (ch & ~1)) + (ch & 1);   // pair-interleaved table
+                  const float4 P = make_float4(__ldg(Pp), __ldg(Pp + 2), __ldg(Pp + 4), __ldg(Pp + 6));
                   const float xin = sidx == 0 ? bf16_lo_f(xhw[e]) + bf16_lo_f(xlw[e]) : bf16_hi_f(xhw[e]) + bf16_hi_f(xlw[e]);
                   float u = __uint_as_float(acc[cl]) + P.x;
                   u = fmaxf(u, 0.01f * u);
                   u = fmaf(P.y, u, P.z) + P.w * xin;
                   v[sidx] = u;
-                  if (a.fuse_out) {
+                  if (FUSE) {
                     o0 = fmaf(u, __ldg(a.out_w + ch), o0);
                     if (a.n_out > 1) o1 = fmaf(u, __ldg(a.out_w + kCh + ch), o1);
                   }
@@ -759,17 +775,17 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 oh[e] = pack_bf16(h0, h1);
                 ol[e] = pack_bf16(l0, l1);
               }
-              if (!a.fuse_out) {
+              if (!FUSE) {
                 *reinterpret_cast<uint4*>(rowp + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
                 *reinterpret_cast<uint4*>(rowp + 16384 + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
               }
             }
           }
           // every thread of the group is done with the staging tile (reads, and the in-place rewrite when it is stored)
-          if (!a.fuse_out) ptx::fence_proxy_async_smem();
+          if (!FUSE) ptx::fence_proxy_async_smem();
           ptx::named_bar_sync(1, 128);
           if (et == 0) {
-            if (!a.fuse_out) {
+            if (!FUSE) {
               if (FMT == 1) {
                 ptx::tma_store_3d(&tm_y, staging, 128 * h, ts, b);
                 ptx::tma_store_3d(&tm_y8, staging + 16384, 256 + 64 * h, ts, b);
@@ -785,7 +801,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             else request_next(tile, sub + 1);
           }
         }
-        if (a.fuse_out) {
+        if (FUSE) {
           const int t = ts + rl;
           if (t < a.T) {
             // clamp(output(x), -1, 1)   architectures.py:143-145
@@ -802,6 +818,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     if (FMT == 1 && a.range_flag != nullptr) {
       // |x| > 448 saturates the e4m3 planes (x itself and (x - fp16 x) 2^11 <= |x|): the next block would then run at single-pass
       // fp16 accuracy.  Report it (one atomic per warp, only when it happened) so the caller can repeat the forward in bf16 x 3.
+      float vmax = fmaxf(__low2float(vmax2), __high2float(vmax2));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
       if (lane == 0 && vmax > MST_TCN_F16F8_RANGE) atomicMax(a.range_flag, __float_as_uint(vmax));
@@ -912,22 +929,23 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   a.n_tiles = B * a.tiles_per_seg;
   a.n_cond = n_cond;
   a.film = reinterpret_cast<const float4*>(film) + (size_t)n * n_cond * kCh;
-  a.fuse_out = fuse_out ? 1 : 0;
   a.n_out = cfg->n_outputs;
   a.out_w = reinterpret_cast<const float*>(packed + L.out_w);
   a.out_b = reinterpret_cast<const float*>(packed + L.out_b);
   a.out = out;
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-#define MST_TCN_LAUNCH(PAIRED_, FMT_)                                                                                        \
-  do {                                                                                                                      \
-    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64, PAIRED_, FMT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)kTcnSmemBytes));                                                                  \
-    tcn_block_umma_kernel<64, PAIRED_, FMT_><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8, a);   \
+#define MST_TCN_LAUNCH(PAIRED_, FMT_, FUSE_)                                                                                        \
+  do {                                                                                                                             \
+    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64, PAIRED_, FMT_, FUSE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)kTcnSmemBytes));                                                                         \
+    tcn_block_umma_kernel<64, PAIRED_, FMT_, FUSE_><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8, a);   \
   } while (0)
-  if (f8 && paired) MST_TCN_LAUNCH(true, 1);
-  else if (f8) MST_TCN_LAUNCH(false, 1);
-  else if (paired) MST_TCN_LAUNCH(true, 0);
-  else MST_TCN_LAUNCH(false, 0);
+#define MST_TCN_LAUNCH2(PAIRED_, FMT_) do { if (fuse_out) MST_TCN_LAUNCH(PAIRED_, FMT_, true); else MST_TCN_LAUNCH(PAIRED_, FMT_, false); } while (0)
+  if (f8 && paired) MST_TCN_LAUNCH2(true, 1);
+  else if (f8) MST_TCN_LAUNCH2(false, 1);
+  else if (paired) MST_TCN_LAUNCH2(true, 0);
+  else MST_TCN_LAUNCH2(false, 0);
+#undef MST_TCN_LAUNCH2
 #undef MST_TCN_LAUNCH
   return launch_ok("tcn_block_umma_kernel");
 }

@@ -118,7 +118,13 @@ block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const f
   for (int q = 0; q < 2; ++q) {
 #pragma unroll
     for (int i = 0; i < NIN * kTaps; ++i) wr[q][i] = __ldg(w0 + ch[q] * NIN * kTaps + i);
-    P[q] = __ldg(film + (size_t)(n_cond > 1 ? b : 0) * kCh + ch[q]);
+  }
+  {
+    // (bn_bias, gamma, beta, res) of the channel pair {ch[0], ch[1]}: two float4 of the pair-interleaved table (tcn.cu)
+    const float4* fp = film + (size_t)(n_cond > 1 ? b : 0) * kCh + ch[0];
+    const float4 A = __ldg(fp), Bq = __ldg(fp + 1);
+    P[0] = make_float4(A.x, A.z, Bq.x, Bq.z);
+    P[1] = make_float4(A.y, A.w, Bq.y, Bq.w);
   }
   const int res_ci = ch[0] / (kCh / NIN);
   float vmax = 0.f;     // max |activation| written by this thread (operand-range guard, see tcn.cu)
