@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(256) tcn_act_unpack_kernel(const uint8_t* __re
 // =====================================================================================================================
 struct TcnLayerArgs {
   int B, T, dilation, tiles_per_seg, n_tiles, n_cond;
-  int pair_m;           // PAIRED kernels: sub-tiles per half block = dilation / 128
+  int pair_m;           // mode 1: sub-tiles per half block = dilation / 128
   const float* inv_scale;   // FMT 1 (f16f8): 1 / (S * 2^11) of this layer's packed weights (tcn_f8.cu)
   unsigned int* range_flag; // FMT 1: receives max |activation| (float bits, atomicMax) if it exceeds the e4m3 range; may be null
   const float4* film;   // this block's [n_cond][128] (bn_bias, gamma, beta, res)
@@ -341,28 +341,32 @@ struct __align__(8) TcnBarriers {
 
 constexpr size_t kTcnSmemBytes = 1024 /*align slack*/ + (size_t)kRingBytes + kStageBytes + 256;
 
-// rows [ts, ts+128) of a shifted sub-tile intersect the real signal [0, T)?  (otherwise it is all zero padding)
-__device__ __forceinline__ bool tap_live(long long ts, int T) { return ts < (long long)T && ts + kSubRows > 0; }
-
-// Where the two 128-row sub-tiles of work item `tile` live.
-//   PAIRED = false: one 256-row tile, sub-tile 1 directly after sub-tile 0.
-//   PAIRED = true (dilation d a multiple of 128): sub-tile 1 sits d rows after sub-tile 0.  The time axis is cut into
-//   blocks of 2d rows; item i of a block pairs rows [i*128, +128) of its first half with the same rows of its second half.
-//   Then tap j of sub-tile 1 reads exactly the rows that tap j+1 of sub-tile 0 reads, so one activation slot serves two
-//   MMA groups and the operand bytes entering the SM per MMA drop by a third (see the producer / issuer loops).
+// Work-item geometry.  MODE selects how the two 128-row sub-tiles of a work item sit in time:
+//   0  one 256-row tile, sub-tile 1 directly after sub-tile 0 (any dilation, any length).
+//   1  "far pairing", dilation d a multiple of 128: sub-tile 1 sits d rows after sub-tile 0.  The time axis is cut into blocks
+//      of 2d rows; item i of a block pairs rows [i*128, +128) of its first half with the same rows of its second half.
+//   2  "interleaved pairing", d < 128 dividing 128, T a multiple of 2d: the work item is still one 256-row span, but sub-tile 0
+//      takes the FIRST d rows of each of its 128/d blocks of 2d rows and sub-tile 1 the second d rows -- 128 rows gathered by
+//      one 5-D TMA box {128 B, d rows, 1 half, 128/d blocks} over the activation viewed as [b][block][half][row][512 B].
+//   In modes 1 and 2 sub-tile 1 is sub-tile 0 shifted by exactly d rows, so tap j of sub-tile 1 reads the rows tap j+1 of
+//   sub-tile 0 reads: one activation slot serves two MMA groups and the activation bytes entering the SM halve (see the
+//   producer / issuer loops).  `ts` below is always the first row of a (shifted) sub-tile; in mode 2 it is a multiple of d.
 struct TcnTile { int b; long long r0, r1; bool sub0, sub1; };
-template <bool PAIRED>
+template <int MODE>
 __device__ __forceinline__ TcnTile tcn_tile(int tile, const TcnLayerArgs& a) {
   TcnTile c;
   c.b = tile / a.tiles_per_seg;
   const int p = tile - c.b * a.tiles_per_seg;
-  if (PAIRED) {
+  if (MODE == 1) {
     // block index fastest: consecutive work items (= the CTAs of one wave) are 2d rows apart and share 14 of their 16 tap
     // tiles, so a wave's working set stays in L2 also for the large dilations (with i fastest the 148 x 16 tiles of a wave are
     // all distinct at d >= 2048: 150 MB, DRAM reads up to 3x the algorithmic bytes)
     const int nblk = a.tiles_per_seg / a.pair_m;
     const int i = p / nblk, blk = p - i * nblk;
     c.r0 = (long long)blk * 2 * a.dilation + (long long)i * kSubRows;
+    c.r1 = c.r0 + a.dilation;
+  } else if (MODE == 2) {
+    c.r0 = (long long)p * kTileRows;
     c.r1 = c.r0 + a.dilation;
   } else {
     c.r0 = (long long)p * kTileRows;
@@ -372,6 +376,13 @@ __device__ __forceinline__ TcnTile tcn_tile(int tile, const TcnLayerArgs& a) {
   c.sub1 = c.r1 < a.T;
   return c;
 }
+// does the (shifted) sub-tile starting at row ts touch the real signal [0, T)?  (otherwise it is all zero padding).  Mode 2
+// sub-tiles span 256 - d rows; the looser bound only costs a few all-zero taps at the segment edges.
+template <int MODE>
+__device__ __forceinline__ bool tap_live(long long ts, int T) { return ts < (long long)T && ts + (MODE == 2 ? kTileRows : kSubRows) > 0; }
+// time row of sub-tile row `rl` (modes 0 / 1: consecutive rows; mode 2: d rows out of every 2d)
+template <int MODE>
+__device__ __forceinline__ int tile_row(int ts, int rl, int d) { return MODE == 2 ? ts + (rl / d) * 2 * d + rl % d : ts + rl; }
 
 // FMT 0: bf16 hi/lo operands, three products per K-step (the default).
 // FMT 1: the "2 tensor units" split of tcn_f8.cu -- rows [fp16 ch 0-63 | fp16 ch 64-127 | e4m3 (x - hi) 2^11, ch 0-127 | e4m3 x, ch
@@ -379,7 +390,7 @@ __device__ __forceinline__ TcnTile tcn_tile(int tile, const TcnLayerArgs& a) {
 //        (kind::f16), group 1 = the two e4m3 tiles (kind::f8f6f4, tile i of X times tile i of W), all into ONE accumulator; the
 //        epilogue multiplies by 1 / (S 2^11).  Tensor maps are byte-typed in this mode (coordinates in bytes).
 // FUSE:  the last block -- Conv1d(128 -> n_out, k=1) + clamp in the epilogue, no activation store.
-template <int KCH, bool PAIRED, int FMT, bool FUSE>
+template <int KCH, int MODE, int FMT, bool FUSE>
 __global__ void __launch_bounds__(256, 1)
 tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                       const __grid_constant__ CUtensorMap tm_xs, const __grid_constant__ CUtensorMap tm_y,
@@ -388,6 +399,16 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   // tm_x / tm_w: operand boxes {KCH ch, 128 rows}, swizzle = 2*KCH bytes;  tm_xs / tm_y: epilogue boxes {64 ch, 128 rows};
   // tm_l8 / tm_y8 (FMT 1 only): epilogue boxes {64 bytes, 128 rows}, SWIZZLE_64B, for the e4m3 half planes
   static_assert(FMT == 0 || KCH == 64, "the f16f8 format uses 128-byte operand rows");
+  constexpr bool PAIRED = MODE != 0;
+  // activation boxes: 3-D {columns, 128 rows, segment} in modes 0 / 1, 5-D {columns, d rows, half, 128/d blocks, segment} in mode 2
+  auto act_load = [&](const CUtensorMap* m, uint64_t* bar, void* dst, int col, int ts, int b) {
+    if (MODE == 2) { const int hh = ts / a.dilation; ptx::tma_load_5d(m, bar, dst, col, 0, hh & 1, hh >> 1, b); }
+    else ptx::tma_load_3d(m, bar, dst, col, ts, b);
+  };
+  auto act_store = [&](const CUtensorMap* m, const void* src, int col, int ts, int b) {
+    if (MODE == 2) { const int hh = ts / a.dilation; ptx::tma_store_5d(m, src, col, 0, hh & 1, hh >> 1, b); }
+    else ptx::tma_store_3d(m, src, col, ts, b);
+  };
   constexpr int kCoord = FMT == 1 ? 2 : 1;             // byte-typed maps: column coordinates in bytes instead of bf16 elements
   constexpr int kKcPerTap = kCh / KCH;                 // 2 or 4 input-channel chunks per tap
   constexpr int kHalf = kSubRows * KCH * 2;            // bytes of one hi (or lo) operand tile: 16 KB / 8 KB
@@ -458,12 +479,12 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         if (MST_TCN_ABLATE & 4) { ptx::mbar_arrive(&bars->full[slot]); next(); return; }
         ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
         uint8_t* dst = ring + (size_t)slot * kSlotBytes;
-        ptx::tma_load_3d(&tm_x, &bars->full[slot], dst, c_hi, (int)ts, b);
-        ptx::tma_load_3d(&tm_x, &bars->full[slot], dst + kHalf, c_lo, (int)ts, b);
+        act_load(&tm_x, &bars->full[slot], dst, c_hi, (int)ts, b);
+        act_load(&tm_x, &bars->full[slot], dst + kHalf, c_lo, (int)ts, b);
         next();
       };
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const TcnTile c = tcn_tile<PAIRED>(tile, a);
+        const TcnTile c = tcn_tile<MODE>(tile, a);
         if (!c.sub0) continue;
         if (PAIRED || FMT == 1) {
           // operand group (channel half / MMA kind) outermost.  Slot order per executed step (kc, j): W, [rows of sub-tile 0's
@@ -471,7 +492,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           for (int kc = 0; kc < kKcPerTap; ++kc) {
             for (int j = 0; j < kTaps; ++j) {
               const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
-              const bool live0 = tap_live(ts0, a.T), live1 = c.sub1 && tap_live(ts1, a.T);
+              const bool live0 = tap_live<MODE>(ts0, a.T), live1 = c.sub1 && tap_live<MODE>(ts1, a.T);
               if (!live0 && !live1) continue;
               load_w(j, kc);
               const bool resident = PAIRED && j >= 1 && c.sub1 && live0;   // ts0 == rows of sub-tile 1 at tap j-1 (same liveness)
@@ -482,7 +503,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         } else {
           for (int j = 0; j < kTaps; ++j) {
             const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
-            const bool live0 = tap_live(ts0, a.T), live1 = c.sub1 && tap_live(ts1, a.T);
+            const bool live0 = tap_live<MODE>(ts0, a.T), live1 = c.sub1 && tap_live<MODE>(ts1, a.T);
             if (!live0 && !live1) continue;
             for (int kc = 0; kc < kKcPerTap; ++kc) {
               load_w(j, kc);
@@ -537,7 +558,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       };
       int it = 0;
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const TcnTile c = tcn_tile<PAIRED>(tile, a);
+        const TcnTile c = tcn_tile<MODE>(tile, a);
         if (!c.sub0) continue;
         const int buf = it & 1;
         ptx::mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
@@ -550,7 +571,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             int carried = -1;      // slot holding the rows sub-tile 1 used at the previous tap = rows of sub-tile 0 at this tap
             for (int j = 0; j < kTaps; ++j) {
               const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
-              const bool live0 = tap_live(ts0, a.T), live1 = c.sub1 && tap_live(ts1, a.T);
+              const bool live0 = tap_live<MODE>(ts0, a.T), live1 = c.sub1 && tap_live<MODE>(ts1, a.T);
               if (!live0 && !live1) continue;
               const uint32_t wslot = slot;
               ptx::mbar_wait(&bars->full[wslot], phase);
@@ -588,7 +609,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         } else {
           for (int j = 0; j < kTaps; ++j) {
             const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
-            const bool live0 = tap_live(ts0, a.T), live1 = c.sub1 && tap_live(ts1, a.T);
+            const bool live0 = tap_live<MODE>(ts0, a.T), live1 = c.sub1 && tap_live<MODE>(ts1, a.T);
             if (!live0 && !live1) continue;
             for (int kc = 0; kc < kKcPerTap; ++kc) {
               const uint32_t wslot = slot;
@@ -639,19 +660,19 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       if (FMT == 1) {
         // the fp16 plane h (16 KB, SWIZZLE_128B) and half of the e4m3 remainder plane (64 bytes per row, 8 KB, SWIZZLE_64B)
         ptx::mbar_expect_tx(stage_full, 16384 + 8192);
-        ptx::tma_load_3d(&tm_xs, stage_full, staging, 128 * h, ts, b);
-        ptx::tma_load_3d(&tm_l8, stage_full, staging + 16384, 256 + 64 * h, ts, b);
+        act_load(&tm_xs, stage_full, staging, 128 * h, ts, b);
+        act_load(&tm_l8, stage_full, staging + 16384, 256 + 64 * h, ts, b);
       } else {
         ptx::mbar_expect_tx(stage_full, kStageBytes);
-        ptx::tma_load_3d(&tm_xs, stage_full, staging, (2 * h) * 64, ts, b);              // x_in hi, ch 64h..
-        ptx::tma_load_3d(&tm_xs, stage_full, staging + 16384, (2 * h + 1) * 64, ts, b);  // x_in lo
+        act_load(&tm_xs, stage_full, staging, (2 * h) * 64, ts, b);              // x_in hi, ch 64h..
+        act_load(&tm_xs, stage_full, staging + 16384, (2 * h + 1) * 64, ts, b);  // x_in lo
       }
     };
     // requests the h = 0 residual tile of the first live sub-tile at or after (tile, sub) in processing order (thread 0 only)
     auto request_next = [&](int tile, int sub) {
       if (MST_TCN_ABLATE & 2) return;
       for (; tile < a.n_tiles; tile += gridDim.x, sub = 0) {
-        const TcnTile c = tcn_tile<PAIRED>(tile, a);
+        const TcnTile c = tcn_tile<MODE>(tile, a);
         if (!c.sub0) continue;
         for (; sub < 2; ++sub) {
           const long long ts = sub == 0 ? c.r0 : c.r1;
@@ -662,7 +683,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     if (et == 0) request_next(blockIdx.x, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-      const TcnTile c = tcn_tile<PAIRED>(tile, a);
+      const TcnTile c = tcn_tile<MODE>(tile, a);
       if (!c.sub0) continue;
       const int b = c.b;
       const int buf = it & 1;
@@ -787,12 +808,12 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           if (et == 0) {
             if (!FUSE) {
               if (FMT == 1) {
-                ptx::tma_store_3d(&tm_y, staging, 128 * h, ts, b);
-                ptx::tma_store_3d(&tm_y8, staging + 16384, 256 + 64 * h, ts, b);
-                ptx::tma_store_3d(&tm_y8, staging + 24576, 384 + 64 * h, ts, b);
+                act_store(&tm_y, staging, 128 * h, ts, b);
+                act_store(&tm_y8, staging + 16384, 256 + 64 * h, ts, b);
+                act_store(&tm_y8, staging + 24576, 384 + 64 * h, ts, b);
               } else {
-                ptx::tma_store_3d(&tm_y, staging, (2 * h) * 64, ts, b);
-                ptx::tma_store_3d(&tm_y, staging + 16384, (2 * h + 1) * 64, ts, b);
+                act_store(&tm_y, staging, (2 * h) * 64, ts, b);
+                act_store(&tm_y, staging + 16384, (2 * h + 1) * 64, ts, b);
               }
               ptx::tma_store_commit();
               ptx::tma_store_wait_read0();       // the staging tile may be overwritten once the store has read it
@@ -802,7 +823,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
           }
         }
         if (FUSE) {
-          const int t = ts + rl;
+          const int t = tile_row<MODE>(ts, rl, a.dilation);
           if (t < a.T) {
             // clamp(output(x), -1, 1)   architectures.py:143-145
             a.out[((size_t)b * a.n_out + 0) * a.T + t] = fminf(fmaxf(o0 + __ldg(a.out_b), -1.f), 1.f);
@@ -893,6 +914,23 @@ static int encode_w_map_bytes(CUtensorMap* m, const void* base) {
   return 0;
 }
 
+// mode-2 activation maps: the time axis viewed as [block of 2d rows][half][d rows], box = {box columns, d rows, 1 half, 128/d blocks}
+// = the 128 rows of an interleaved sub-tile (tcn_tile<2>).  Requires T % 2d == 0.  `bytes` = byte-typed map (f16f8) or bf16 elements.
+static int encode_act_map5(CUtensorMap* m, const void* base, int B, int T, int d, int box_cols, bool bytes) {
+  PFN_encodeTiled enc = tensor_map_encoder();
+  if (!enc) return 1;
+  cuuint64_t dims[5] = {(cuuint64_t)(bytes ? kRowBytes : 256), (cuuint64_t)d, 2, (cuuint64_t)(T / (2 * d)), (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)kRowBytes, (cuuint64_t)d * kRowBytes, (cuuint64_t)2 * d * kRowBytes, (cuuint64_t)T * kRowBytes};
+  cuuint32_t box[5] = {(cuuint32_t)box_cols, (cuuint32_t)d, 1, (cuuint32_t)(kSubRows / d), 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const int row_bytes = bytes ? box_cols : box_cols * 2;
+  CUresult r = enc(m, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(interleaved activation B=%d T=%d d=%d box=%d) failed: CUresult %d", B, T, d, box_cols, (int)r);
+  return 0;
+}
+
 // one dilated block (n >= 1): act_in -> act_out, or -> fp32 `out` when fuse_out
 static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, const TcnPacked& L, int n,
                              const uint8_t* act_in, uint8_t* act_out, const float* film, int n_cond, int B, int T,
@@ -900,9 +938,26 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   const long long d = block_dilation(cfg, n);
   MST_CHECK(7 * d + kTileRows < (1ll << 31) - T, "tcn: dilation %lld too large", d);
   const bool f8 = precision == MST_TCN_F16F8;
+  // work-item geometry (tcn_tile): far pairing for dilations that are a multiple of 128, interleaved pairing for the small
+  // ones when the length allows it, plain 256-row tiles otherwise
+  const int mode = (d >= kSubRows && d % kSubRows == 0) ? 1 : ((d < kSubRows && kSubRows % d == 0 && T % (2 * d) == 0) ? 2 : 0);
   CUtensorMap tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8;
   const uint8_t* w_layer = packed + (f8 ? L.wumma : L.wbf16) + (size_t)(n - 1) * kWBytesPerLayer;
-  if (f8) {
+  const void* dst_act = fuse_out ? (const void*)act_in : (const void*)act_out;
+  if (mode == 2) {
+    if (encode_act_map5(&tm_x, act_in, B, T, (int)d, f8 ? 128 : 64, f8)) return 1;
+    tm_xs = tm_x;
+    if (encode_act_map5(&tm_y, dst_act, B, T, (int)d, f8 ? 128 : 64, f8)) return 1;
+    if (f8) {
+      if (encode_act_map5(&tm_l8, act_in, B, T, (int)d, 64, true)) return 1;
+      if (encode_act_map5(&tm_y8, dst_act, B, T, (int)d, 64, true)) return 1;
+      if (encode_w_map_bytes(&tm_w, w_layer)) return 1;
+    } else {
+      tm_l8 = tm_xs;
+      tm_y8 = tm_y;
+      if (encode_w_map(&tm_w, w_layer, 64)) return 1;
+    }
+  } else if (f8) {
     if (encode_act_map_bytes(&tm_x, act_in, B, T, 128)) return 1;
     tm_xs = tm_x;
     if (encode_act_map_bytes(&tm_y, fuse_out ? act_in : act_out, B, T, 128)) return 1;
@@ -921,11 +976,8 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   a.inv_scale = reinterpret_cast<const float*>(packed + L.f8_scale) + 2 * n;
   a.range_flag = f8 ? range_flag : nullptr;
   a.B = B; a.T = T; a.dilation = (int)d;
-  // Paired sub-tiles (tcn_tile<true>) for dilations that are a multiple of 128: L2->SM bytes 100.9 -> 70 GB per launch,
-  // tensor pipe 82.8 -> 85.9 % (profiles/r01g_summary.md)
-  const bool paired = d >= kSubRows && d % kSubRows == 0;
-  a.pair_m = paired ? (int)(d / kSubRows) : 1;
-  a.tiles_per_seg = paired ? (int)(((T + 2 * d - 1) / (2 * d)) * a.pair_m) : cdiv(T, kTileRows);
+  a.pair_m = mode == 1 ? (int)(d / kSubRows) : 1;
+  a.tiles_per_seg = mode == 1 ? (int)(((T + 2 * d - 1) / (2 * d)) * a.pair_m) : cdiv(T, kTileRows);
   a.n_tiles = B * a.tiles_per_seg;
   a.n_cond = n_cond;
   a.film = reinterpret_cast<const float4*>(film) + (size_t)n * n_cond * kCh;
@@ -934,17 +986,18 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   a.out_b = reinterpret_cast<const float*>(packed + L.out_b);
   a.out = out;
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
-#define MST_TCN_LAUNCH(PAIRED_, FMT_, FUSE_)                                                                                        \
-  do {                                                                                                                             \
-    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64, PAIRED_, FMT_, FUSE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)kTcnSmemBytes));                                                                         \
-    tcn_block_umma_kernel<64, PAIRED_, FMT_, FUSE_><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8, a);   \
+#define MST_TCN_LAUNCH(MODE_, FMT_, FUSE_)                                                                                        \
+  do {                                                                                                                           \
+    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64, MODE_, FMT_, FUSE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)kTcnSmemBytes));                                                                       \
+    tcn_block_umma_kernel<64, MODE_, FMT_, FUSE_><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8, a);   \
   } while (0)
-#define MST_TCN_LAUNCH2(PAIRED_, FMT_) do { if (fuse_out) MST_TCN_LAUNCH(PAIRED_, FMT_, true); else MST_TCN_LAUNCH(PAIRED_, FMT_, false); } while (0)
-  if (f8 && paired) MST_TCN_LAUNCH2(true, 1);
-  else if (f8) MST_TCN_LAUNCH2(false, 1);
-  else if (paired) MST_TCN_LAUNCH2(true, 0);
-  else MST_TCN_LAUNCH2(false, 0);
+#define MST_TCN_LAUNCH2(MODE_, FMT_) do { if (fuse_out) MST_TCN_LAUNCH(MODE_, FMT_, true); else MST_TCN_LAUNCH(MODE_, FMT_, false); } while (0)
+#define MST_TCN_LAUNCH3(FMT_) do { if (mode == 1) MST_TCN_LAUNCH2(1, FMT_); else if (mode == 2) MST_TCN_LAUNCH2(2, FMT_); else MST_TCN_LAUNCH2(0, FMT_); } while (0)
+  if (f8) MST_TCN_LAUNCH3(1);
+  else MST_TCN_LAUNCH3(0);
+#undef MST_TCN_LAUNCH3
+#undef MST_TCN_LAUNCH2
 #undef MST_TCN_LAUNCH2
 #undef MST_TCN_LAUNCH
   return launch_ok("tcn_block_umma_kernel");

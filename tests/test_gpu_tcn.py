@@ -38,6 +38,36 @@ def test_blocks_long_lengths(n, L):
     assert e["rms"] <= 3e-5 * max(1.0, e["ref_rms"]) and e["max"] <= 5e-4 * max(1.0, e["ref_rms"]), (n, L, e)
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("L", [4224, 6400])
+def test_small_dilation_blocks_interleaved_pairing(n, L):
+    """Dilations 2 .. 64 at lengths that are a multiple of 2d: the kernel takes its interleaved-pairing geometry (tcn_tile mode 2:
+    sub-tile 0 = first d rows of every 2d-row block, 5-D TMA boxes).  4224 = 16.5 tiles (partial last tile), 6400 = 25 tiles."""
+    e, _, _ = _block_case(n, B=2, L=L, seed=1000 + 7 * n + L)
+    assert e["rms"] <= 3e-5 * max(1.0, e["ref_rms"]) and e["max"] <= 5e-4 * max(1.0, e["ref_rms"]), (n, L, e)
+
+
+@pytest.mark.parametrize("nblocks", [3, 5, 7])
+def test_short_models_fuse_the_output_conv_into_small_dilation_blocks(nblocks):
+    """TCNModel with fewer blocks: the fused Conv1d(128 -> 2) + clamp epilogue runs on a block with dilation 4 / 16 / 64, in both
+    geometries (L = 3001: plain tiles; L = 3072: interleaved pairing, whose rows are not consecutive in time)."""
+    oracle_threads()
+    from music_mixing_style_transfer_b200.networks import TCNModel
+    tsd = W.make_tcn_state_dict(4, nblocks=nblocks)
+    m = TCNModel(nparams=2048, ninputs=2, noutputs=2, nblocks=nblocks, dilation_growth=2, kernel_size=15, channel_width=128,
+                 stack_size=15, cond_dim=2048, causal=False)
+    m.load_state_dict(tsd)
+    m = m.cuda().eval()
+    cond = fixtures.make_cond(2, 77)
+    for L in (3001, 3072):
+        x = W.synthetic_audio(2, L, seed=78)
+        with torch.no_grad():
+            ref = O.tcn_forward(x, cond, tsd, nblocks=nblocks)
+            got = m(x.cuda(), cond.cuda()).cpu()
+        e = err_stats(got, ref)
+        assert e["rms"] <= 2e-5, (nblocks, L, e)
+
+
 def test_block_per_segment_condition():
     e, _, _ = _block_case(5, B=3, L=2500, seed=900, n_cond=3)
     assert e["rms"] <= 3e-5 * max(1.0, e["ref_rms"]), e

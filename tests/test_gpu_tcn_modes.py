@@ -38,6 +38,21 @@ def test_bf16x3_every_block_matches_oracle(bf16x3_tcn, n):
     assert e["rms"] <= 3e-5 * max(1.0, e["ref_rms"]) and e["max"] <= 5e-4 * max(1.0, e["ref_rms"]), (n, e)
 
 
+@pytest.mark.parametrize("n", [1, 3, 6])
+def test_bf16x3_interleaved_pairing(bf16x3_tcn, n):
+    oracle_threads()
+    _, tsd = state_dicts()
+    g = torch.Generator()
+    g.manual_seed(1800 + n)
+    x = torch.randn(2, 128, 4224, generator=g) * 0.5
+    cond = fixtures.make_cond(1, 1801 + n)
+    with torch.no_grad():
+        ref = O.tcn_block(x, cond, tsd, f"blocks.{n}", 15, 2 ** n)
+        got = bf16x3_tcn.blocks[n](x.cuda(), cond.cuda()).cpu()
+    e = err_stats(got, ref)
+    assert e["rms"] <= 3e-5 * max(1.0, e["ref_rms"]) and e["max"] <= 5e-4 * max(1.0, e["ref_rms"]), (n, e)
+
+
 @pytest.mark.parametrize("name,B,L,seed,cseed,ncond", [("tcn_small.npz", 2, 8191, 12, 21, 1),
                                                         ("tcn_percond.npz", 3, 4099, 13, 22, 3)])
 def test_bf16x3_golden_full_tcn(bf16x3_tcn, name, B, L, seed, cseed, ncond):
