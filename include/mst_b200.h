@@ -168,6 +168,25 @@ int mst_block_energy(const float* x, int n_channels, long long T, const long lon
 int mst_haas(const float* x, float* y, int B, long long L, const int* delay, const float* feedback, const int* channel,
              void* stream);
 
+/* ---- spectral pieces of the input FX normaliser's EQ matching (csrc/spectral.cu) -------------------------
+ * Reference paths relative to mixing_style_transfer/mixing_manipulator/.
+ * mst_row_absmax: out[r] = max |x[r][0..T)| (float64, rows `stride` floats apart): np.max(np.abs(.)) per channel
+ *   (utils_data_normalization.py:69, fx_utils.py:231).
+ * mst_stft_mag_mean: out[s][k] = mean over frames of |rfft(window * x_s[f*hop : f*hop + n_fft])[k]|, k = 0..n_fft/2, float64:
+ *   compute_stft + np.abs + np.mean of get_eq_matching (utils_data_normalization.py:74-79; common_miscellaneous.py:50-77,
+ *   librosa.stft(center=False), n_frames = 1 + (T - n_fft) / hop, spectra in complex64).  n_fft: power of two in
+ *   [1024, 65536]; window: device float32 [n_fft]; signals `stride` floats apart.
+ * mst_fir_filtfilt: y_s = float32(scale[s] * filtfilt(taps_s, 1, x_s)) with scipy's defaults (padtype='odd', padlen = 3*n_taps,
+ *   method='pad': utils_data_normalization.py:100-102), float64 arithmetic; taps: device float64 [n_signals][n_taps];
+ *   scale: device float64 [n_signals] or NULL; needs T > 3*n_taps like scipy. */
+int mst_row_absmax(const float* x, int n_rows, long long T, long long stride, double* out, void* stream);
+size_t mst_stft_workspace_bytes(int n_signals, int n_fft);
+int mst_stft_mag_mean(const float* x, int n_signals, long long T, long long stride, int n_fft, int hop, const float* window,
+                      double* out, void* workspace, size_t workspace_bytes, void* stream);
+size_t mst_fir_filtfilt_workspace_bytes(int n_signals, long long T, int n_taps);
+int mst_fir_filtfilt(const float* x, int n_signals, long long T, long long stride, const double* taps, int n_taps,
+                     const double* scale, float* y, long long y_stride, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- WAV sample formats on the device: the steps either side of the forward -------------------
  * mst_pcm_decode replaces load_wav_segment's int -> float conversion and de-interleave
  * (mixing_style_transfer/data_loader/loader_utils.py:54-70) plus the stem clamp (data_loader/data_loader.py:589-590) and

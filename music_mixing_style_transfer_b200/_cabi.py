@@ -65,6 +65,13 @@ SIGNATURES = {
     "mst_stereo_mix": (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.c_longlong, c_void_p]),
     "mst_block_energy": (c_int, [c_void_p, c_int, ctypes.c_longlong, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "mst_haas": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mst_row_absmax": (c_int, [c_void_p, c_int, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_void_p]),
+    "mst_stft_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mst_stft_mag_mean": (c_int, [c_void_p, c_int, ctypes.c_longlong, ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_size_t, c_void_p]),
+    "mst_fir_filtfilt_workspace_bytes": (c_size_t, [c_int, ctypes.c_longlong, c_int]),
+    "mst_fir_filtfilt": (c_int, [c_void_p, c_int, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_int, c_void_p, c_void_p,
+                                 ctypes.c_longlong, c_void_p, c_size_t, c_void_p]),
     "mst_pcm_decode": (c_int, [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, ctypes.c_longlong, c_void_p]),
     "mst_pcm_encode_mix": (c_int, [c_void_p, c_int, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_void_p]),
 }

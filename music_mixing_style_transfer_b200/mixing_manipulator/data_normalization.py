@@ -101,8 +101,9 @@ def gated_loudness(z_sums, rate=44100, block_size=0.400):
         return float(-0.691 + 10.0 * np.log10(np.sum(g[:, 0] * z_avg)))
 
 
-def integrated_loudness(x, rate=44100):
-    """x float32 CUDA [2, T] -> LUFS of (x + 1e-10), as fx_utils.lufs_normalize measures it (fx_utils.py:224)."""
+def kweighted_block_sums(x, rate=44100):
+    """x float32 CUDA [2, T] -> float64 numpy [2, blocks]: sums of squares of the K-weighted (x + 1e-10) per gating block
+    (fx_utils.py:224: the meter is fed x + 1e-10), or None when the signal is shorter than one block."""
     lib = _cabi.lib()
     T = x.shape[-1]
     xe = (x + 1e-10).unsqueeze(0).contiguous()
@@ -114,12 +115,25 @@ def integrated_loudness(x, rate=44100):
                                        _stream()), "biquad_cascade")
     lo, hi = gating_block_bounds(T, rate)
     if len(lo) == 0:
-        return float('-inf')
+        return None
     lo_d, hi_d = torch.from_numpy(lo).to(x.device), torch.from_numpy(hi).to(x.device)
     z = torch.empty(2, len(lo), dtype=torch.float64, device=x.device)
     _cabi.check(lib.mst_block_energy(_cabi.ptr(y), 2, T, lo_d.data_ptr(), hi_d.data_ptr(), len(lo), z.data_ptr(), _stream()),
                 "block_energy")
-    return gated_loudness(z.cpu().numpy(), rate)
+    return z.cpu().numpy()
+
+
+def integrated_loudness(x, rate=44100):
+    """x float32 CUDA [2, T] -> LUFS of (x + 1e-10), as fx_utils.lufs_normalize measures it (fx_utils.py:224)."""
+    z = kweighted_block_sums(x, rate)
+    return float('-inf') if z is None else gated_loudness(z, rate)
+
+
+def integrated_loudness_per_channel(x, rate=44100):
+    """Each channel of x float32 CUDA [2, T] measured as a MONO signal (get_eq_matching normalises one channel at a time,
+    utils_data_normalization.py:72): one K-weighting pass over both channels, the gating per channel."""
+    z = kweighted_block_sums(x, rate)
+    return [float('-inf')] * 2 if z is None else [gated_loudness(z[c:c + 1], rate) for c in range(2)]
 
 
 def lufs_normalize(x, sr, lufs):
@@ -129,6 +143,82 @@ def lufs_normalize(x, sr, lufs):
     peak = gain * float(stereo_stats(x.unsqueeze(0))[0, 3])
     k = gain / max(1.0, 1e-6 + peak)
     return stereo_mix(x.unsqueeze(0), [[k, 0.0, 0.0, k]])[0]
+
+
+def row_absmax(x):
+    """x float32 CUDA [R, T] -> float64 numpy [R]: max |x| per row."""
+    R, T = x.shape
+    out = torch.empty(R, dtype=torch.float64, device=x.device)
+    _cabi.check(_cabi.lib().mst_row_absmax(_cabi.ptr(x), R, T, x.stride(0), out.data_ptr(), _stream()), "row_absmax")
+    return out.cpu().numpy()
+
+
+_window_cache = {}
+
+
+def stft_mag_mean(x, n_fft=FFT_SIZE, hop=FFT_SIZE // 4):
+    """x float32 CUDA [R, T] -> float64 numpy [R, n_fft/2 + 1]: the frame-averaged magnitude of the sqrt-Hann STFT
+    (compute_stft + np.abs + np.mean, utils_data_normalization.py:74-79)."""
+    lib = _cabi.lib()
+    R, T = x.shape
+    key = (n_fft, x.device)
+    if key not in _window_cache:
+        _window_cache[key] = torch.from_numpy(np.sqrt(np.hanning(n_fft + 1)[:-1]).astype(np.float32)).to(x.device)
+    ws = torch.empty(lib.mst_stft_workspace_bytes(R, n_fft), dtype=torch.uint8, device=x.device)
+    out = torch.empty(R, n_fft // 2 + 1, dtype=torch.float64, device=x.device)
+    _cabi.check(lib.mst_stft_mag_mean(_cabi.ptr(x), R, T, x.stride(0), n_fft, hop, _cabi.ptr(_window_cache[key]), out.data_ptr(),
+                                      _cabi.ptr(ws), ws.numel(), _stream()), "stft_mag_mean")
+    return out.cpu().numpy()
+
+
+def fir_filtfilt(x, taps, scale=None):
+    """scipy.signal.filtfilt(taps[r], 1, x[r]) per row (odd padding of 3 * n_taps, float64), times scale[r], as float32.
+    x float32 CUDA [R, T]; taps float64 [R, n_taps]."""
+    lib = _cabi.lib()
+    R, T = x.shape
+    taps = np.ascontiguousarray(np.asarray(taps, dtype=np.float64).reshape(R, -1))
+    n_taps = taps.shape[1]
+    t_d = torch.from_numpy(taps).to(x.device)
+    s_d = None if scale is None else torch.from_numpy(np.asarray(scale, dtype=np.float64).reshape(R).copy()).to(x.device)
+    ws = torch.empty(lib.mst_fir_filtfilt_workspace_bytes(R, T, n_taps), dtype=torch.uint8, device=x.device)
+    y = torch.empty(R, T, dtype=torch.float32, device=x.device)
+    _cabi.check(lib.mst_fir_filtfilt(_cabi.ptr(x), R, T, x.stride(0), t_d.data_ptr(), n_taps, None if s_d is None else s_d.data_ptr(),
+                                     _cabi.ptr(y), y.stride(0), _cabi.ptr(ws), ws.numel(), _stream()), "fir_filtfilt")
+    return y
+
+
+def _amp_to_db(x):
+    return 20 * np.log10(x + 1e-30)
+
+
+def eq_matching(x, ref_spec, sr=44100, n_fft=FFT_SIZE, hop=FFT_SIZE // 4, min_db=-40, ntaps=1001, lufs=-30):
+    """get_eq_matching (utils_data_normalization.py:65-107) on both channels of x float32 CUDA [2, T] at once: each channel is
+    loudness-normalised as a mono signal (gain k, folded into the output), its averaged STFT magnitude is compared with the
+    target spectrum, the difference becomes a 1001-tap linear-phase FIR (scipy.signal.firwin2 on the host: a filter DESIGN on
+    32,769 numbers) and the channel is filtered forwards and backwards.  A channel below min_db passes through unchanged."""
+    import scipy.signal
+    peaks = row_absmax(x)
+    with np.errstate(divide='ignore'):
+        active = [_amp_to_db(float(p)) > min_db for p in peaks]
+    if not any(active):
+        return x
+    loud = integrated_loudness_per_channel(x, sr)
+    avg = stft_mag_mean(x, n_fft, hop)
+    ref_spec = np.asarray(ref_spec)
+    m = ref_spec.shape[0]
+    frq = np.arange(m) / (m / sr) / 2
+    taps = np.zeros((2, ntaps))
+    scale = np.ones(2)
+    for c in range(2):
+        if not active[c]:
+            taps[c, 0] = 1.0                         # identity: the channel is returned as it is (:104-105)
+            continue
+        gain = np.power(10.0, (lufs - loud[c]) / 20.0)
+        scale[c] = gain / np.maximum(1.0, 1e-6 + gain * peaks[c])          # fx_utils.py:229-232
+        with np.errstate(divide='ignore'):
+            diff_eq = np.sqrt(np.power(10.0, (_amp_to_db(ref_spec) - _amp_to_db(scale[c] * avg[c])) / 20))
+        taps[c] = scipy.signal.firwin2(ntaps, frq / np.max(frq), diff_eq, nfreqs=None, window='hamming', antisymmetric=False)
+    return fir_filtfilt(x, taps, scale)
 
 
 def _balance_gains(e1, e2, tgt_e1_bal, eps):
@@ -159,11 +249,11 @@ class Audio_Effects_Normalizer:
                  EFFECTS=['eq', 'compression', 'imager', 'loudness']):
         self.STEMS = STEMS          # Stems to be normalized
         self.EFFECTS = EFFECTS      # Effects to be normalized, order matters
-        unsupported = [e for e in EFFECTS if e not in ('loudness', 'imager')]
+        unsupported = [e for e in EFFECTS if e not in ('loudness', 'imager', 'eq')]
         if unsupported:
             raise NotImplementedError(
-                f"Audio_Effects_Normalizer (B200 engine): effects {unsupported} are not on the GPU yet -- 'loudness' and 'imager' are "
-                "(SURVEY.md 8f-2).  Pass normalization_order with those only, or --normalize_input False")
+                f"Audio_Effects_Normalizer (B200 engine): effects {unsupported} are not on the GPU yet -- 'loudness', 'eq' and "
+                "'imager' are (SURVEY.md 8f-2).  Pass normalization_order with those only, or --normalize_input False")
         # Audio settings
         self.SR = 44100
         self.SUBTYPE = 'PCM_16'
@@ -176,9 +266,10 @@ class Audio_Effects_Normalizer:
         self.MIN_DB = -40           # Min amplitude to apply the effects
         # Load Pre-computed Audio Effects Features
         if isinstance(precomputed_feature_path, dict):
-            self.features_mean = precomputed_feature_path
+            features_mean = {k: dict(v) for k, v in precomputed_feature_path.items()}
         else:
-            self.features_mean = np.load(precomputed_feature_path, allow_pickle='TRUE')[()]
+            features_mean = np.load(precomputed_feature_path, allow_pickle='TRUE')[()]
+        self.features_mean = self.smooth_feature(features_mean)
         self.haas_rng = np.random.RandomState()
 
     # normalize current audio input with the order of designed audio FX
@@ -207,7 +298,10 @@ class Audio_Effects_Normalizer:
         with np.errstate(divide='ignore'):
             max_db = 20 * np.log10(peak + 1e-30)
         if max_db > self.MIN_DB:
-            if effect == 'loudness':
+            if effect == 'eq':
+                track = eq_matching(track, self.features_mean[effect][src], sr=self.SR, n_fft=self.FFT_SIZE,
+                                    hop=self.HOP_LENGTH, min_db=self.MIN_DB, ntaps=self.NTAPS, lufs=self.LUFS)
+            elif effect == 'loudness':
                 track = lufs_normalize(track, self.SR, self.features_mean[effect][src])
             elif effect == 'imager':
                 # threshold of applying Haas effects
@@ -216,6 +310,18 @@ class Audio_Effects_Normalizer:
             else:
                 raise NotImplementedError(effect)
         return track[:, self.FFT_SIZE:self.FFT_SIZE + T].contiguous()
+
+    def smooth_feature(self, feature_dict_):
+        """data_normalization.py:158-175: Savitzky-Golay smoothing of the target spectra (and panning features)."""
+        import scipy.signal
+        for effect in self.EFFECTS:
+            for key in self.STEMS:
+                if effect == 'eq':
+                    f = 401 if key in ['other', 'vocals'] else 151
+                    feature_dict_[effect][key] = scipy.signal.savgol_filter(feature_dict_[effect][key], f, 1, mode='mirror')
+                elif effect == 'panning':
+                    feature_dict_[effect][key] = scipy.signal.savgol_filter(feature_dict_[effect][key], 501, 1, mode='mirror')
+        return feature_dict_
 
     def normalize_imager(self, data, target_side_mid_bal, mono_threshold, eps=1e-4):
         """normalization_imager.normalize_imager on data float32 CUDA [2, T]."""

@@ -1,8 +1,10 @@
-"""TEST INFRASTRUCTURE ONLY -- CPU (numpy / scipy float64) restatement of the input FX normaliser's loudness and imager
-effects.  Paths relative to /root/reference/mixing_style_transfer/mixing_manipulator/.
+"""TEST INFRASTRUCTURE ONLY -- CPU (numpy / scipy float64) restatement of the input FX normaliser's EQ-matching, loudness and
+imager effects.  Paths relative to /root/reference/mixing_style_transfer/mixing_manipulator/.
 
   normalize_audio / normalize_audio_per_effect   data_normalization.py:77-155   (pad by FFT_SIZE, -40 dB gate, crop)
   lufs_normalize                                  fx_utils.py:220-238
+  get_eq_matching / compute_stft                  utils_data_normalization.py:65-107, common_miscellaneous.py:50-77
+                                                  (librosa.stft underneath is third-party and absent: restated in stft())
   normalize_imager / process_balance              normalization_imager.py:22-118 (Haas branch excluded: it draws random
                                                   parameters through pymixconsole's Processor.randomize)
   Meter / loudness_gain_apply                     pyloudnorm==0.1.0 (requirements.txt:9), third-party, NOT in the reference
@@ -105,6 +107,54 @@ def lufs_normalize(x, sr, lufs):
     return y
 
 
+def sqrt_hann(n_fft):
+    return np.sqrt(np.hanning(n_fft + 1)[:-1])          # utils_data_normalization.py:77
+
+
+def stft(y, n_fft, hop_length, window):
+    """librosa.stft(y, n_fft=, hop_length=, window=, center=False) -- librosa==0.9.2 is third-party and absent: restated from
+    its documented behaviour (frames y[f*hop : f*hop + n_fft] * window, rfft, [1 + n_fft/2, n_frames], complex64 for float32
+    input and complex128 for float64)."""
+    y = np.asarray(y)
+    n_frames = 1 + (len(y) - n_fft) // hop_length
+    out = np.empty((n_fft // 2 + 1, n_frames), dtype=np.complex64 if y.dtype == np.float32 else np.complex128)
+    for f in range(n_frames):
+        out[:, f] = np.fft.rfft(window * y[f * hop_length:f * hop_length + n_fft])
+    return out
+
+
+def stft_mag_mean(x, n_fft=FFT_SIZE, hop=FFT_SIZE // 4):
+    """compute_stft (common_miscellaneous.py:50-77: complex64 storage) + np.abs + np.mean over frames
+    (utils_data_normalization.py:74-79) of a 1-D signal."""
+    n_frames = 1 + int((x.shape[0] - n_fft) / hop)
+    D = np.empty((n_frames, n_fft // 2 + 1), dtype=np.complex64)
+    D[:, :] = stft(x, n_fft, hop, sqrt_hann(n_fft)).transpose()
+    return np.mean(np.abs(D), axis=0)
+
+
+def get_eq_matching(audio_t, ref_spec, sr=SR, n_fft=FFT_SIZE, hop_length=FFT_SIZE // 4, min_db=MIN_DB, ntaps=1001, lufs=-30):
+    """utils_data_normalization.py:65-107 on one channel (1-D)."""
+    audio_t = np.copy(audio_t)
+    with np.errstate(divide='ignore'):
+        max_db = 20 * np.log10(np.max(np.abs(audio_t)) + 1e-30)
+    if not max_db > min_db:
+        return audio_t
+    audio_t = lufs_normalize(audio_t, sr, lufs)
+    avg = stft_mag_mean(audio_t, n_fft, hop_length)
+    m = ref_spec.shape[0]
+    frq = np.arange(m) / (m / sr) / 2
+    with np.errstate(divide='ignore'):
+        diff_eq = (20 * np.log10(ref_spec + 1e-30)) - (20 * np.log10(avg + 1e-30))
+    diff_eq = np.sqrt(10 ** (diff_eq / 20))
+    taps = scipy.signal.firwin2(ntaps, frq / np.max(frq), diff_eq, nfreqs=None, window='hamming', antisymmetric=False)
+    return scipy.signal.filtfilt(taps, 1, audio_t, axis=-1, padtype='odd', padlen=None, method='pad', irlen=None)
+
+
+def smooth_eq_feature(ref_spec, src):
+    """Audio_Effects_Normalizer.smooth_feature for 'eq' (data_normalization.py:158-170)."""
+    return scipy.signal.savgol_filter(ref_spec, 401 if src in ('other', 'vocals') else 151, 1, mode='mirror')
+
+
 def process_balance(d1, d2, tgt_e1_bal=0.5, eps=1e-04):
     """normalization_imager.py:84-99."""
     e1, e2 = np.sum(d1 ** 2), np.sum(d2 ** 2)
@@ -135,14 +185,18 @@ def normalize_imager(data, target_side_mid_bal=0.9, mono_threshold=0.95, eps=1e-
 
 
 def normalize_audio_per_effect(audio, effect, feature, src="drums"):
-    """data_normalization.py:88-155 for effect in ('loudness', 'imager').  audio: [n, 2]; feature = features_mean[effect][src]."""
+    """data_normalization.py:88-155 for effect in ('eq', 'loudness', 'imager').  audio: [n, 2]; feature = features_mean[effect][src]
+    as the normaliser holds it after smooth_feature."""
     audio = audio.astype(np.float32)
     track = np.pad(audio, ((FFT_SIZE, FFT_SIZE), (0, 0)), mode='constant')
     out = track.copy()
     with np.errstate(divide='ignore'):
         max_db = 20.0 * np.log10(np.max(np.abs(out)) + 1e-30)       # amp_to_db, utils_data_normalization.py:35-36
     if max_db > MIN_DB:
-        if effect == 'loudness':
+        if effect == 'eq':
+            for ch in range(out.shape[1]):        # feature = the SMOOTHED target spectrum (smooth_eq_feature)
+                np.copyto(out[:, ch], get_eq_matching(out[:, ch], feature), casting='same_kind')
+        elif effect == 'loudness':
             out = lufs_normalize(out, SR, feature)
         elif effect == 'imager':
             np.copyto(out, normalize_imager(out, target_side_mid_bal=feature,

@@ -9,8 +9,20 @@ from gpu_helpers import err_stats
 from oracle import fixtures, norm_oracle as N
 
 pytestmark = pytest.mark.gpu
+def _target_spectrum(seed):
+    """A plausible averaged-magnitude target (the reference's lives in weights/*.npy, absent on the GPU box): pink-ish slope
+    with a few broad resonances, float32 [32769] like features_mean['eq'][stem]."""
+    f = np.arange(32769) / 32768.0
+    r = np.random.RandomState(seed)
+    s = 30.0 / (1.0 + 200.0 * f) + 0.02
+    for _ in range(4):
+        s *= 1.0 + 0.8 * np.exp(-0.5 * ((f - r.uniform(0.02, 0.6)) / r.uniform(0.01, 0.1)) ** 2)
+    return (s * (1.0 + 0.05 * r.randn(32769))).astype(np.float32)
+
+
 FEATS = {"loudness": {"drums": np.array([-28.9674596]), "bass": np.array([-24.37411392])},
-         "imager": {"drums": np.float32(0.94471526), "bass": np.float32(0.9816045)}}
+         "imager": {"drums": np.float32(0.94471526), "bass": np.float32(0.9816045)},
+         "eq": {"drums": _target_spectrum(1), "bass": _target_spectrum(2)}}
 
 
 def _stem(n=60000, wide=True):
@@ -37,12 +49,51 @@ def test_stereo_building_blocks():
         assert np.abs(y - N.haas_process(x, delay, np.float32(0.4), ch)).max() <= 1e-7, (delay, ch)
 
 
-@pytest.mark.parametrize("order", [['loudness'], ['imager'], ['loudness', 'imager', 'loudness']])
+def test_stft_mag_mean_matches_oracle():
+    """Four-step FFT (256 x N2) + pair packing against numpy's rfft: the reference's frame size (65,536 / 16,384), a small one
+    (N2 = 8), an odd number of signals."""
+    from music_mixing_style_transfer_b200.mixing_manipulator import data_normalization as dn
+    x = _stem(65536)
+    sig = np.ascontiguousarray(np.concatenate([x.T, x.T[::-1] * 0.5, x.T[:1] * 2.0], axis=0))      # [5, 65536]
+    sig = np.concatenate([sig, sig[:, ::-1], sig * 0.3, sig], axis=1)[:, :250001]
+    xt = torch.from_numpy(sig).cuda()
+    for n_fft, hop, rows in ((65536, 16384, 2), (65536, 16384, 5), (2048, 1024, 3), (1024, 300, 1)):
+        got = dn.stft_mag_mean(xt[:rows], n_fft, hop)
+        for r in range(rows):
+            ref = N.stft_mag_mean(sig[r], n_fft, hop).astype(np.float64)
+            assert got.shape == (rows, n_fft // 2 + 1)
+            # float32 transform of 2^16 points: ~1e-6 of the spectrum's scale
+            assert np.abs(got[r] - ref).max() <= 2e-6 * ref.max() + 1e-9, (n_fft, r, np.abs(got[r] - ref).max(), ref.max())
+
+
+def test_fir_filtfilt_matches_scipy():
+    import scipy.signal
+    from music_mixing_style_transfer_b200.mixing_manipulator import data_normalization as dn
+    x = _stem(65536)
+    sig = np.ascontiguousarray(np.concatenate([x.T, x.T[::-1]], axis=1)[:, :100003])                # odd length
+    sig[:, 0] += 0.2; sig[1, -1] -= 0.3                                                            # non-zero ends: the odd extension matters
+    xt = torch.from_numpy(sig).cuda()
+    r = np.random.RandomState(0)
+    for n_taps in (1001, 101, 8, 1):
+        taps = r.randn(2, n_taps) / np.sqrt(n_taps)
+        scale = np.array([0.7, 1.9])
+        got = dn.fir_filtfilt(xt, taps, scale).cpu().numpy()
+        for c in range(2):
+            ref = scale[c] * scipy.signal.filtfilt(taps[c], 1, sig[c].astype(np.float64))
+            assert np.abs(got[c] - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max()), (n_taps, c, np.abs(got[c] - ref).max())
+    with pytest.raises(RuntimeError):
+        dn.fir_filtfilt(xt[:, :3000], r.randn(2, 1001))                                            # scipy: ValueError, padlen >= length
+    assert dn.row_absmax(xt).tolist() == np.abs(sig).max(axis=1).astype(np.float64).tolist()
+
+
+@pytest.mark.parametrize("order", [['loudness'], ['imager'], ['eq'], ['loudness', 'imager', 'loudness'],
+                                   ['loudness', 'eq', 'imager', 'loudness']])
 def test_normalizer_matches_oracle(order):
     from music_mixing_style_transfer_b200.mixing_manipulator import Audio_Effects_Normalizer
     x = _stem()
     norm = Audio_Effects_Normalizer(FEATS, STEMS=['drums', 'bass'], EFFECTS=order)
-    ref = N.normalize_audio(x.copy(), order, FEATS, src='drums')
+    feats = dict(FEATS, eq={k: N.smooth_eq_feature(v, k) for k, v in FEATS["eq"].items()})
+    ref = N.normalize_audio(x.copy(), order, feats, src='drums')
     got_np = norm.normalize_audio(x.copy(), src='drums')                            # the reference's call: numpy [n, 2]
     got_t = norm.normalize_audio(torch.from_numpy(np.ascontiguousarray(x.T)).cuda(), src='drums')   # the engine's call
     assert got_np.shape == ref.shape and np.array_equal(got_np, got_t.cpu().numpy().T)
@@ -64,7 +115,15 @@ def test_normalizer_gates_and_haas_branch():
     bal = np.sum(mid ** 2) / (np.sum(mid ** 2) + np.sum(side ** 2))
     assert np.isfinite(y).all() and abs(bal - float(FEATS["imager"]["drums"])) < 2e-2, bal
     with pytest.raises(NotImplementedError):
-        Audio_Effects_Normalizer(FEATS, EFFECTS=['loudness', 'eq'])
+        Audio_Effects_Normalizer(FEATS, EFFECTS=['loudness', 'compression'])
+    # EQ matching: a silent channel passes through untouched, the other one is matched (utils_data_normalization.py:69-70, 104-105)
+    norm = Audio_Effects_Normalizer(FEATS, STEMS=['drums', 'bass'], EFFECTS=['eq'])
+    half = _stem(30000)
+    half[:, 1] = 0.0
+    y = norm.normalize_audio(half.copy(), src='bass')
+    feats = {"eq": {"bass": N.smooth_eq_feature(FEATS["eq"]["bass"], 'bass')}}
+    ref = N.normalize_audio(half.copy(), ['eq'], feats, src='bass')
+    assert np.array_equal(y[:, 1], half[:, 1]) and np.abs(y[:, 0] - ref[:, 0]).max() <= 2e-5 * np.abs(ref).max()
 
 
 def test_panner_and_haas_processors_in_a_chain():

@@ -192,3 +192,32 @@ def test_normalizer_oracle_equals_reference_code(tmp_path):
     ref = norm.normalize_audio(x.copy(), src='drums')
     got = N.normalize_audio(x.copy(), order, feats, src='drums')
     assert ref.shape == got.shape and np.abs(got - ref).max() <= 1e-7
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree not present (GPU box)")
+def test_eq_matching_oracle_equals_reference_code(tmp_path, monkeypatch):
+    """oracle/norm_oracle.get_eq_matching and the 'eq' effect of normalize_audio against the reference's own get_eq_matching /
+    Audio_Effects_Normalizer on a real stem window and the reference's own target spectra (weights/*.npy).  librosa.stft and
+    the BS.1770 meter are restated third-party code on both sides (unpinned); firwin2 / filtfilt / savgol are the real scipy.
+    scipy >= 1.12 no longer accepts the `nyq=None` keyword the reference passes to firwin2: it is dropped by a wrapper."""
+    import scipy.signal
+    from oracle import norm_oracle as N
+    dn, fx_utils, nimg = ref_import.import_reference_normalizer()
+    import utils_data_normalization as udn
+    real_firwin2 = scipy.signal.firwin2
+    monkeypatch.setattr(scipy.signal, "firwin2", lambda *a, nyq=None, **k: real_firwin2(*a, **k))
+    feats = np.load(os.path.join(ref_import.REFERENCE_ROOT, "weights", "musdb18_fxfeatures_eqcompimagegain.npy"), allow_pickle=True)[()]
+    g = fixtures.load_golden("real_audio.npz")
+    x = (g["x_drums"].astype(np.float64) / 32768.0).astype(np.float32)[:40000]
+    spec = N.smooth_eq_feature(feats['eq']['drums'], 'drums')
+    xs = np.pad(x[:, 0], (65536, 65536))
+    ref = udn.get_eq_matching(xs, spec, sr=44100, n_fft=65536, hop_length=16384, min_db=-40, ntaps=1001, lufs=-30)
+    assert np.abs(N.get_eq_matching(xs, spec) - ref).max() <= 1e-12
+    assert np.array_equal(N.get_eq_matching(xs * 1e-4, spec), xs * 1e-4)                 # below min_db: untouched
+    sub = {"eq": {"drums": feats['eq']['drums'].copy()}, "loudness": {"drums": feats['loudness']['drums']}}
+    np.save(tmp_path / "feats.npy", sub, allow_pickle=True)
+    order = ['loudness', 'eq', 'loudness']
+    norm = dn.Audio_Effects_Normalizer(str(tmp_path / "feats.npy"), STEMS=['drums'], EFFECTS=order)
+    ref = norm.normalize_audio(x.copy(), src='drums')
+    got = N.normalize_audio(x.copy(), order, {"eq": {"drums": spec}, "loudness": sub["loudness"]}, src='drums')
+    assert ref.shape == got.shape and np.abs(got - ref).max() <= 1e-7
