@@ -28,8 +28,9 @@
     `--batch_size` therefore only carries its reference semantics (the interpolation weight index) -- not memory, not speed.
 
     Outside this engine (raise, never silently skipped): the demucs subprocess (:77-90; pass --do_not_separate True with
-    stems already separated) and the normalisation effects that mixing_manipulator/data_normalization.py does not yet run
-    on the GPU (see Audio_Effects_Normalizer there).  CUDA only.
+    stems already separated).  All four normalisation effects run through mixing_manipulator/data_normalization.py; the
+    'compression' effect needs the third-party `aubio` onset detector on the host exactly like the reference, and raises
+    with that message when the package is missing.  CUDA only.
 """
 import os
 import queue

@@ -8,9 +8,12 @@
                 relative gates), gain to the stem's target LUFS, then division by max(1, peak)
     'imager'    normalize_imager (normalization_imager.py:22-81): mid/side balance to the stem's target, left/right balance
                 50-50, mid/side balance again; a Haas effect first when the stem is almost mono
-    'eq', 'compression': NOT on the GPU yet -> NotImplementedError (EQ matching = 65,536-point STFT average -> firwin2 ->
-                filtfilt, utils_data_normalization.py:65-107; compression matching = a data-dependent search over aubio onsets,
-                :357-429, which SURVEY.md leaves on the CPU)
+    'eq'        get_eq_matching (utils_data_normalization.py:65-107): per channel, mono loudness normalisation to -30 LUFS,
+                65,536-point sqrt-Hann STFT averaged over frames (csrc/spectral.cu), difference to the stem's target spectrum
+                -> scipy.signal.firwin2 (1001 taps, host) -> zero-phase filtering (mst_fir_filtfilt, float64)
+    'compression' get_comp_matching (:357-429): peak-normalise to -10 dB, mean inter-onset peak (onset detector = aubio, a
+                third-party package, on the host), then a (ratio, threshold) grid of compressor runs -- those are the FX chain's
+                compressor kernel, several thresholds per launch -- until the peak falls into the stem's target band
 
 Device work per effect: one reduction pass (mst_stereo_stats, and for loudness mst_biquad_cascade + mst_block_energy), a few
 dozen float64 operations on the host with the reference's own formulas, one 2x2 mix pass (mst_stereo_mix).  The three
@@ -221,6 +224,106 @@ def eq_matching(x, ref_spec, sr=44100, n_fft=FFT_SIZE, hop=FFT_SIZE // 4, min_db
     return fir_filtfilt(x, taps, scale)
 
 
+def aubio_onsets(x, sr=44100, window=1024):
+    """Onset positions (samples) of a 1-D float signal from aubio's 'hfc' detector, driven as get_mean_peak drives it
+    (utils_data_normalization.py:302-312): float32 frames of `window` samples, hop = window.  aubio is a third-party C library
+    the reference depends on (requirements.txt); it is imported here on first use."""
+    try:
+        import aubio
+    except ImportError as e:
+        raise NotImplementedError(
+            "the 'compression' effect of the input FX normaliser needs the `aubio` package for its onset detection "
+            "(utils_data_normalization.py:302), as in the reference; install it, pass onset_detector=..., or leave "
+            "'compression' out of normalization_order") from e
+    onset_func = aubio.onset('hfc', buf_size=window, hop_size=window, samplerate=sr)
+    x = np.ascontiguousarray(x)
+    frames = np.float32(np.lib.stride_tricks.sliding_window_view(x, window)[::window])
+    return [onset_func.get_last() for frame in frames if onset_func(frame)]
+
+
+def mean_peak(x, onset_fn, sr=44100, percentile=75):
+    """get_mean_peak (utils_data_normalization.py:284-337, true_peak=False) of a 1-D host signal: the largest |x| between
+    consecutive onsets, in dB; mean and std of the values above the percentile.  None when there is no onset."""
+    onset_times = onset_fn(x, sr, 2 ** 10)
+    if not onset_times:
+        return None
+    a = np.abs(x)
+    bounds = list(onset_times) + [len(x)]
+    samples = [bounds[i] + int(np.argmax(a[bounds[i]:bounds[i + 1]])) for i in range(len(onset_times))]
+    p_value = np.array([_amp_to_db(a[p]) for p in samples])
+    top = p_value[p_value > np.percentile(p_value, percentile)]
+    sel = top if len(top) else p_value
+    return float(np.mean(sel)), float(np.std(sel))
+
+
+def comp_matching(x, ref_peak, ref_std, ratio, attack, release, onset_fn, sr=44100, min_db=-40, comp_peak_norm=-10.0, min_th=-40,
+                  max_ratio=20, percentile=75, chunk=8):
+    """get_comp_matching (utils_data_normalization.py:357-429, expander off) for both channels of x float32 CUDA [2, T].
+    The reference searches each channel on its own: peak-normalise to -10 dB, measure the mean inter-onset peak, and if it lies
+    above the target band walk a (ratio, threshold) grid -- up to 15 x 61 compressor runs over the whole stem, each followed by
+    the onset detector -- until the peak drops into the band.  Here the compressor runs are the FX chain's compressor kernel on
+    the GPU, `chunk` thresholds per launch with both channels in lockstep (the candidate order is the same for both; each
+    channel keeps the output of ITS first accepted candidate); the onset detection and the few dozen scalars per candidate stay
+    on the host, as in the reference.  A channel whose measurement fails (no onset) stops the loop over channels like the
+    reference's `except: break` (data_normalization.py:137-138): it and the following channel are returned untouched."""
+    from .common_audioeffects import FX_COMP, N_PARAMS, fx_chain_forward
+    T = x.shape[-1]
+    peaks = row_absmax(x)
+    out = x.clone()
+    xn = torch.empty_like(x)
+    todo = []
+    for c in range(2):
+        with np.errstate(divide='ignore'):
+            if not _amp_to_db(float(peaks[c])) > min_db:
+                continue                                      # below min_db: the channel is returned as it is (:428-429)
+        k = np.power(10.0, comp_peak_norm / 20.0) / peaks[c]   # pyloudnorm.normalize.peak (:374)
+        xn[c] = stereo_mix(x[c].reshape(1, 1, T).expand(1, 2, T).contiguous(), [[k, 0.0, 0.0, k]])[0, 0]
+        m = mean_peak(xn[c].cpu().numpy(), onset_fn, sr, percentile)
+        if m is None:
+            break                                             # TypeError in the reference -> `except: break`
+        out[c] = xn[c]
+        if m[0] >= ref_peak + ref_std:
+            todo.append(c)                                    # downward compression needed (:382)
+        # inside the band, or below it with the expander off: the peak-normalised channel (:379-380, :425-426)
+    if not todo:
+        return out
+    ratios = np.linspace(ratio, max_ratio, max_ratio - ratio + 1)
+    ths = np.linspace(-1 - 9, min_th, 2 * np.abs(min_th) - 1 - 18)
+    cands = [(rt, th) for rt in ratios for th in ths]
+    src = torch.stack([xn[todo[0]], xn[todo[-1]]])            # one or two channels to search, as the (L, R) of a segment
+    pending = set(todo)
+    last = None
+    for i0 in range(0, len(cands), chunk):
+        part = cands[i0:i0 + chunk]
+        P = np.zeros((len(part), N_PARAMS), np.float32)
+        P[:, 13] = [th for _, th in part]
+        P[:, 14], P[:, 15] = attack, release
+        P[:, 16] = [rt for rt, _ in part]
+        y = fx_chain_forward(src.unsqueeze(0).expand(len(part), 2, T).contiguous(), torch.from_numpy(P).to(x.device), FX_COMP, float(sr))
+        # ratio > 1: the gain 10^(-y_l / 20) never exceeds 1 and |xn| <= 10^(-10/20), so the reference's clip to +-1 (:349-350) is idle
+        y_host = y.cpu().numpy()
+        for j in range(len(part)):
+            for c in sorted(pending):
+                row = 0 if c == todo[0] else 1
+                m = mean_peak(y_host[j, row], onset_fn, sr, percentile)
+                if m is None:
+                    # the reference raises here and its caller breaks out of the channel loop: this channel keeps what it had
+                    # before the effect, and so does every later channel
+                    for cc in range(c, 2):
+                        out[cc] = x[cc]
+                    pending = {p for p in pending if p < c}
+                    break
+                if m[0] < ref_peak + ref_std:
+                    out[c] = y[j, row]
+                    pending.discard(c)
+            if not pending:
+                return out
+        last = y[len(part) - 1]
+    for c in pending:                                          # grid exhausted: the last candidate's output (:399)
+        out[c] = last[0 if c == todo[0] else 1]
+    return out
+
+
 def _balance_gains(e1, e2, tgt_e1_bal, eps):
     """process_balance (normalization_imager.py:84-99) on energies: gains for the two signals."""
     total = e1 + e2
@@ -246,14 +349,14 @@ def imager_matrix(ll, rr, lr, target_side_mid_bal, eps=1e-4):
 
 class Audio_Effects_Normalizer:
     def __init__(self, precomputed_feature_path, STEMS=['drums', 'bass', 'other', 'vocals'],
-                 EFFECTS=['eq', 'compression', 'imager', 'loudness']):
+                 EFFECTS=['eq', 'compression', 'imager', 'loudness'], onset_detector=None):
         self.STEMS = STEMS          # Stems to be normalized
         self.EFFECTS = EFFECTS      # Effects to be normalized, order matters
-        unsupported = [e for e in EFFECTS if e not in ('loudness', 'imager', 'eq')]
+        unsupported = [e for e in EFFECTS if e not in ('loudness', 'imager', 'eq', 'compression')]
         if unsupported:
             raise NotImplementedError(
-                f"Audio_Effects_Normalizer (B200 engine): effects {unsupported} are not on the GPU yet -- 'loudness', 'eq' and "
-                "'imager' are (SURVEY.md 8f-2).  Pass normalization_order with those only, or --normalize_input False")
+                f"Audio_Effects_Normalizer: unknown effects {unsupported} (the reference knows 'eq', 'compression', 'imager', "
+                "'loudness'; data_normalization.py:22)")
         # Audio settings
         self.SR = 44100
         self.SUBTYPE = 'PCM_16'
@@ -264,6 +367,15 @@ class Audio_Effects_Normalizer:
         self.NTAPS = 1001
         self.LUFS = -30
         self.MIN_DB = -40           # Min amplitude to apply the effects
+        # Compressor (data_normalization.py:39-72): attack ms, release ms, starting ratio per stem
+        self.COMP_PEAK_NORM = -10.0
+        self.COMP_PERCENTILE = 75
+        self.COMP_MIN_TH = -40
+        self.COMP_MAX_RATIO = 20
+        self.comp_settings = {'vocals': {'attack': 7.5, 'release': 400.0, 'ratio': 4}, 'drums': {'attack': 10.0, 'release': 180.0, 'ratio': 6},
+                              'bass': {'attack': 10.0, 'release': 500.0, 'ratio': 5}, 'other': {'attack': 15.0, 'release': 666.0, 'ratio': 4}}
+        # onset detector of the compressor matching: callable (x 1-D numpy, sr, window) -> onset sample positions; aubio's 'hfc' by default
+        self.onset_detector = onset_detector if onset_detector is not None else aubio_onsets
         # Load Pre-computed Audio Effects Features
         if isinstance(precomputed_feature_path, dict):
             features_mean = {k: dict(v) for k, v in precomputed_feature_path.items()}
@@ -301,6 +413,13 @@ class Audio_Effects_Normalizer:
             if effect == 'eq':
                 track = eq_matching(track, self.features_mean[effect][src], sr=self.SR, n_fft=self.FFT_SIZE,
                                     hop=self.HOP_LENGTH, min_db=self.MIN_DB, ntaps=self.NTAPS, lufs=self.LUFS)
+            elif effect == 'compression':
+                feat = self.features_mean[effect][src]
+                assert len(feat) == 2
+                cs = self.comp_settings[src]
+                track = comp_matching(track, float(feat[0]), float(feat[1]), cs['ratio'], cs['attack'], cs['release'],
+                                      self.onset_detector, sr=self.SR, min_db=self.MIN_DB, comp_peak_norm=self.COMP_PEAK_NORM,
+                                      min_th=self.COMP_MIN_TH, max_ratio=self.COMP_MAX_RATIO, percentile=self.COMP_PERCENTILE)
             elif effect == 'loudness':
                 track = lufs_normalize(track, self.SR, self.features_mean[effect][src])
             elif effect == 'imager':

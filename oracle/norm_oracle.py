@@ -155,6 +155,84 @@ def smooth_eq_feature(ref_spec, src):
     return scipy.signal.savgol_filter(ref_spec, 401 if src in ('other', 'vocals') else 151, 1, mode='mirror')
 
 
+def stub_onsets(x, sr=SR, window=1024):
+    """Onset positions (samples) of a 1-D signal under the rule of oracle/shims/aubio (NOT aubio's detector), driven exactly as
+    get_mean_peak drives aubio (utils_data_normalization.py:302-312): float32 frames of `window` samples, hop = window."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("_mst_aubio_stub", os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims", "aubio", "__init__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    o = mod.onset('hfc', buf_size=window, hop_size=window, samplerate=sr)
+    frames = np.float32(np.lib.stride_tricks.sliding_window_view(np.asarray(x), window)[::window])
+    return [o.get_last() for fr in frames if o(fr)]
+
+
+def get_mean_peak(audio, onset_fn=stub_onsets, sr=SR, percentile=75):
+    """utils_data_normalization.py:284-337 (true_peak=False): mean / std in dB of the inter-onset peaks above the percentile."""
+    peak, std = [], []
+    for ch in range(audio.shape[-1]):
+        x = np.ascontiguousarray(audio[:, ch])
+        onset_times = onset_fn(x, sr, 2 ** 10)
+        samples = []
+        if onset_times:
+            for i in range(len(onset_times) - 1):
+                samples.append(onset_times[i] + np.argmax(np.abs(x[onset_times[i]:onset_times[i + 1]])))
+            samples.append(onset_times[-1] + np.argmax(np.abs(x[onset_times[-1]:])))
+        p_value = [20 * np.log10(np.abs(x[p]) + 1e-30) for p in samples]
+        p_value_ = [p for p in p_value if p > np.percentile(p_value, percentile)]
+        if p_value_:
+            peak.append(np.mean(p_value_)); std.append(np.std(p_value_))
+        elif p_value:
+            peak.append(np.mean(p_value)); std.append(np.std(p_value))
+        else:
+            return None
+    return [np.mean(peak), np.mean(std)]
+
+
+def get_comp_matching(audio, ref_peak, ref_std, ratio, attack, release, onset_fn=stub_onsets, sr=SR, min_db=MIN_DB,
+                      comp_peak_norm=-10.0, min_th=-40, max_ratio=20, percentile=75, expander=False):
+    """utils_data_normalization.py:357-429 on one channel (1-D in, [n, 1] out).  The compressor is oracle/fx_oracle's (pinned to
+    the reference's numba code); pyloudnorm.normalize.peak is restated (gain = 10^(target/20) / max|x|)."""
+    from oracle import fx_oracle
+    x = audio.copy()
+    if x.ndim < 2:
+        x = np.expand_dims(x, 1)
+    with np.errstate(divide='ignore'):
+        max_db = 20 * np.log10(np.max(np.abs(x)) + 1e-30)
+    if not max_db > min_db:
+        return x
+    x = (np.power(10.0, comp_peak_norm / 20.0) / np.max(np.abs(x))) * x
+    peak, std = get_mean_peak(x, onset_fn, sr, percentile)            # None -> TypeError, like the reference
+    if ref_peak - ref_std < peak < ref_peak + ref_std:
+        return x
+    if peak > (ref_peak - ref_std):
+        ratios = np.linspace(ratio, max_ratio, max_ratio - ratio + 1)
+        ths = np.linspace(-1 - 9, min_th, 2 * np.abs(min_th) - 1 - 18)
+        y = x
+        for rt in ratios:
+            done = False
+            for th in ths:
+                p = np.zeros(20)
+                p[13], p[14], p[15], p[16] = th, attack, release, rt
+                y = fx_oracle.compressor(x, p, sr)
+                if np.max(np.abs(y)) >= 1.0:
+                    y = np.clip(y, -1.0, 1.0)
+                peak, std = get_mean_peak(y, onset_fn, sr, percentile)
+                if peak < (ref_peak + ref_std):
+                    done = True
+                    break
+            if done:
+                break
+        return y
+    if expander:
+        raise NotImplementedError("COMP_USE_EXPANDER is False in the reference (data_normalization.py:40)")
+    return x
+
+
+COMP_SETTINGS = {'vocals': (7.5, 400.0, 4), 'drums': (10.0, 180.0, 6), 'bass': (10.0, 500.0, 5), 'other': (15.0, 666.0, 4)}   # data_normalization.py:47-71
+
+
 def process_balance(d1, d2, tgt_e1_bal=0.5, eps=1e-04):
     """normalization_imager.py:84-99."""
     e1, e2 = np.sum(d1 ** 2), np.sum(d2 ** 2)
@@ -184,7 +262,7 @@ def normalize_imager(data, target_side_mid_bal=0.9, mono_threshold=0.95, eps=1e-
     return np.stack([(mid + side) / 2, (mid - side) / 2], 1)
 
 
-def normalize_audio_per_effect(audio, effect, feature, src="drums"):
+def normalize_audio_per_effect(audio, effect, feature, src="drums", onset_fn=stub_onsets):
     """data_normalization.py:88-155 for effect in ('eq', 'loudness', 'imager').  audio: [n, 2]; feature = features_mean[effect][src]
     as the normaliser holds it after smooth_feature."""
     audio = audio.astype(np.float32)
@@ -196,6 +274,14 @@ def normalize_audio_per_effect(audio, effect, feature, src="drums"):
         if effect == 'eq':
             for ch in range(out.shape[1]):        # feature = the SMOOTHED target spectrum (smooth_eq_feature)
                 np.copyto(out[:, ch], get_eq_matching(out[:, ch], feature), casting='same_kind')
+        elif effect == 'compression':
+            att, rel, ratio = COMP_SETTINGS[src]
+            for ch in range(out.shape[1]):
+                try:
+                    y = get_comp_matching(out[:, ch], feature[0], feature[1], ratio, att, rel, onset_fn=onset_fn)
+                    np.copyto(out[:, ch], y[:, 0], casting='same_kind')
+                except Exception:          # the reference's bare `except: break` (data_normalization.py:137-138)
+                    break
         elif effect == 'loudness':
             out = lufs_normalize(out, SR, feature)
         elif effect == 'imager':
@@ -206,11 +292,11 @@ def normalize_audio_per_effect(audio, effect, feature, src="drums"):
     return out[FFT_SIZE:FFT_SIZE + audio.shape[0]]
 
 
-def normalize_audio(audio, effects, features, src="drums"):
+def normalize_audio(audio, effects, features, src="drums", onset_fn=stub_onsets):
     """data_normalization.py:77-85."""
     y = audio
     for e in effects:
-        y = normalize_audio_per_effect(y, e, features[e][src], src)
+        y = normalize_audio_per_effect(y, e, features[e][src], src, onset_fn)
     return y
 
 

@@ -22,7 +22,8 @@ def _target_spectrum(seed):
 
 FEATS = {"loudness": {"drums": np.array([-28.9674596]), "bass": np.array([-24.37411392])},
          "imager": {"drums": np.float32(0.94471526), "bass": np.float32(0.9816045)},
-         "eq": {"drums": _target_spectrum(1), "bass": _target_spectrum(2)}}
+         "eq": {"drums": _target_spectrum(1), "bass": _target_spectrum(2)},
+         "compression": {"drums": np.array([-13.53084647, 1.12951587]), "bass": np.array([-5.0, 1.0])}}
 
 
 def _stem(n=60000, wide=True):
@@ -102,6 +103,35 @@ def test_normalizer_matches_oracle(order):
     assert e["rel"] <= 2e-5 and e["max"] <= 2e-5 * max(1.0, np.abs(ref).max()), (order, e)
 
 
+@pytest.mark.parametrize("src", ['drums', 'bass'])
+def test_compression_matching_matches_oracle(src):
+    """The (ratio, threshold) search of get_comp_matching with the compressor runs on the GPU.  aubio is absent here and on the
+    GPU box: product and oracle are both driven by the stand-in detector of oracle/shims/aubio (norm_oracle.stub_onsets), the
+    one the reference's own get_comp_matching is pinned with in tests/test_oracle_pinned.py.  'drums' target: the search
+    accepts a candidate after a few compressor runs; 'bass' target (-5 dB): the peak is below the band, the channel is only
+    peak-normalised."""
+    from music_mixing_style_transfer_b200.mixing_manipulator import Audio_Effects_Normalizer
+    x = _stem(50000)
+    x[:, 1] *= 0.5
+    norm = Audio_Effects_Normalizer(FEATS, STEMS=['drums', 'bass'], EFFECTS=['compression'], onset_detector=N.stub_onsets)
+    got = norm.normalize_audio(x.copy(), src=src)
+    ref = N.normalize_audio(x.copy(), ['compression'], FEATS, src=src, onset_fn=N.stub_onsets)
+    e = err_stats(got.T, np.asarray(ref, np.float64).T)
+    assert got.shape == ref.shape and e["rel"] <= 2e-5 and e["max"] <= 2e-5, (src, e)
+    if src == 'drums':
+        k = 10 ** (-10.0 / 20) / np.abs(x[:, 0]).max()
+        assert np.abs(ref[:, 0] - k * x[:, 0]).max() > 1e-2          # the search really compressed
+    # no onset anywhere -> the reference's `except: break`: both channels come back untouched
+    norm.onset_detector = lambda sig, sr, window: []
+    assert np.array_equal(norm.normalize_audio(x.copy(), src='drums'), x)
+    # without aubio and without an injected detector the effect raises with the reason
+    try:
+        import aubio  # noqa: F401
+    except ImportError:
+        with pytest.raises(NotImplementedError):
+            Audio_Effects_Normalizer(FEATS, STEMS=['drums'], EFFECTS=['compression']).normalize_audio(x.copy(), src='drums')
+
+
 def test_normalizer_gates_and_haas_branch():
     from music_mixing_style_transfer_b200.mixing_manipulator import Audio_Effects_Normalizer
     norm = Audio_Effects_Normalizer(FEATS, STEMS=['drums', 'bass'], EFFECTS=['imager'])
@@ -115,7 +145,7 @@ def test_normalizer_gates_and_haas_branch():
     bal = np.sum(mid ** 2) / (np.sum(mid ** 2) + np.sum(side ** 2))
     assert np.isfinite(y).all() and abs(bal - float(FEATS["imager"]["drums"])) < 2e-2, bal
     with pytest.raises(NotImplementedError):
-        Audio_Effects_Normalizer(FEATS, EFFECTS=['loudness', 'compression'])
+        Audio_Effects_Normalizer(FEATS, EFFECTS=['loudness', 'panning'])
     # EQ matching: a silent channel passes through untouched, the other one is matched (utils_data_normalization.py:69-70, 104-105)
     norm = Audio_Effects_Normalizer(FEATS, STEMS=['drums', 'bass'], EFFECTS=['eq'])
     half = _stem(30000)

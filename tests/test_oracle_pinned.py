@@ -221,3 +221,33 @@ def test_eq_matching_oracle_equals_reference_code(tmp_path, monkeypatch):
     ref = norm.normalize_audio(x.copy(), src='drums')
     got = N.normalize_audio(x.copy(), order, {"eq": {"drums": spec}, "loudness": sub["loudness"]}, src='drums')
     assert ref.shape == got.shape and np.abs(got - ref).max() <= 1e-7
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="reference tree not present (GPU box)")
+def test_comp_matching_oracle_equals_reference_code(tmp_path):
+    """oracle/norm_oracle.get_comp_matching / get_mean_peak against the reference's own functions (the reference's numba
+    compressor, its search loops and break conditions) on a real drum stem.  aubio (third-party C library, absent) is the
+    stand-in detector of oracle/shims/aubio on both sides, pyloudnorm.normalize.peak the restated one-liner."""
+    from oracle import norm_oracle as N
+    dn, fx_utils, nimg = ref_import.import_reference_normalizer()
+    import utils_data_normalization as udn
+    g = fixtures.load_golden("real_audio.npz")
+    x = (g["x_drums"].astype(np.float64) / 32768.0).astype(np.float32)[:40000]
+    xs = np.pad(x[:, 0], (65536, 65536))
+    k = 10 ** (-10.0 / 20) / np.abs(xs).max()
+    assert np.allclose(udn.get_mean_peak((k * xs)[:, None], 44100, n_mels=128, true_peak=False, percentile=75),
+                       N.get_mean_peak((k * xs)[:, None]), rtol=0, atol=1e-12)
+    for ref_peak, ref_std, changed in ((-13.53084647, 1.12951587, True), (-5.0, 1.0, False), (-10.3, 0.5, False)):
+        ref = udn.get_comp_matching(xs, ref_peak, ref_std, 6, 10.0, 180.0, sr=44100, min_db=-40, min_th=-40, comp_peak_norm=-10.0,
+                                    max_ratio=20, n_mels=128, true_peak=False, percentile=75, expander=False)
+        got = N.get_comp_matching(xs, ref_peak, ref_std, 6, 10.0, 180.0)
+        assert ref.shape == got.shape and np.abs(ref - got).max() <= 1e-7
+        assert (np.abs(ref[:, 0] - k * xs).max() > 1e-3) == changed
+    feats = {"compression": {"drums": np.array([-13.53084647, 1.12951587])}}
+    np.save(tmp_path / "feats.npy", feats, allow_pickle=True)
+    norm = dn.Audio_Effects_Normalizer(str(tmp_path / "feats.npy"), STEMS=['drums'], EFFECTS=['compression'])
+    x2 = x.copy()
+    x2[:, 1] *= 0.5
+    ref = norm.normalize_audio(x2.copy(), src='drums')
+    got = N.normalize_audio(x2.copy(), ['compression'], feats, src='drums')
+    assert np.abs(got - ref).max() <= 1e-7
