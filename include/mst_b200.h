@@ -187,6 +187,23 @@ size_t mst_fir_filtfilt_workspace_bytes(int n_signals, long long T, int n_taps);
 int mst_fir_filtfilt(const float* x, int n_signals, long long T, long long stride, const double* taps, int n_taps,
                      const double* scale, float* y, long long y_stride, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- remaining FXmanipulator processors -------------------------------------------------------------------
+ * mst_fft_convolve: ConvolutionalReverb.process (common_audioeffects.py:735-764): y[c][t] = dry * x[c][t] + wet * full[c][t + offset],
+ *   full = x[c] convolved with h[c] (mode='full'; scipy.signal.oaconvolve in the reference), as a partitioned overlap-add on the
+ *   device FFT of csrc/spectral.cu.  x, y: fp32 [2][T] (rows x_stride / y_stride apart); h: fp32 [h_channels][M], h_channels 1
+ *   (the mono response serves both channels, :738-739) or 2; offset = the reference's cut index (:752-757).
+ * mst_algo_reverb: AlgorithmicReverb.process (:1446-1509): per channel four damped feedback comb filters (the reference
+ *   overwrites the sum of combs 1-4 with comb 5, :1474-1488 -- reproduced) followed by four all-pass sections, then the wet /
+ *   dry / width mix.  The comb / all-pass arithmetic is pymixconsole's (third-party, absent): restated, PARITY UNPINNED.
+ *   x, y: fp32 [B][2][L]; params: fp32 [B][5] = (room_size, damping, dry_mix, wet_mix, width). */
+size_t mst_fft_convolve_workspace_bytes(long long T, long long M);
+int mst_fft_convolve(const float* x, long long T, long long x_stride, const float* h, long long M, long long h_stride,
+                     int h_channels, long long offset, float dry, float wet, float* y, long long y_stride, void* workspace,
+                     size_t workspace_bytes, void* stream);
+size_t mst_algo_reverb_workspace_bytes(int B, int L);
+int mst_algo_reverb(const float* x, const float* params, float* y, int B, int L, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
 /* ---- WAV sample formats on the device: the steps either side of the forward -------------------
  * mst_pcm_decode replaces load_wav_segment's int -> float conversion and de-interleave
  * (mixing_style_transfer/data_loader/loader_utils.py:54-70) plus the stem clamp (data_loader/data_loader.py:589-590) and

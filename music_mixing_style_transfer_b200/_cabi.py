@@ -72,6 +72,12 @@ SIGNATURES = {
     "mst_fir_filtfilt_workspace_bytes": (c_size_t, [c_int, ctypes.c_longlong, c_int]),
     "mst_fir_filtfilt": (c_int, [c_void_p, c_int, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_int, c_void_p, c_void_p,
                                  ctypes.c_longlong, c_void_p, c_size_t, c_void_p]),
+    "mst_fft_convolve_workspace_bytes": (c_size_t, [ctypes.c_longlong, ctypes.c_longlong]),
+    "mst_fft_convolve": (c_int, [c_void_p, ctypes.c_longlong, ctypes.c_longlong, c_void_p, ctypes.c_longlong, ctypes.c_longlong,
+                                 c_int, ctypes.c_longlong, c_float, c_float, c_void_p, ctypes.c_longlong, c_void_p, c_size_t,
+                                 c_void_p]),
+    "mst_algo_reverb_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mst_algo_reverb": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "mst_pcm_decode": (c_int, [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, ctypes.c_longlong, c_void_p]),
     "mst_pcm_encode_mix": (c_int, [c_void_p, c_int, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_void_p]),
 }
@@ -106,12 +112,20 @@ def check(rc: int, what: str = "") -> None:
         raise RuntimeError(f"libmst_b200 {what}: {last_error()}")
 
 
-def ptr(t) -> int:
-    """Raw device pointer of a CUDA tensor (None -> NULL)."""
+def ptr(t, rows_strided: bool = False) -> int:
+    """Raw device pointer of a CUDA tensor (None -> NULL).  The C ABI takes dense buffers: a tensor whose strides are not the
+    contiguous ones is refused instead of being read with the wrong layout (`rows_strided`: a 2-D view whose rows are dense but
+    may lie further apart than their length, for the entry points that take a row stride)."""
     if t is None:
         return None
     if not t.is_cuda:
         raise RuntimeError("libmst_b200 op called with a CPU tensor: this engine has no CPU fallback")
+    if rows_strided:
+        if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1) or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+            raise RuntimeError(f"libmst_b200 op needs dense rows, got strides {tuple(t.stride())} for shape {tuple(t.shape)}")
+    elif not t.is_contiguous():
+        raise RuntimeError(f"libmst_b200 op called with a non-contiguous tensor (shape {tuple(t.shape)}, strides {tuple(t.stride())}); "
+                           "call .contiguous() first")
     return t.data_ptr()
 
 

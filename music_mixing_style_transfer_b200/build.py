@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libmst_b200.so")
 STAMP = LIB_PATH + ".stamp"
-SOURCES = ["api.cu", "encoder.cu", "enc_umma.cu", "tcn.cu", "tcn_f8.cu", "fx2.cu", "fxnorm.cu", "spectral.cu", "pcm.cu"]
+SOURCES = ["api.cu", "encoder.cu", "enc_umma.cu", "tcn.cu", "tcn_f8.cu", "fx2.cu", "fxnorm.cu", "spectral.cu", "reverb.cu", "pcm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--cudart", "static"]
 

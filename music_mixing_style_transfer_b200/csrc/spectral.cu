@@ -9,6 +9,8 @@
 //                       odd extension by 3*n_taps samples, forward FIR, backward FIR, both started in the steady state of
 //                       the first sample (lfilter_zi), float64 like scipy
 //   mst_row_absmax      np.max(np.abs(x)) per channel (:69, fx_utils.py:231)
+//   mst_fft_convolve    oaconvolve(x, h, mode='full', axes=0) + cut + dry / wet mix of ConvolutionalReverb.process
+//                       (common_audioeffects.py:735-764), SURVEY.md 8f-4
 //
 // FFT: four-step decomposition N = 256 * N2 (N2 = 4 .. 256).  Two signals share one complex transform (real part = signal
 // 2p, imaginary part = signal 2p + 1; the spectra are separated from Z[k] and conj(Z[N - k])).  Pass A: 16 columns per CTA,
@@ -142,6 +144,95 @@ mag_accumulate_kernel(const float2* __restrict__ Z, int N, int n_frames, int n_s
 __global__ void scale_kernel(double* __restrict__ a, size_t n, double s) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] *= s;
+}
+
+// ---- FFT convolution (ConvolutionalReverb: scipy.signal.oaconvolve, common_audioeffects.py:748) ----------------------------------
+// Partitioned overlap-add at frame length N, hop H = N / 2: x is cut into blocks of H samples, h into partitions of H samples,
+// all zero-padded to N and transformed with the passes above (window = 1 on the first half, 0 on the second; the two channels
+// of a stereo signal travel as real / imaginary part of one complex transform).  Output block j = sum over i + p = j of
+// X_i H_p, built per bin from the separated channel spectra and re-packed as Y = Y_L + i Y_R; the inverse transform is the
+// forward one on conj(Y); blocks overlap-add with hop H.
+__device__ __forceinline__ void unpack_pair(float2 p, float2 q, float2& a, float2& b) {
+  a = make_float2(0.5f * (p.x + q.x), 0.5f * (p.y - q.y));       // (p + conj q) / 2
+  b = make_float2(0.5f * (p.y + q.y), 0.5f * (q.x - p.x));       // (p - conj q) / (2i)
+}
+
+// Yc[j][k] = conj( sum_p XL[j-p][k] HL[p][k]  +  i * sum_p XR[j-p][k] HR[p][k] )   (conjugated for the inverse pass)
+__global__ void __launch_bounds__(kThreads)
+conv_mac_kernel(const float2* __restrict__ Zx, int nbx, const float2* __restrict__ Zh, int P, int N, float2* __restrict__ Yc) {
+  const int k = blockIdx.x * kThreads + threadIdx.x, j = blockIdx.y;
+  if (k >= N) return;
+  const int km = (N - k) & (N - 1);
+  float2 yl = make_float2(0.f, 0.f), yr = yl;
+  for (int p = 0; p < P; ++p) {
+    const int i = j - p;
+    if (i < 0 || i >= nbx) continue;
+    float2 xl, xr, hl, hr;
+    unpack_pair(Zx[(size_t)i * N + k], Zx[(size_t)i * N + km], xl, xr);
+    unpack_pair(Zh[(size_t)p * N + k], Zh[(size_t)p * N + km], hl, hr);
+    const float2 a = cmul(xl, hl), b = cmul(xr, hr);
+    yl.x += a.x; yl.y += a.y; yr.x += b.x; yr.y += b.y;
+  }
+  // Y = yl + i yr = (yl.x - yr.y) + i (yl.y + yr.x);  store conj(Y)
+  Yc[(size_t)j * N + k] = make_float2(yl.x - yr.y, -(yl.y + yr.x));
+}
+
+// pass A on complex input (one transform per frame): Y[f][k1][n2] = W_N^(n2 k1) * sum_n1 z[f][n1 N2 + n2] W_256^(n1 k1)
+__global__ void __launch_bounds__(kThreads)
+fft_cols_cplx_kernel(const float2* __restrict__ zin, int N2, float2* __restrict__ Y) {
+  __shared__ float2 d[kN1 * kCols];
+  __shared__ float2 tw[128];
+  const int c0 = blockIdx.x * kCols, f = blockIdx.y;
+  const int N = kN1 * N2;
+  const int cols = min(kCols, N2 - c0);
+  load_twiddles(tw);
+  const float2* z = zin + (size_t)f * N;
+  for (int q = threadIdx.x; q < kN1 * cols; q += kThreads) {
+    const int j = q % cols, n1 = q / cols;
+    d[(__brev((unsigned)n1) >> 24) * cols + j] = z[n1 * N2 + c0 + j];
+  }
+  __syncthreads();
+  fft_inplace(d, tw, kN1, 8, cols);
+  float2* out = Y + (size_t)f * N;
+  for (int q = threadIdx.x; q < kN1 * cols; q += kThreads) {
+    const int j = q % cols, k1 = q / cols;
+    const int n2 = c0 + j;
+    float sn, cs;
+    sincospif(-2.0f * (float)((n2 * k1) & (N - 1)) / (float)N, &sn, &cs);
+    out[(size_t)k1 * N2 + n2] = cmul(d[k1 * cols + j], make_float2(cs, sn));
+  }
+}
+
+// y[c][t] = dry * x[c][t] + wet * full[c][t + offset],  full = overlap-add of the inverse blocks: the inverse transform of Y is
+// conj(F) / N with F = FFT(conj Y), so full_L = Re(F) / N and full_R = -Im(F) / N
+__global__ void __launch_bounds__(kThreads)
+conv_ola_kernel(const float2* __restrict__ F, int nby, int N, const float* __restrict__ x, long long T, long long x_stride,
+                long long offset, float dry, float wet, float* __restrict__ y, long long y_stride) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= T) return;
+  const int H = N / 2;
+  const long long u = t + offset;
+  const long long j = u / H;
+  const int n = (int)(u - j * H);
+  float2 v = make_float2(0.f, 0.f);
+  if (j < nby) { const float2 a = F[(size_t)j * N + n]; v.x += a.x; v.y += a.y; }
+  if (j >= 1 && j - 1 < nby) { const float2 a = F[(size_t)(j - 1) * N + n + H]; v.x += a.x; v.y += a.y; }
+  const float inv = 1.0f / (float)N;
+  y[t] = dry * x[t] + wet * (v.x * inv);
+  y[y_stride + t] = dry * x[x_stride + t] + wet * (-v.y * inv);
+}
+
+__global__ void __launch_bounds__(kThreads)
+conv_pad_kernel(const float* __restrict__ src, long long n, long long src_stride, int mono, float* __restrict__ dst, long long n_pad) {
+  const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= n_pad) return;
+  const int c = blockIdx.y;
+  dst[(size_t)c * n_pad + t] = t < n ? src[(size_t)(mono ? 0 : c) * src_stride + t] : 0.f;
+}
+
+__global__ void half_window_kernel(float* __restrict__ w, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) w[i] = i < N / 2 ? 1.f : 0.f;
 }
 
 // ---- per-row peak --------------------------------------------------------------------------------------------------------
@@ -306,6 +397,71 @@ int mst_stft_mag_mean(const float* x, int n_signals, long long T, long long stri
   const size_t n = (size_t)n_signals * nb;
   scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, n, 1.0 / (double)n_frames);
   return launch_ok("scale_kernel");
+}
+
+static int conv_frame_len(long long M) {
+  int N = 1024;
+  while (N < 65536 && (long long)N / 2 < M) N *= 2;       // one partition when the impulse response fits half a frame
+  return N;
+}
+
+size_t mst_fft_convolve_workspace_bytes(long long T, long long M) {
+  if (T <= 0 || M <= 0) return 0;
+  const long long N = conv_frame_len(M), H = N / 2;
+  const long long nbx = (T + H - 1) / H, P = (M + H - 1) / H, nby = nbx + P - 1;
+  size_t b = 0;
+  b += align_up((size_t)N * sizeof(float), 256);                               // half window
+  b += align_up((size_t)2 * (nbx + 1) * H * sizeof(float), 256);               // padded x
+  b += align_up((size_t)2 * (P + 1) * H * sizeof(float), 256);                 // padded h
+  b += 2 * align_up((size_t)(nbx > nby ? nbx : nby) * N * sizeof(float2), 256); // pass A scratch + block spectra / inverse blocks
+  b += align_up((size_t)nbx * N * sizeof(float2), 256);                        // Zx
+  b += align_up((size_t)P * N * sizeof(float2), 256);                          // Zh
+  return b;
+}
+
+int mst_fft_convolve(const float* x, long long T, long long x_stride, const float* h, long long M, long long h_stride,
+                     int h_channels, long long offset, float dry, float wet, float* y, long long y_stride, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  using namespace spec;
+  MST_CHECK(x && h && y && workspace, "fft_convolve: null pointer");
+  MST_CHECK(T > 0 && M > 0 && x_stride >= T && y_stride >= T && h_stride >= M && (h_channels == 1 || h_channels == 2) && offset >= 0,
+            "fft_convolve: bad arguments");
+  MST_CHECK(workspace_bytes >= mst_fft_convolve_workspace_bytes(T, M), "fft_convolve: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = conv_frame_len(M), H = N / 2, N2 = N / kN1;
+  int logn = 0;
+  while ((1 << logn) < N) ++logn;
+  const long long nbx = (T + H - 1) / H, P = (M + H - 1) / H, nby = nbx + P - 1;
+  MST_CHECK(nby <= 65535, "fft_convolve: too many blocks (%lld)", nby);
+  uint8_t* w8 = reinterpret_cast<uint8_t*>(workspace);
+  auto take = [&](size_t bytes) { uint8_t* r = w8; w8 += align_up(bytes, 256); return r; };
+  float* win = reinterpret_cast<float*>(take((size_t)N * sizeof(float)));
+  float* xp = reinterpret_cast<float*>(take((size_t)2 * (nbx + 1) * H * sizeof(float)));
+  float* hp = reinterpret_cast<float*>(take((size_t)2 * (P + 1) * H * sizeof(float)));
+  const size_t big = align_up((size_t)(nbx > nby ? nbx : nby) * N * sizeof(float2), 256);
+  float2* S1 = reinterpret_cast<float2*>(take(big));
+  float2* S2 = reinterpret_cast<float2*>(take(big));
+  float2* Zx = reinterpret_cast<float2*>(take((size_t)nbx * N * sizeof(float2)));
+  float2* Zh = reinterpret_cast<float2*>(take((size_t)P * N * sizeof(float2)));
+  half_window_kernel<<<cdiv(N, 256), 256, 0, st>>>(win, N);
+  const long long xpad = (nbx + 1) * H, hpad = (P + 1) * H;
+  conv_pad_kernel<<<dim3((unsigned)((xpad + kThreads - 1) / kThreads), 2), kThreads, 0, st>>>(x, T, x_stride, 0, xp, xpad);
+  conv_pad_kernel<<<dim3((unsigned)((hpad + kThreads - 1) / kThreads), 2), kThreads, 0, st>>>(h, M, h_stride, h_channels == 1, hp, hpad);
+  if (launch_ok("conv_pad_kernel")) return 1;
+  const size_t rows_smem = ((size_t)N2 * kCols + 128) * sizeof(float2);
+  // forward transforms of the x blocks and the h partitions (pair-packed: L real, R imaginary)
+  fft_cols_kernel<<<dim3(cdiv(N2, kCols), (unsigned)nbx, 1), kThreads, 0, st>>>(xp, xpad, 2, 0, H, N2, win, S1);
+  fft_rows_kernel<<<dim3(kN1 / kCols, (unsigned)nbx, 1), kThreads, rows_smem, st>>>(S1, N2, logn - 8, Zx);
+  fft_cols_kernel<<<dim3(cdiv(N2, kCols), (unsigned)P, 1), kThreads, 0, st>>>(hp, hpad, 2, 0, H, N2, win, S1);
+  fft_rows_kernel<<<dim3(kN1 / kCols, (unsigned)P, 1), kThreads, rows_smem, st>>>(S1, N2, logn - 8, Zh);
+  if (launch_ok("fft (convolution, forward)")) return 1;
+  conv_mac_kernel<<<dim3(cdiv(N, kThreads), (unsigned)nby), kThreads, 0, st>>>(Zx, (int)nbx, Zh, (int)P, N, S2);
+  if (launch_ok("conv_mac_kernel")) return 1;
+  fft_cols_cplx_kernel<<<dim3(cdiv(N2, kCols), (unsigned)nby), kThreads, 0, st>>>(S2, N2, S1);
+  fft_rows_kernel<<<dim3(kN1 / kCols, (unsigned)nby, 1), kThreads, rows_smem, st>>>(S1, N2, logn - 8, S2);
+  if (launch_ok("fft (convolution, inverse)")) return 1;
+  conv_ola_kernel<<<(unsigned)((T + kThreads - 1) / kThreads), kThreads, 0, st>>>(S2, (int)nby, N, x, T, x_stride, offset, dry, wet, y, y_stride);
+  return launch_ok("conv_ola_kernel");
 }
 
 size_t mst_fir_filtfilt_workspace_bytes(int n_signals, long long T, int n_taps) {

@@ -150,6 +150,9 @@ class Processor:
         return _process_numpy(x, self.param_vector(), self.STAGE, self.sample_rate)
 
 
+_ALL_BANDS = ['low_shelf', 'first_band', 'second_band', 'third_band', 'high_shelf']
+
+
 # %%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%% EQUALISER %%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%
 class Equaliser(Processor):
     """Five band parametric equaliser (two shelves and three central bands): cascade of five RBJ biquads."""
@@ -161,8 +164,13 @@ class Equaliser(Processor):
         super().__init__(name, parameters=parameters, block_size=None, sample_rate=sample_rate)
         if n_channels != 2:
             raise NotImplementedError("Equaliser: the B200 path is stereo (n_channels=2) like the chain factory builds it")
-        if list(bands) != ['low_shelf', 'first_band', 'second_band', 'third_band', 'high_shelf']:
-            raise NotImplementedError("Equaliser: only the default five bands have a B200 path")
+        unknown = [b for b in bands if b not in _ALL_BANDS]
+        if unknown:
+            raise ValueError(f"Equaliser: unknown bands {unknown}")
+        if list(bands) != _ALL_BANDS:
+            # a subset of the bands (the per-instrument factory builds one-shelf equalisers, audio_effects_chain.py:125-146):
+            # explicit RBJ coefficients through mst_biquad_cascade instead of the 13-parameter fused stage
+            self.STAGE = 0
         self.n_channels = n_channels
         MIN_GAIN, MAX_GAIN = gain_range
         MIN_Q, MAX_Q = q_range
@@ -193,8 +201,43 @@ class Equaliser(Processor):
     def reset_state(self):
         """Filters start from zero state at every `process` call (common_audioeffects.py:512); nothing to reset."""
 
+    def _band_coefficients(self):
+        """(b0, b1, b2, a1, a2) per band of `self.bands`, RBJ cookbook, float64 (setup_filters, common_audioeffects.py:438-462)."""
+        rows = []
+        for band in self.bands:
+            G = float(getattr(self.parameters, band + '_gain').value)
+            fc = float(getattr(self.parameters, band + '_freq').value)
+            shelf = band in ('low_shelf', 'high_shelf')
+            Q = 0.707 if shelf else float(getattr(self.parameters, band + '_q').value)
+            A = 10.0 ** (G / 40.0)
+            w0 = 2.0 * np.pi * (fc / self.sample_rate)
+            alpha, c = np.sin(w0) / (2.0 * Q), np.cos(w0)
+            sq = 2.0 * np.sqrt(A) * alpha
+            if not shelf:
+                b = [1.0 + alpha * A, -2.0 * c, 1.0 - alpha * A]
+                a_ = [1.0 + alpha / A, -2.0 * c, 1.0 - alpha / A]
+            elif band == 'low_shelf':
+                b = [A * ((A + 1) - (A - 1) * c + sq), 2 * A * ((A - 1) - (A + 1) * c), A * ((A + 1) - (A - 1) * c - sq)]
+                a_ = [(A + 1) + (A - 1) * c + sq, -2 * ((A - 1) + (A + 1) * c), (A + 1) + (A - 1) * c - sq]
+            else:
+                b = [A * ((A + 1) + (A - 1) * c + sq), -2 * A * ((A - 1) + (A + 1) * c), A * ((A + 1) + (A - 1) * c - sq)]
+                a_ = [(A + 1) - (A - 1) * c + sq, 2 * ((A - 1) - (A + 1) * c), (A + 1) - (A - 1) * c - sq]
+            rows.append([b[0] / a_[0], b[1] / a_[0], b[2] / a_[0], a_[1] / a_[0], a_[2] / a_[0]])
+        return np.asarray(rows, dtype=np.float64)
+
     def process(self, x):
-        y = super().process(x)
+        if self.STAGE:
+            y = super().process(x)
+        else:
+            xt = _to_device(x)
+            lib = _cabi.lib()
+            n = xt.shape[-1]
+            coef = torch.from_numpy(self._band_coefficients()[None]).to(xt.device)
+            ws = torch.empty(max(lib.mst_fx_workspace_bytes(1, n), 4096), dtype=torch.uint8, device=xt.device)
+            yt = torch.empty_like(xt)
+            _cabi.check(lib.mst_biquad_cascade(_cabi.ptr(xt), coef.data_ptr(), len(self.bands), _cabi.ptr(yt), 1, n, _cabi.ptr(ws),
+                                               ws.numel(), _cabi.current_stream()), "biquad_cascade")
+            y = np.ascontiguousarray(yt[0].cpu().numpy().T)
         if self.hard_clip:
             y = np.clip(y, -1.0, 1.0)
         return y
@@ -332,6 +375,112 @@ class Panner(Processor):
             x = np.repeat(x, 2, axis=1)
         y = stereo_mix(_to_device(x), [[float(self.gains[0]), 0.0, 0.0, float(self.gains[1])]])
         return np.ascontiguousarray(y[0].cpu().numpy().T)
+
+
+# %%%%%%%%%%%%%%%%%%%%%%%%%% CONVOLUTIONAL REVERB %%%%%%%%%%%%%%%%%%%%%%%%%%%%%
+class ConvolutionalReverb(Processor):
+    """Convolutional reverb (common_audioeffects.py:665-764): the input convolved with a sampled impulse response, cut at the
+    response's peak (+ pre-delay) and mixed with the dry signal.  `impulse_responses` is the reference's structure: a list (one
+    entry per RT60 class) of lists of dicts whose 'impulse_response' entry is a callable returning float [m, 1 or 2].  The
+    convolution is mst_fft_convolve (partitioned overlap-add on the device FFT)."""
+    STAGE = 0
+
+    def __init__(self, impulse_responses, sample_rate, name='ConvolutionalReverb', parameters=None):
+        super().__init__(name=name, parameters=parameters, block_size=None, sample_rate=sample_rate)
+        if impulse_responses is None:
+            raise ValueError('List of impulse responses must be provided for ConvolutionalReverb processor.')
+        self.impulse_responses = impulse_responses
+        if not parameters:
+            self.parameters = ParameterList()
+            self.max_ir_num = len(max(impulse_responses, key=len))
+            self.parameters.add(Parameter('index', 0, 'int', minimum=0, maximum=len(impulse_responses)))
+            self.parameters.add(Parameter('index_ir', 0, 'int', minimum=0, maximum=self.max_ir_num))
+            self.parameters.add(Parameter('wet', 1.0, 'float', minimum=1.0, maximum=1.0))
+            self.parameters.add(Parameter('dry', 0.0, 'float', minimum=0.0, maximum=0.0))
+            self.parameters.add(Parameter('decay', 1.0, 'float', minimum=1.0, maximum=1.0))
+            self.parameters.add(Parameter('pre_delay', 0, 'int', units='ms', minimum=0, maximum=0))
+        self.h = None
+
+    def update(self, parameter_name=None):
+        """Pick the impulse response (RT60 class `index`, response `index_ir` modulo the class size) and apply the decay fade
+        (:712-733)."""
+        ir_class = self.impulse_responses[min(int(self.parameters.index.value), len(self.impulse_responses) - 1)]
+        self.h = np.copy(ir_class[int(self.parameters.index_ir.value) % len(ir_class)]['impulse_response']())
+        decay = self.parameters.decay.value
+        if decay < 1.:
+            n_h = self.h.shape[0]
+            peak = int(np.argmax(np.max(np.abs(self.h), axis=1), axis=0))
+            fstart = min(n_h, peak + int(decay * (n_h - peak)))
+            fstop = min(n_h, fstart + int(0.020 * self.sample_rate))          # constant 20 ms fade out
+            flen = fstop - fstart
+            fade = np.power(0.1, np.arange(1, flen + 1, dtype=self.dtype) / flen * 5)
+            self.h[fstart:fstop, :] *= fade[:, np.newaxis]
+            self.h = self.h[:fstop]
+
+    def process(self, x):
+        x = np.asarray(x)
+        n_channels = x.shape[1]
+        if self.h is None:
+            self.update()
+        if self.h.shape[1] > 1 and n_channels == 1:
+            self.h = self.h[:, np.random.randint(self.h.shape[1]), np.newaxis]      # randomly choose one IR channel (:740-741)
+        if self.parameters.wet.value == 0.0:
+            return x
+        h = self.h
+        idx = int(np.argmax(np.max(np.abs(h), axis=1), axis=0))                     # the response's own delay (:751-757)
+        idx += int(0.001 * np.abs(self.parameters.pre_delay.value) * self.sample_rate)
+        idx = int(np.clip(idx, 0, h.shape[0] - 1))
+        xs = np.repeat(x, 2, axis=1) if n_channels == 1 else x
+        xt = _to_device(xs)[0]                                                       # [2, n]
+        ht = torch.from_numpy(np.ascontiguousarray(h.T, dtype=np.float32)).cuda()    # [1 or 2, m]
+        lib = _cabi.lib()
+        T, M = xt.shape[-1], ht.shape[-1]
+        ws = torch.empty(lib.mst_fft_convolve_workspace_bytes(T, M), dtype=torch.uint8, device=xt.device)
+        y = torch.empty_like(xt)
+        _cabi.check(lib.mst_fft_convolve(_cabi.ptr(xt, True), T, max(xt.stride(0), T), _cabi.ptr(ht, True), M, max(ht.stride(0), M), ht.shape[0], idx,
+                                         float(self.parameters.dry.value), float(self.parameters.wet.value), _cabi.ptr(y),
+                                         y.stride(0), _cabi.ptr(ws), ws.numel(), _cabi.current_stream()), "fft_convolve")
+        out = np.ascontiguousarray(y.cpu().numpy().T)
+        return out[:, :1] if n_channels == 1 else out
+
+
+# %%%%%%%%%%%%%%%%%%%%%%%%%%%%%% ALGORITHMIC REVERB %%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%%
+class AlgorithmicReverb(Processor):
+    """Freeverb-style comb / all-pass reverb (common_audioeffects.py:1429-1536); kernel mst_algo_reverb (csrc/reverb.cu).
+    Difference to the reference: every `process` call starts from silent delay lines.  The reference rebuilds its filters in
+    `update` (i.e. once per chain call) but not between the arrays of one list, so there the tail of one array rings into the
+    next one."""
+    STAGE = 0
+
+    def __init__(self, name="algoreverb", parameters=None, sample_rate=44100, **kwargs):
+        super().__init__(name=name, parameters=parameters, block_size=None, sample_rate=sample_rate)
+        if not parameters:
+            self.parameters = ParameterList()
+            self.parameters.add(Parameter("room_size", 0.5, "float", minimum=0.05, maximum=0.85))
+            self.parameters.add(Parameter("damping", 0.1, "float", minimum=0.0, maximum=1.0))
+            self.parameters.add(Parameter("dry_mix", 0.9, "float", minimum=0.0, maximum=1.0))
+            self.parameters.add(Parameter("wet_mix", 0.1, "float", minimum=0.0, maximum=1.0))
+            self.parameters.add(Parameter("width", 0.7, "float", minimum=0.0, maximum=1.0))
+        # Tuning
+        self.stereospread = 23
+        self.scalegain = 0.2
+
+    def process(self, data):
+        data = np.asarray(data)
+        if data.ndim < 2:
+            data = data[:, None]
+        xs = data if data.shape[1] == 2 else np.repeat(data[:, :1], 2, axis=1)      # mono: both sides read channel 0 (:1448-1456)
+        xt = _to_device(xs)
+        pr = self.parameters
+        p5 = torch.tensor([[pr.room_size.value, pr.damping.value, pr.dry_mix.value, pr.wet_mix.value, pr.width.value]],
+                          dtype=torch.float32, device=xt.device)
+        lib = _cabi.lib()
+        L = xt.shape[-1]
+        ws = torch.empty(lib.mst_algo_reverb_workspace_bytes(1, L), dtype=torch.uint8, device=xt.device)
+        y = torch.empty_like(xt)
+        _cabi.check(lib.mst_algo_reverb(_cabi.ptr(xt), _cabi.ptr(p5), _cabi.ptr(y), 1, L, _cabi.ptr(ws), ws.numel(),
+                                        _cabi.current_stream()), "algo_reverb")
+        return np.ascontiguousarray(y[0].cpu().numpy().T).astype(np.float64)          # the reference returns float64 (:1458)
 
 
 def _to_device(x):

@@ -152,7 +152,7 @@ def row_absmax(x):
     """x float32 CUDA [R, T] -> float64 numpy [R]: max |x| per row."""
     R, T = x.shape
     out = torch.empty(R, dtype=torch.float64, device=x.device)
-    _cabi.check(_cabi.lib().mst_row_absmax(_cabi.ptr(x), R, T, x.stride(0), out.data_ptr(), _stream()), "row_absmax")
+    _cabi.check(_cabi.lib().mst_row_absmax(_cabi.ptr(x, True), R, T, max(x.stride(0), T), out.data_ptr(), _stream()), "row_absmax")
     return out.cpu().numpy()
 
 
@@ -169,7 +169,7 @@ def stft_mag_mean(x, n_fft=FFT_SIZE, hop=FFT_SIZE // 4):
         _window_cache[key] = torch.from_numpy(np.sqrt(np.hanning(n_fft + 1)[:-1]).astype(np.float32)).to(x.device)
     ws = torch.empty(lib.mst_stft_workspace_bytes(R, n_fft), dtype=torch.uint8, device=x.device)
     out = torch.empty(R, n_fft // 2 + 1, dtype=torch.float64, device=x.device)
-    _cabi.check(lib.mst_stft_mag_mean(_cabi.ptr(x), R, T, x.stride(0), n_fft, hop, _cabi.ptr(_window_cache[key]), out.data_ptr(),
+    _cabi.check(lib.mst_stft_mag_mean(_cabi.ptr(x, True), R, T, max(x.stride(0), T), n_fft, hop, _cabi.ptr(_window_cache[key]), out.data_ptr(),
                                       _cabi.ptr(ws), ws.numel(), _stream()), "stft_mag_mean")
     return out.cpu().numpy()
 
@@ -185,7 +185,7 @@ def fir_filtfilt(x, taps, scale=None):
     s_d = None if scale is None else torch.from_numpy(np.asarray(scale, dtype=np.float64).reshape(R).copy()).to(x.device)
     ws = torch.empty(lib.mst_fir_filtfilt_workspace_bytes(R, T, n_taps), dtype=torch.uint8, device=x.device)
     y = torch.empty(R, T, dtype=torch.float32, device=x.device)
-    _cabi.check(lib.mst_fir_filtfilt(_cabi.ptr(x), R, T, x.stride(0), t_d.data_ptr(), n_taps, None if s_d is None else s_d.data_ptr(),
+    _cabi.check(lib.mst_fir_filtfilt(_cabi.ptr(x, True), R, T, max(x.stride(0), T), t_d.data_ptr(), n_taps, None if s_d is None else s_d.data_ptr(),
                                      _cabi.ptr(y), y.stride(0), _cabi.ptr(ws), ws.numel(), _stream()), "fir_filtfilt")
     return y
 

@@ -183,3 +183,73 @@ def fx_chain(x, p, rate=SAMPLE_RATE):
     y = rms_normalize(y, compressor(y, p, rate)).astype(np.float32)
     y = rms_normalize(y, imager(y, p)).astype(np.float32)
     return np.asarray(gain(y, p), np.float32)
+
+
+# ---- the reverbs ---------------------------------------------------------------------------------------
+COMB_DELAYS = (1116, 1188, 1277, 1356, 1422, 1491, 1557, 1617)      # common_audioeffects.py:1525-1540
+ALLPASS_DELAYS = ((556, 441, 341, 225), (556 + 23, 441 + 23, 341 + 23, 255 + 23))   # :1516-1523 (R4 is `255 + ss` in the reference)
+
+
+def _comb_blocks(x, D, damp, feedback):
+    """Freeverb comb (restated pymixconsole component, see oracle/shims/pymixconsole/components/comb.py) block by block: the
+    delay line couples sample n to n - D only, the damping one-pole runs along n -- the decomposition the GPU kernel uses."""
+    n = len(x)
+    out = np.zeros(n)
+    buf = np.zeros(D)
+    store = 0.0
+    for k in range(0, n, D):
+        m = min(D, n - k)
+        y = buf[:m].copy()
+        f, _ = scipy.signal.lfilter([1.0 - damp], [1.0, -damp], y, zi=[damp * store])
+        store = f[-1]
+        buf[:m] = x[k:k + m] + f * feedback
+        out[k:k + m] = y
+    return out
+
+
+def _allpass_blocks(x, D, feedback):
+    n = len(x)
+    out = np.zeros(n)
+    buf = np.zeros(D)
+    for k in range(0, n, D):
+        m = min(D, n - k)
+        b = buf[:m].copy()
+        out[k:k + m] = -x[k:k + m] + b
+        buf[:m] = x[k:k + m] + b * feedback
+    return out
+
+
+def algorithmic_reverb(x, room_size, damping, dry_mix, wet_mix, width):
+    """AlgorithmicReverb.process (common_audioeffects.py:1446-1509) on float [n, 2]; float64 [n, 2] out like the reference.
+    Combs 1-4 are computed and then overwritten by comb 5 in the reference (:1478, :1487): only combs 5-8 matter."""
+    chans = []
+    for c in range(2):
+        src = x[:, c].copy() * 0.2                                   # `dataL.copy() * self.scalegain` in the data's dtype
+        s = None
+        for D in COMB_DELAYS[4:]:
+            y = _comb_blocks(np.asarray(src, dtype=np.float64), D + (23 if c else 0), damping, room_size)
+            s = y if s is None else s + y
+        for D in ALLPASS_DELAYS[c]:
+            s = _allpass_blocks(s, D, room_size)
+        chans.append(s)
+    wet1 = wet_mix * ((width / 2) + 0.5)
+    wet2 = wet_mix * ((1 - width) / 2)
+    out = np.zeros((x.shape[0], 2))
+    out[:, 0] = (wet1 * chans[0]) + (wet2 * chans[1]) + (dry_mix * x[:, 0])
+    out[:, 1] = (wet1 * chans[1]) + (wet2 * chans[0]) + (dry_mix * x[:, 1])
+    return out
+
+
+def convolutional_reverb(x, h, pre_delay_ms=0, wet=1.0, dry=0.0, sample_rate=SAMPLE_RATE):
+    """ConvolutionalReverb.process (common_audioeffects.py:735-764) with a given impulse response h [m, 1 or 2]."""
+    from scipy.signal import oaconvolve
+    if h.shape[1] == 1 and x.shape[1] > 1:
+        h = np.hstack([h] * x.shape[1])
+    if wet == 0.0:
+        return x
+    y = oaconvolve(x, h, mode='full', axes=0)
+    idx = np.argmax(np.max(np.abs(h), axis=1), axis=0)
+    idx += int(0.001 * np.abs(pre_delay_ms) * sample_rate)
+    idx = np.clip(idx, 0, h.shape[0] - 1)
+    y = y[idx:idx + x.shape[0], :]
+    return dry * x + wet * y

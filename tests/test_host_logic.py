@@ -66,7 +66,9 @@ def test_unsupported_variants_raise():
         TCNModel(nparams=2048, grouped=True)
     from music_mixing_style_transfer_b200.mixing_manipulator import create_effects_augmentation_chain
     with pytest.raises(NotImplementedError):
-        create_effects_augmentation_chain(["eq", "reverb"])
+        create_effects_augmentation_chain(["eq", "expander"])     # the reference's factory dies with NameError here
+    chain = create_effects_augmentation_chain(["eq", ("reverb", 0.3), "algorithmic"])
+    assert [(f.name, p, n) for f, p, n in chain.fxs] == [("Equaliser", 1, True), ("algoreverb", 0.3, True), ("algoreverb", 1, True)]
     with pytest.raises(ValueError):
         create_effects_augmentation_chain(["wobble"])
     chain = create_effects_augmentation_chain(["eq", ("comp", 0.5), "imager", "gain"])
@@ -280,3 +282,33 @@ def test_interpolation_weights():
     assert torch.allclose(w[:16], (15 - torch.arange(16).float()) / 15)      # style_transfer.py:250 per segment
     with pytest.raises(ValueError):
         shard.interpolation_weights(4, 1)
+
+
+def _chain_structure(chain):
+    """(class name, processor name, probability, normalise flag) tree of an AugmentationChain, with the chain-level switches."""
+    out = {"shuffle": bool(chain.shuffle), "parallel": bool(chain.parallel), "weight": chain.parallel_weight_factor, "fxs": []}
+    for fx, p, norm in chain.fxs:
+        if hasattr(fx, "fxs"):
+            out["fxs"].append((_chain_structure(fx), p, norm))
+        else:
+            params = sorted((q.name, q.value) for q in fx.parameters) if type(fx).__name__ == "Equaliser" and len(fx.bands) == 1 else None
+            out["fxs"].append((type(fx).__name__, fx.name, list(getattr(fx, "bands", [])), params, p, norm))
+    return out
+
+
+def test_instrument_chain_factory_structure():
+    """create_inst_effects_augmentation_chain (audio_effects_chain.py:99-164): nested / parallel structure per instrument."""
+    from music_mixing_style_transfer_b200.mixing_manipulator import create_inst_effects_augmentation_chain
+    prob = {"eq": 0.9, "comp": 0.8, "pan": 0.7, "imager": 0.6, "reverb": 0.5, "gain": 1.0}
+    s = _chain_structure(create_inst_effects_augmentation_chain("vocals", prob, algorithmic=True))
+    assert [type(f[0]) for f in s["fxs"]] == [dict, dict, dict, str] and s["fxs"][3][:2] == ("Gain", "Gain") and s["fxs"][3][-1] is False
+    assert s["fxs"][0][0]["shuffle"] and [f[0] for f in s["fxs"][0][0]["fxs"]] == ["Equaliser", "Compressor"]
+    assert [f[0] for f in s["fxs"][1][0]["fxs"]] == ["Panner", "MidSideImager"]
+    rv = s["fxs"][2][0]
+    assert rv["parallel"] and rv["weight"] is None and [(f[0], f[-2]) for f in rv["fxs"]] == [("AlgorithmicReverb", 0.5)]
+    d = _chain_structure(create_inst_effects_augmentation_chain("drums", prob, algorithmic=True))
+    low, high = d["fxs"][2][0]["fxs"][0][0], d["fxs"][2][0]["fxs"][1][0]
+    assert (low["parallel"], low["weight"], high["weight"]) == (True, 0.8, 0.6)
+    assert low["fxs"][0][2] == ["high_shelf"] and high["fxs"][0][2] == ["low_shelf"]
+    assert low["fxs"][0][3] == [("high_shelf_freq", 100.0), ("high_shelf_gain", -50.0)]
+    assert abs(low["fxs"][1][-2] - 0.005) < 1e-12 and high["fxs"][1][-2] == 0.5

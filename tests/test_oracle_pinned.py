@@ -251,3 +251,41 @@ def test_comp_matching_oracle_equals_reference_code(tmp_path):
     ref = norm.normalize_audio(x2.copy(), src='drums')
     got = N.normalize_audio(x2.copy(), ['compression'], feats, src='drums')
     assert np.abs(got - ref).max() <= 1e-7
+
+
+@needs_ref
+def test_reverb_oracles_and_factory_equal_reference_code():
+    """(1) oracle/fx_oracle.algorithmic_reverb (block-wise comb / all-pass, the decomposition of the GPU kernel)
+    against the reference's AlgorithmicReverb class -- its network wiring, the comb-5 overwrite, the mix -- running on the
+    restated pymixconsole Comb / Allpass sample loops (third-party, unpinned); (2) convolutional_reverb against the reference's
+    ConvolutionalReverb.process (scipy oaconvolve); (3) the per-instrument factory's chain structure against the reference's."""
+    import sys
+    ca = ref_import.import_reference_fx()
+    x = fixtures.fx_input(3, 20000)
+    r = ca.AlgorithmicReverb(sample_rate=44100)
+    for name, v in (("room_size", 0.6), ("damping", 0.3), ("dry_mix", 0.8), ("wet_mix", 0.35), ("width", 0.6)):
+        getattr(r.parameters, name).value = v
+    r.update(None)
+    ref = r.process(x.copy())
+    assert np.abs(ref - fx_oracle.algorithmic_reverb(x, 0.6, 0.3, 0.8, 0.35, 0.6)).max() <= 1e-12
+    rng = np.random.RandomState(1)
+    for m, ch in ((3000, 1), (9000, 2)):
+        h = (rng.randn(m, ch) * np.exp(-np.arange(m) / (m / 6.0))[:, None]).astype(np.float32)
+        h[37] *= 8.0                                                       # the peak the cut index is taken from
+        cr = ca.ConvolutionalReverb([[{'impulse_response': lambda h=h: h}]], 44100)
+        cr.parameters.wet.value, cr.parameters.dry.value, cr.parameters.pre_delay.value = 0.7, 0.4, 3
+        cr.update()
+        ref = cr.process(x.copy())
+        assert np.abs(ref - fx_oracle.convolutional_reverb(x, h, 3, 0.7, 0.4)).max() <= 1e-6
+    # factory structure: the reference module imports soundfile / librosa (stand-ins) through common_dataprocessing
+    import types
+    sys.modules.setdefault("soundfile", types.ModuleType("soundfile"))
+    import importlib
+    ref_chain = importlib.import_module("audio_effects_chain")
+    from music_mixing_style_transfer_b200.mixing_manipulator import create_inst_effects_augmentation_chain
+    from test_host_logic import _chain_structure
+    prob = {"eq": 0.9, "comp": 0.8, "pan": 0.7, "imager": 0.6, "reverb": 0.5, "gain": 1.0}
+    for inst in ("drums", "bass"):
+        a = _chain_structure(ref_chain.create_inst_effects_augmentation_chain(inst, prob, algorithmic=True))
+        b = _chain_structure(create_inst_effects_augmentation_chain(inst, prob, algorithmic=True))
+        assert a == b, inst
