@@ -214,13 +214,10 @@ tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, con
   // full 128-byte plane row; 60 weights per lane keep the kernel at 2 CTAs / SM
   const int half = warp & 1, rgrp = warp >> 1;
   const int ch[2] = {64 * half + 2 * lane, 64 * half + 2 * lane + 1};
-  float wr[2][NIN * kTaps];
+  u64 wr[NIN * kTaps];      // (channel 2l, channel 2l + 1) packed: one fma.rn.f32x2 per tap and row, bit-identical to two scalar FMAs
   float4 P[2];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-#pragma unroll
-    for (int i = 0; i < NIN * kTaps; ++i) wr[q][i] = __ldg(w0 + ch[q] * NIN * kTaps + i);
-  }
+  for (int i = 0; i < NIN * kTaps; ++i) wr[i] = pk(__ldg(w0 + ch[0] * NIN * kTaps + i), __ldg(w0 + ch[1] * NIN * kTaps + i));
   {
     // (bn_bias, gamma, beta, res) of the channel pair {ch[0], ch[1]}: two float4 of the pair-interleaved table
     const float4* fp = film + (size_t)(n_cond > 1 ? b : 0) * kCh + ch[0];
@@ -235,21 +232,18 @@ tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, con
   constexpr int RB = 4;
   for (int r = rgrp * 64; r < rgrp * 64 + 64; r += RB) {
     if (t0 + r >= T) break;
-    float acc[RB][2];
+    u64 acc[RB];
 #pragma unroll
-    for (int u = 0; u < RB; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; }
+    for (int u = 0; u < RB; ++u) acc[u] = 0ull;
 #pragma unroll
     for (int ci = 0; ci < NIN; ++ci) {
 #pragma unroll
       for (int m = 0; m < kTaps + RB - 1; ++m) {
-        const float xv = xs[ci][r + m];
+        const u64 xv = dup(xs[ci][r + m]);
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
           const int j = m - u;   // tap of row r+u that touches window position m
-          if (j >= 0 && j < kTaps) {
-            acc[u][0] = fmaf(wr[0][ci * kTaps + j], xv, acc[u][0]);
-            acc[u][1] = fmaf(wr[1][ci * kTaps + j], xv, acc[u][1]);
-          }
+          if (j >= 0 && j < kTaps) acc[u] = fma2(wr[ci * kTaps + j], xv, acc[u]);
         }
       }
     }
@@ -261,7 +255,7 @@ tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, con
       const float xin = xs[res_ci][r + u + HALO];
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        float v = acc[u][q] + P[q].x;
+        float v = (q == 0 ? lo_of(acc[u]) : hi_of(acc[u])) + P[q].x;
         v = v > 0.f ? v : 0.01f * v;
         v = fmaf(P[q].y, v, P[q].z) + P[q].w * xin;
         split_bf16(v, hi[q], lo[q]);

@@ -21,6 +21,7 @@
 #include <cuda_fp8.h>
 
 #include "common.cuh"
+#include "f32x2.cuh"
 #include "sm100_ptx.cuh"
 
 namespace mst {
@@ -112,13 +113,12 @@ block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const f
   }
   const int half = warp & 1, rgrp = warp >> 1;
   const int ch[2] = {64 * half + 2 * lane, 64 * half + 2 * lane + 1};
-  float wr[2][NIN * kTaps];
+  // the lane's two channels ride in one packed fma.rn.f32x2 (each half rounds like the scalar FMA, so the sums are bit-identical
+  // to the scalar kernel's): 120 FFMA2 instead of 240 FFMA per 4 rows, the input sample is the broadcast operand
+  f2::u64 wr[NIN * kTaps];
   float4 P[2];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-#pragma unroll
-    for (int i = 0; i < NIN * kTaps; ++i) wr[q][i] = __ldg(w0 + ch[q] * NIN * kTaps + i);
-  }
+  for (int i = 0; i < NIN * kTaps; ++i) wr[i] = f2::pk(__ldg(w0 + ch[0] * NIN * kTaps + i), __ldg(w0 + ch[1] * NIN * kTaps + i));
   {
     // (bn_bias, gamma, beta, res) of the channel pair {ch[0], ch[1]}: two float4 of the pair-interleaved table (tcn.cu)
     const float4* fp = film + (size_t)(n_cond > 1 ? b : 0) * kCh + ch[0];
@@ -126,26 +126,24 @@ block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const f
     P[0] = make_float4(A.x, A.z, Bq.x, Bq.z);
     P[1] = make_float4(A.y, A.w, Bq.y, Bq.w);
   }
+  const f2::u64 Pb = f2::pk(P[0].x, P[1].x), Pg = f2::pk(P[0].y, P[1].y), Pbe = f2::pk(P[0].z, P[1].z), Pr = f2::pk(P[0].w, P[1].w);
   const int res_ci = ch[0] / (kCh / NIN);
   float vmax = 0.f;     // max |activation| written by this thread (operand-range guard, see tcn.cu)
   __syncthreads();
   for (int r = rgrp * 64; r < rgrp * 64 + 64; r += RB) {
     if (t0 + r >= T) break;
-    float acc[RB][2];
+    f2::u64 acc[RB];
 #pragma unroll
-    for (int u = 0; u < RB; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; }
+    for (int u = 0; u < RB; ++u) acc[u] = 0ull;
 #pragma unroll
     for (int ci = 0; ci < NIN; ++ci) {
 #pragma unroll
       for (int m = 0; m < kTaps + RB - 1; ++m) {
-        const float xv = xs[ci][r + m];
+        const f2::u64 xv = f2::dup(xs[ci][r + m]);
 #pragma unroll
         for (int u = 0; u < RB; ++u) {
           const int j = m - u;
-          if (j >= 0 && j < kTaps) {
-            acc[u][0] = fmaf(wr[0][ci * kTaps + j], xv, acc[u][0]);
-            acc[u][1] = fmaf(wr[1][ci * kTaps + j], xv, acc[u][1]);
-          }
+          if (j >= 0 && j < kTaps) acc[u] = f2::fma2(wr[ci * kTaps + j], xv, acc[u]);
         }
       }
     }
@@ -153,21 +151,24 @@ block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const f
     for (int u = 0; u < RB; ++u) {
       const int t = t0 + r + u;
       if (t >= T) break;
-      const float xin = xs[res_ci][r + u + HALO];
-      __half hi[2];
-      uint8_t l8[2], h8[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        float v = acc[u][q] + P[q].x;
-        v = v > 0.f ? v : 0.01f * v;
-        v = fmaf(P[q].y, v, P[q].z) + P[q].w * xin;
-        vmax = fmaxf(vmax, fabsf(v));
-        encode3(v, hi[q], l8[q], h8[q]);
-      }
+      // the channel pair stays packed through the epilogue (the arithmetic of tcn.cu's tensor-core epilogue: add, max(v, 0.01 v),
+      // two fused multiply-adds, exact remainder) and is converted two values per instruction
+      const f2::u64 xin = f2::dup(xs[res_ci][r + u + HALO]);
+      f2::u64 v = f2::add2(acc[u], Pb);
+      const f2::u64 vl = f2::mul2(v, f2::dup(0.01f));
+      v = f2::pk(fmaxf(f2::lo_of(v), f2::lo_of(vl)), fmaxf(f2::hi_of(v), f2::hi_of(vl)));
+      v = f2::fma2(Pr, xin, f2::fma2(Pg, v, Pbe));             // gamma v + beta + res x_in (the contraction nvcc applied to the scalar form)
+      const float v0 = f2::lo_of(v), v1 = f2::hi_of(v);
+      vmax = fmaxf(vmax, fmaxf(fabsf(v0), fabsf(v1)));
+      const uint32_t hbits = ptx::cvt_f16x2_satfinite(v0, v1);                     // fp16 pair, clamped to +-65504
+      const float2 hb = __half22float2(*reinterpret_cast<const __half2*>(&hbits));
+      const f2::u64 rem = f2::mul2(f2::fma2(f2::pk(hb.x, hb.y), f2::dup(-1.f), v), f2::dup(kLoScale));
+      const uint16_t l2 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(f2::lo_of(rem), f2::hi_of(rem)), __NV_SATFINITE, __NV_E4M3);
+      const uint16_t h2 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(v0, v1), __NV_SATFINITE, __NV_E4M3);
       uint8_t* row = act + ((size_t)b * T + t) * kRowBytes;
-      reinterpret_cast<__half2*>(row + half * 128)[lane] = __halves2half2(hi[0], hi[1]);
-      reinterpret_cast<uint16_t*>(row + 256 + half * 64)[lane] = (uint16_t)l8[0] | ((uint16_t)l8[1] << 8);
-      reinterpret_cast<uint16_t*>(row + 384 + half * 64)[lane] = (uint16_t)h8[0] | ((uint16_t)h8[1] << 8);
+      reinterpret_cast<uint32_t*>(row + half * 128)[lane] = hbits;
+      reinterpret_cast<uint16_t*>(row + 256 + half * 64)[lane] = l2;
+      reinterpret_cast<uint16_t*>(row + 384 + half * 64)[lane] = h2;
     }
   }
   // the e4m3 planes saturate at 448: report (rarely, so the atomic is not a hot spot) when this block left the format's range
