@@ -211,6 +211,96 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- CTA pair (cta_group::2): one MMA spans two SMs
+// A cluster of two CTAs on one TPC.  M = 256: each CTA holds 128 rows of A and its 128 TMEM lanes of D; B (N = 128) is
+// split, 64 rows per CTA, at the SAME shared-memory offsets in both.  The leader (cluster rank 0) issues the MMAs; both CTAs
+// run their own TMA loads, which signal the LEADER's `full` barrier (cluster address from mapa); tcgen05.commit multicasts
+// the completion to the barrier at the same offset in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the variable at shared::cta address `saddr` in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_caddr, uint32_t bytes) {
+  // relaxed: the arrival only announces bytes a TMA load is about to deliver (the load's own complete_tx carries the data
+  // dependency); a release at cluster scope here costs the single producer thread a fence per slot
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_caddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_caddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_caddr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* m, uint32_t bar_caddr, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_caddr), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(const CUtensorMap* m, uint32_t bar_caddr, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_caddr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_cg2(const CUtensorMap* m, uint32_t bar_caddr, void* dst, int c0, int c1, int c2, int c3,
+                                                int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_caddr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_mma_f16kind_elect_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                           uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_mma_f8kind_elect_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                          uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+// completion of every MMA issued so far -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_elect_cg2(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      ".reg .b16 m;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t"
+      "}\n" ::"r"(smem_u32(bar)), "r"(leader)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of SWZ bytes (SWZ/2 bf16) with the SWZ-byte
 // swizzle (what TMA SWIZZLE_128B / SWIZZLE_64B produces): 8-row groups are 8*SWZ bytes apart (SBO), LBO unused for

@@ -45,6 +45,10 @@
 #ifndef MST_TCN_ABLATE
 #define MST_TCN_ABLATE 0
 #endif
+// CTA-pair variant of the dilated blocks (tcgen05 cta_group::2, see tcn_block_umma_kernel): 2 = on for the f16f8 format
+#ifndef MST_TCN_CG
+#define MST_TCN_CG 2
+#endif
 
 namespace mst {
 
@@ -384,7 +388,12 @@ __device__ __forceinline__ int tile_row(int ts, int rl, int d) { return MODE == 
 //        (kind::f16), group 1 = the two e4m3 tiles (kind::f8f6f4, tile i of X times tile i of W), all into ONE accumulator; the
 //        epilogue multiplies by 1 / (S 2^11).  Tensor maps are byte-typed in this mode (coordinates in bytes).
 // FUSE:  the last block -- Conv1d(128 -> n_out, k=1) + clamp in the epilogue, no activation store.
-template <int KCH, int MODE, int FMT, bool FUSE>
+// CG:    1 = one CTA per work item; 2 = CTA pair (cluster of 2 on one TPC, tcgen05 cta_group::2): the pair takes two consecutive
+//        work items, one per CTA, as ONE M = 256 MMA stream issued by the leader; every weight tile is staged half in each CTA
+//        (64 of its 128 output-channel rows), so the weight bytes entering an SM halve.  Both CTAs walk the same (operand group,
+//        tap) steps -- a step runs when it is live for either work item; a CTA whose own item (or tap) lies outside the signal
+//        loads zero-filled rows and stores nothing.
+template <int KCH, int MODE, int FMT, bool FUSE, int CG>
 __global__ void __launch_bounds__(256, 1)
 tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                       const __grid_constant__ CUtensorMap tm_xs, const __grid_constant__ CUtensorMap tm_y,
@@ -393,11 +402,29 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   // tm_x / tm_w: operand boxes {KCH ch, 128 rows}, swizzle = 2*KCH bytes;  tm_xs / tm_y: epilogue boxes {64 ch, 128 rows};
   // tm_l8 / tm_y8 (FMT 1 only): epilogue boxes {64 bytes, 128 rows}, SWIZZLE_64B, for the e4m3 half planes
   static_assert(FMT == 0 || KCH == 64, "the f16f8 format uses 128-byte operand rows");
+  static_assert(CG == 1 || (KCH == 64 && (MODE != 0 || FMT == 1)), "the CTA pair uses the operand-group-outermost schedule");
   constexpr bool PAIRED = MODE != 0;
+  const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
+  const int n_workers = CG == 2 ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int worker = CG == 2 ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int n_items = CG == 2 ? (a.n_tiles + 1) / 2 : a.n_tiles;        // work items of a worker step (pairs of tiles for CG 2)
   // activation boxes: 3-D {columns, 128 rows, segment} in modes 0 / 1, 5-D {columns, d rows, half, 128/d blocks, segment} in mode 2
   auto act_load = [&](const CUtensorMap* m, uint64_t* bar, void* dst, int col, int ts, int b) {
     if (MODE == 2) { const int hh = ts / a.dilation; ptx::tma_load_5d(m, bar, dst, col, 0, hh & 1, hh >> 1, b); }
     else ptx::tma_load_3d(m, bar, dst, col, ts, b);
+  };
+  // operand loads of the CTA pair: completion is signalled on the LEADER's barrier (cluster address)
+  auto act_load_cg2 = [&](const CUtensorMap* m, uint32_t bar_caddr, void* dst, int col, int ts, int b) {
+    if (MODE == 2) { const int hh = ts / a.dilation; ptx::tma_load_5d_cg2(m, bar_caddr, dst, col, 0, hh & 1, hh >> 1, b); }
+    else ptx::tma_load_3d_cg2(m, bar_caddr, dst, col, ts, b);
+  };
+  // the two work items of a worker step: `c` = this CTA's, `o` = the partner's (CG 1: o == c)
+  auto item_tiles = [&](int q, TcnTile& c, TcnTile& o) {
+    const int t_own = CG == 2 ? 2 * q + (int)cta_rank : q, t_oth = CG == 2 ? 2 * q + 1 - (int)cta_rank : q;
+    c = tcn_tile<MODE>(t_own, a);
+    o = tcn_tile<MODE>(t_oth, a);
+    if (t_own >= a.n_tiles) { c.sub0 = false; c.sub1 = false; }
+    if (t_oth >= a.n_tiles) { o.sub0 = false; o.sub1 = false; }
   };
   auto act_store = [&](const CUtensorMap* m, const void* src, int col, int ts, int b) {
     if (MODE == 2) { const int hh = ts / a.dilation; ptx::tma_store_5d(m, src, col, 0, hh & 1, hh >> 1, b); }
@@ -428,22 +455,23 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kNumSlots; ++i) {
-      ptx::mbar_init(&bars->full[i], 1);
+      ptx::mbar_init(&bars->full[i], CG);            // one producer arrival per CTA of the pair
       ptx::mbar_init(&bars->empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->tmem_full[i], 1);
-      ptx::mbar_init(&bars->tmem_empty[i], 128);
+      ptx::mbar_init(&bars->tmem_empty[i], 128 * CG);  // the epilogue threads of both CTAs release the leader's accumulators
     }
     ptx::mbar_init(&bars->stage_full, 1);
     ptx::mbar_fence_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(&bars->tmem_base, 512);
-    ptx::tmem_relinquish();
+    if (CG == 2) { ptx::tmem_alloc_cg2(&bars->tmem_base, 512); ptx::tmem_relinquish_cg2(); }
+    else { ptx::tmem_alloc(&bars->tmem_base, 512); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) ptx::cluster_sync();                  // the partner's barriers exist before anything arrives on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -459,11 +487,19 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
       auto load_w = [&](int j, int kc) {
         // weights: rows ((j*kKcPerTap+kc)*2 + split)*128 .. : hi tile then lo tile
         ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
-        ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
         uint8_t* dst = ring + (size_t)slot * kSlotBytes;
         const int wrow = ((j * kKcPerTap + kc) * 2) * kCh;
-        ptx::tma_load_2d(&tm_w, &bars->full[slot], dst, 0, wrow);
-        ptx::tma_load_2d(&tm_w, &bars->full[slot], dst + kHalf, 0, wrow + kCh);
+        if (CG == 2) {
+          // this CTA's 64 output-channel rows of both tiles (tm_w boxes are 64 rows high), same slot offsets as the full tiles
+          const uint32_t fb = ptx::mapa(ptx::smem_u32(&bars->full[slot]), 0);
+          ptx::mbar_expect_tx_cluster(fb, kSlotBytes / 2);
+          ptx::tma_load_2d_cg2(&tm_w, fb, dst, 0, wrow + 64 * (int)cta_rank);
+          ptx::tma_load_2d_cg2(&tm_w, fb, dst + kHalf, 0, wrow + kCh + 64 * (int)cta_rank);
+        } else {
+          ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
+          ptx::tma_load_2d(&tm_w, &bars->full[slot], dst, 0, wrow);
+          ptx::tma_load_2d(&tm_w, &bars->full[slot], dst + kHalf, 0, wrow + kCh);
+        }
         next();
       };
       auto load_x = [&](int kc, long long ts, int b) {
@@ -471,27 +507,40 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const int c_hi = (((kc * KCH) / 64) * 128 + (kc * KCH) % 64) * kCoord, c_lo = c_hi + 64 * kCoord;
         ptx::mbar_wait(&bars->empty[slot], phase ^ 1);
         if (MST_TCN_ABLATE & 4) { ptx::mbar_arrive(&bars->full[slot]); next(); return; }
-        ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
         uint8_t* dst = ring + (size_t)slot * kSlotBytes;
-        act_load(&tm_x, &bars->full[slot], dst, c_hi, (int)ts, b);
-        act_load(&tm_x, &bars->full[slot], dst + kHalf, c_lo, (int)ts, b);
+        if (CG == 2) {
+          const uint32_t fb = ptx::mapa(ptx::smem_u32(&bars->full[slot]), 0);
+          ptx::mbar_expect_tx_cluster(fb, kSlotBytes);
+          act_load_cg2(&tm_x, fb, dst, c_hi, (int)ts, b);
+          act_load_cg2(&tm_x, fb, dst + kHalf, c_lo, (int)ts, b);
+        } else {
+          ptx::mbar_expect_tx(&bars->full[slot], kSlotBytes);
+          act_load(&tm_x, &bars->full[slot], dst, c_hi, (int)ts, b);
+          act_load(&tm_x, &bars->full[slot], dst + kHalf, c_lo, (int)ts, b);
+        }
         next();
       };
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const TcnTile c = tcn_tile<MODE>(tile, a);
-        if (!c.sub0) continue;
+      for (int q = worker; q < n_items; q += n_workers) {
+        TcnTile c, o;
+        item_tiles(q, c, o);
+        if (!c.sub0 && !o.sub0) continue;
         if (PAIRED || FMT == 1) {
           // operand group (channel half / MMA kind) outermost.  Slot order per executed step (kc, j): W, [rows of sub-tile 0's
-          // tap j unless step j-1 loaded them as sub-tile 1's tap j-1 (PAIRED only)], [rows of sub-tile 1's tap j]
+          // tap j unless step j-1 loaded them as sub-tile 1's tap j-1 (PAIRED only)], [rows of sub-tile 1's tap j].  Liveness is
+          // the union over the work items of the step (CG 2); this CTA always loads ITS item's rows (zero-filled outside).
           for (int kc = 0; kc < kKcPerTap; ++kc) {
+            bool prev_live1 = false;
             for (int j = 0; j < kTaps; ++j) {
               const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
-              const bool live0 = tap_live<MODE>(ts0, a.T), live1 = c.sub1 && tap_live<MODE>(ts1, a.T);
-              if (!live0 && !live1) continue;
+              const long long os0 = o.r0 + (long long)(j - 7) * d, os1 = o.r1 + (long long)(j - 7) * d;
+              const bool live0 = (c.sub0 && tap_live<MODE>(ts0, a.T)) || (o.sub0 && tap_live<MODE>(os0, a.T));
+              const bool live1 = (c.sub1 && tap_live<MODE>(ts1, a.T)) || (o.sub1 && tap_live<MODE>(os1, a.T));
+              if (!live0 && !live1) { prev_live1 = false; continue; }
               load_w(j, kc);
-              const bool resident = PAIRED && j >= 1 && c.sub1 && live0;   // ts0 == rows of sub-tile 1 at tap j-1 (same liveness)
+              const bool resident = PAIRED && prev_live1 && live0;   // ts0 == rows of sub-tile 1 at tap j-1, still in its slot
               if (live0 && !resident) load_x(kc, ts0, c.b);
               if (live1) load_x(kc, ts1, c.b);
+              prev_live1 = live1;
             }
           }
         } else {
@@ -510,11 +559,24 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    // all 32 lanes run this (warp-uniform) loop; only the tcgen05 instructions are predicated on the elected lane
-    {
+    // all 32 lanes run this (warp-uniform) loop; only the tcgen05 instructions are predicated on the elected lane.
+    // CTA pair: the leader CTA issues for both (M = 256); the partner's warp 1 has nothing to do.
+    if (CG == 1 || cta_rank == 0) {
       const uint32_t leader = ptx::elect_one() ? 1u : 0u;
-      constexpr uint32_t idesc = FMT == 1 ? ptx::umma_idesc_f16_f32(kSubRows, kCh)     // format code 0 = F16 (kind::f16) = E4M3 (kind::f8f6f4)
-                                          : ptx::umma_idesc_bf16_f32(kSubRows, kCh);
+      constexpr uint32_t idesc = FMT == 1 ? ptx::umma_idesc_f16_f32(kSubRows * CG, kCh)     // format code 0 = F16 (kind::f16) = E4M3 (kind::f8f6f4)
+                                          : ptx::umma_idesc_bf16_f32(kSubRows * CG, kCh);
+      auto mma_f16 = [&](uint32_t dt, uint64_t ad, uint64_t bd, uint32_t acc) {
+        if (CG == 2) ptx::umma_mma_f16kind_elect_cg2(dt, ad, bd, idesc, acc, leader);
+        else ptx::umma_mma_f16kind_elect(dt, ad, bd, idesc, acc, leader);
+      };
+      auto mma_f8 = [&](uint32_t dt, uint64_t ad, uint64_t bd, uint32_t acc) {
+        if (CG == 2) ptx::umma_mma_f8kind_elect_cg2(dt, ad, bd, idesc, acc, leader);
+        else ptx::umma_mma_f8kind_elect(dt, ad, bd, idesc, acc, leader);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (CG == 2) ptx::umma_commit_elect_cg2(bar, leader);
+        else ptx::umma_commit_elect(bar, leader);
+      };
       uint32_t slot = 0, phase = 0;
       bool f8_group = false;     // FMT 1: the slots being consumed hold the e4m3 tiles (operand group 1)
       auto next = [&]() { if (++slot == kNumSlots) { slot = 0; phase ^= 1; } };
@@ -529,15 +591,15 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 32 >> 4);
-              ptx::umma_mma_f8kind_elect(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u, leader);
-              ptx::umma_mma_f8kind_elect(d_tmem, xl + adv, wl + adv, idesc, 1u, leader);
+              mma_f8(d_tmem, xh + adv, wh + adv, (first && k == 0) ? 0u : 1u);
+              mma_f8(d_tmem, xl + adv, wl + adv, 1u);
             }
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t adv = (uint64_t)(k * 32 >> 4);
-              ptx::umma_mma_f16kind_elect(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u, leader);
-              ptx::umma_mma_f16kind_elect(d_tmem, xl + adv, wl + adv, idesc, 1u, leader);
+              mma_f16(d_tmem, xh + adv, wh + adv, (first && k == 0) ? 0u : 1u);
+              mma_f16(d_tmem, xl + adv, wl + adv, 1u);
             }
           }
           return;
@@ -545,15 +607,16 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 #pragma unroll
         for (int k = 0; k < kK16; ++k) {
           const uint64_t adv = (uint64_t)(k * 32 >> 4);  // +32 bytes along K inside the 128-byte swizzle row
-          ptx::umma_mma_f16kind_elect(d_tmem, xh + adv, wh + adv, idesc, (first && k == 0) ? 0u : 1u, leader);
-          ptx::umma_mma_f16kind_elect(d_tmem, xl + adv, wh + adv, idesc, 1u, leader);
-          ptx::umma_mma_f16kind_elect(d_tmem, xh + adv, wl + adv, idesc, 1u, leader);
+          mma_f16(d_tmem, xh + adv, wh + adv, (first && k == 0) ? 0u : 1u);
+          mma_f16(d_tmem, xl + adv, wh + adv, 1u);
+          mma_f16(d_tmem, xh + adv, wl + adv, 1u);
         }
       };
       int it = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const TcnTile c = tcn_tile<MODE>(tile, a);
-        if (!c.sub0) continue;
+      for (int q = worker; q < n_items; q += n_workers) {
+        TcnTile c, o;
+        item_tiles(q, c, o);
+        if (!c.sub0 && !o.sub0) continue;
         const int buf = it & 1;
         ptx::mbar_wait(&bars->tmem_empty[buf], ((it >> 1) & 1) ^ 1);
         ptx::tc_fence_after();
@@ -565,8 +628,10 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
             int carried = -1;      // slot holding the rows sub-tile 1 used at the previous tap = rows of sub-tile 0 at this tap
             for (int j = 0; j < kTaps; ++j) {
               const long long ts0 = c.r0 + (long long)(j - 7) * d, ts1 = c.r1 + (long long)(j - 7) * d;
-              const bool live0 = tap_live<MODE>(ts0, a.T), live1 = c.sub1 && tap_live<MODE>(ts1, a.T);
-              if (!live0 && !live1) continue;
+              const long long os0 = o.r0 + (long long)(j - 7) * d, os1 = o.r1 + (long long)(j - 7) * d;
+              const bool live0 = (c.sub0 && tap_live<MODE>(ts0, a.T)) || (o.sub0 && tap_live<MODE>(os0, a.T));
+              const bool live1 = (c.sub1 && tap_live<MODE>(ts1, a.T)) || (o.sub1 && tap_live<MODE>(os1, a.T));
+              if (!live0 && !live1) { carried = -1; continue; }
               const uint32_t wslot = slot;
               ptx::mbar_wait(&bars->full[wslot], phase);
               const uint32_t w_addr = ptx::smem_u32(ring + (size_t)wslot * kSlotBytes);
@@ -583,7 +648,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 ptx::tc_fence_after();
                 issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc0, first0);
                 first0 = false;
-                ptx::umma_commit_elect(&bars->empty[xs], leader);
+                commit(&bars->empty[xs]);
               }
               carried = -1;
               if (live1) {
@@ -595,9 +660,9 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 first1 = false;
                 // the same rows are sub-tile 0's operand at tap j+1 (ts1 = r0 + (j-6) d): keep the slot if that tap runs
                 if (PAIRED && j + 1 < kTaps) carried = (int)xs;
-                else ptx::umma_commit_elect(&bars->empty[xs], leader);
+                else commit(&bars->empty[xs]);
               }
-              ptx::umma_commit_elect(&bars->empty[wslot], leader);
+              commit(&bars->empty[wslot]);
             }
           }
         } else {
@@ -617,7 +682,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 ptx::tc_fence_after();
                 issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc0, first0);
                 first0 = false;
-                ptx::umma_commit_elect(&bars->empty[xs], leader);
+                commit(&bars->empty[xs]);
               }
               if (live1) {
                 const uint32_t xs = slot;
@@ -626,13 +691,13 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 ptx::tc_fence_after();
                 issue_group(ptx::smem_u32(ring + (size_t)xs * kSlotBytes), w_addr, acc1, first1);
                 first1 = false;
-                ptx::umma_commit_elect(&bars->empty[xs], leader);
+                commit(&bars->empty[xs]);
               }
-              ptx::umma_commit_elect(&bars->empty[wslot], leader);
+              commit(&bars->empty[wslot]);
             }
           }
         }
-        ptx::umma_commit_elect(&bars->tmem_full[buf], leader);
+        commit(&bars->tmem_full[buf]);
         ++it;
       }
     }
@@ -662,11 +727,13 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         act_load(&tm_xs, stage_full, staging + 16384, (2 * h + 1) * 64, ts, b);  // x_in lo
       }
     };
-    // requests the h = 0 residual tile of the first live sub-tile at or after (tile, sub) in processing order (thread 0 only)
-    auto request_next = [&](int tile, int sub) {
+    // requests the h = 0 residual tile of the first live sub-tile of THIS CTA at or after (item q, sub) in processing order
+    // (thread 0 only)
+    auto request_next = [&](int q, int sub) {
       if (MST_TCN_ABLATE & 2) return;
-      for (; tile < a.n_tiles; tile += gridDim.x, sub = 0) {
-        const TcnTile c = tcn_tile<MODE>(tile, a);
+      for (; q < n_items; q += n_workers, sub = 0) {
+        TcnTile c, o;
+        item_tiles(q, c, o);
         if (!c.sub0) continue;
         for (; sub < 2; ++sub) {
           const long long ts = sub == 0 ? c.r0 : c.r1;
@@ -674,19 +741,22 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         }
       }
     };
-    if (et == 0) request_next(blockIdx.x, 0);
+    if (et == 0) request_next(worker, 0);
+    const uint32_t tmem_empty_lead[2] = {CG == 2 ? ptx::mapa(ptx::smem_u32(&bars->tmem_empty[0]), 0) : 0u,
+                                         CG == 2 ? ptx::mapa(ptx::smem_u32(&bars->tmem_empty[1]), 0) : 0u};
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-      const TcnTile c = tcn_tile<MODE>(tile, a);
-      if (!c.sub0) continue;
+    for (int q = worker; q < n_items; q += n_workers) {
+      TcnTile c, o;
+      item_tiles(q, c, o);
+      if (!c.sub0 && !o.sub0) continue;
       const int b = c.b;
       const int buf = it & 1;
-      const float4* film = a.film + (size_t)(a.n_cond > 1 ? b : 0) * kCh;
+      const float4* film = a.film + (size_t)(a.n_cond > 1 && c.sub0 ? b : 0) * kCh;
       ptx::mbar_wait(&bars->tmem_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();
       for (int sub = 0; sub < 2; ++sub) {
         const int ts = (int)(sub == 0 ? c.r0 : c.r1);
-        if (ts >= a.T || (MST_TCN_ABLATE & 2)) break;
+        if (!c.sub0 || ts >= a.T || (MST_TCN_ABLATE & 2)) break;     // !c.sub0: the partner's item only (CTA pair)
         float o0 = 0.f, o1 = 0.f;
         for (int h = 0; h < 2; ++h) {
           uint32_t acc[64];
@@ -813,7 +883,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
               ptx::tma_store_wait_read0();       // the staging tile may be overwritten once the store has read it
             }
             if (h == 0) request_residual(1, ts, b);
-            else request_next(tile, sub + 1);
+            else request_next(q, sub + 1);
           }
         }
         if (FUSE) {
@@ -826,7 +896,8 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         }
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&bars->tmem_empty[buf]);
+      if (CG == 2) ptx::mbar_arrive_cluster(tmem_empty_lead[buf]);
+      else ptx::mbar_arrive(&bars->tmem_empty[buf]);
       ++it;
     }
     if (et == 0) ptx::tma_store_wait_all();
@@ -842,9 +913,11 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) ptx::cluster_sync();       // neither CTA leaves (or frees TMEM) while the other may still signal it
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, 512);
+    else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -894,12 +967,12 @@ static int encode_act_map_bytes(CUtensorMap* m, const void* base, int B, int T, 
   MST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f16f8 activation B=%d T=%d box=%d) failed: CUresult %d", B, T, box_bytes, (int)r);
   return 0;
 }
-static int encode_w_map_bytes(CUtensorMap* m, const void* base) {
+static int encode_w_map_bytes(CUtensorMap* m, const void* base, int box_rows = kCh) {
   PFN_encodeTiled enc = tensor_map_encoder();
   if (!enc) return 1;
   cuuint64_t dims[2] = {128, (cuuint64_t)kTaps * 4 * kCh};
   cuuint64_t strides[1] = {128};
-  cuuint32_t box[2] = {128, (cuuint32_t)kCh};
+  cuuint32_t box[2] = {128, (cuuint32_t)box_rows};      // 64 rows: the half of a weight tile one CTA of a pair stages
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -935,6 +1008,9 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   // work-item geometry (tcn_tile): far pairing for dilations that are a multiple of 128, interleaved pairing for the small
   // ones when the length allows it, plain 256-row tiles otherwise
   const int mode = (d >= kSubRows && d % kSubRows == 0) ? 1 : ((d < kSubRows && kSubRows % d == 0 && T % (2 * d) == 0) ? 2 : 0);
+  // CTA pairs for the f16f8 format in the paired geometries (plain 256-row tiles need three slots per step: the half-filled
+  // weight slot then costs ring depth, measured 8 % slower at L = 82,412)
+  const int cg = (f8 && MST_TCN_CG == 2 && mode != 0 && sm_count() % 2 == 0) ? 2 : 1;
   CUtensorMap tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8;
   const uint8_t* w_layer = packed + (f8 ? L.wumma : L.wbf16) + (size_t)(n - 1) * kWBytesPerLayer;
   const void* dst_act = fuse_out ? (const void*)act_in : (const void*)act_out;
@@ -945,7 +1021,7 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
     if (f8) {
       if (encode_act_map5(&tm_l8, act_in, B, T, (int)d, 64, true)) return 1;
       if (encode_act_map5(&tm_y8, dst_act, B, T, (int)d, 64, true)) return 1;
-      if (encode_w_map_bytes(&tm_w, w_layer)) return 1;
+      if (encode_w_map_bytes(&tm_w, w_layer, cg == 2 ? 64 : kCh)) return 1;
     } else {
       tm_l8 = tm_xs;
       tm_y8 = tm_y;
@@ -957,7 +1033,7 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
     if (encode_act_map_bytes(&tm_y, fuse_out ? act_in : act_out, B, T, 128)) return 1;
     if (encode_act_map_bytes(&tm_l8, act_in, B, T, 64)) return 1;
     if (encode_act_map_bytes(&tm_y8, fuse_out ? act_in : act_out, B, T, 64)) return 1;
-    if (encode_w_map_bytes(&tm_w, w_layer)) return 1;
+    if (encode_w_map_bytes(&tm_w, w_layer, cg == 2 ? 64 : kCh)) return 1;
   } else {
     if (encode_act_map(&tm_x, act_in, B, T, 64)) return 1;
     tm_xs = tm_x;
@@ -979,12 +1055,34 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   a.out_w = reinterpret_cast<const float*>(packed + L.out_w);
   a.out_b = reinterpret_cast<const float*>(packed + L.out_b);
   a.out = out;
-  const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
+  int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
+  if (cg == 2) {
+    const int pairs = (a.n_tiles + 1) / 2;
+    grid = 2 * (pairs < sm_count() / 2 ? pairs : sm_count() / 2);
+  }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(256);
+  lc.dynamicSmemBytes = kTcnSmemBytes;
+  lc.stream = st;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeClusterDimension;
+  lattr[0].val.clusterDim.x = 2;
+  lattr[0].val.clusterDim.y = 1;
+  lattr[0].val.clusterDim.z = 1;
+  lc.attrs = lattr;
+  lc.numAttrs = 1;
 #define MST_TCN_LAUNCH(MODE_, FMT_, FUSE_)                                                                                        \
   do {                                                                                                                           \
-    MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64, MODE_, FMT_, FUSE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)kTcnSmemBytes));                                                                       \
-    tcn_block_umma_kernel<64, MODE_, FMT_, FUSE_><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8, a);   \
+    if (FMT_ == 1 && cg == 2) {                                                                                                  \
+      auto kern = tcn_block_umma_kernel<64, MODE_, 1, FUSE_, 2>;                                                                 \
+      MST_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcnSmemBytes));                  \
+      MST_CUDA_OK(cudaLaunchKernelEx(&lc, kern, tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8, a));                                      \
+    } else {                                                                                                                     \
+      MST_CUDA_OK(cudaFuncSetAttribute(tcn_block_umma_kernel<64, MODE_, FMT_, FUSE_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)kTcnSmemBytes));                                                                     \
+      tcn_block_umma_kernel<64, MODE_, FMT_, FUSE_, 1><<<grid, 256, kTcnSmemBytes, st>>>(tm_x, tm_w, tm_xs, tm_y, tm_l8, tm_y8, a); \
+    }                                                                                                                            \
   } while (0)
 #define MST_TCN_LAUNCH2(MODE_, FMT_) do { if (fuse_out) MST_TCN_LAUNCH(MODE_, FMT_, true); else MST_TCN_LAUNCH(MODE_, FMT_, false); } while (0)
 #define MST_TCN_LAUNCH3(FMT_) do { if (mode == 1) MST_TCN_LAUNCH2(1, FMT_); else if (mode == 2) MST_TCN_LAUNCH2(2, FMT_); else MST_TCN_LAUNCH2(0, FMT_); } while (0)
