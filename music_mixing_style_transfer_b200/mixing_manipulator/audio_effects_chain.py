@@ -65,50 +65,36 @@ def create_effects_augmentation_chain(effects,
             parallel (boolean) : compute parallel FX computation (alpha * input + (1-alpha) * manipulated output)
             parallel_weight_factor : the value of alpha for parallel FX computation. default=None : random value in between (0.0, 0.5)
     '''
-    fx_list = []
-    apply_prob = []
-    for cur_fx in effects:
-        # store probability to apply current effects. default is to set as 100%
-        if isinstance(cur_fx, tuple):
-            apply_prob.append(cur_fx[1])
-            cur_fx = cur_fx[0]
-        else:
-            apply_prob.append(1)
+    def build(name):
+        """One processor from its effect name; the reference matches substrings in this order (:41-84)."""
+        key = name.lower()
+        if key == 'gain':
+            return Gain()
+        rules = (('eq', lambda: Equaliser(n_channels=2, sample_rate=sample_rate)),
+                 ('comp', lambda: Compressor(sample_rate=sample_rate)),
+                 ('expand', None),
+                 ('pan', lambda: Panner()),
+                 ('image', lambda: MidSideImager()),
+                 ('algorithmic', lambda: AlgorithmicReverb(sample_rate=sample_rate)),
+                 # convolution reverberation needs impulse responses; without a directory the algorithmic one is used
+                 ('reverb', lambda: AlgorithmicReverb(sample_rate=sample_rate) if ir_dir_path is None
+                  else ConvolutionalReverb(load_impulse_responses(ir_dir_path, sample_rate), sample_rate)))
+        for fragment, make in rules:
+            if fragment in key:
+                if make is None:
+                    raise NotImplementedError(f"effect {name!r}: the reference's factory builds `Expander(...)` here (:49), a class "
+                                              "its common_audioeffects.py does not define (NameError there)")
+                return make()
+        raise ValueError(f"make sure the target effects are in the Augment FX chain : received fx called {name}")
 
-        # processors of each audio effects
-        if isinstance(cur_fx, AugmentationChain) or isinstance(cur_fx, Processor):
-            fx_list.append(cur_fx)
-        elif cur_fx.lower() == 'gain':
-            fx_list.append(Gain())
-        elif 'eq' in cur_fx.lower():
-            fx_list.append(Equaliser(n_channels=2, sample_rate=sample_rate))
-        elif 'comp' in cur_fx.lower():
-            fx_list.append(Compressor(sample_rate=sample_rate))
-        elif 'expand' in cur_fx.lower():
-            raise NotImplementedError(f"effect {cur_fx!r}: the reference's factory builds `Expander(...)` here (:49), a class its "
-                                      "common_audioeffects.py does not define (NameError there)")
-        elif 'pan' in cur_fx.lower():
-            fx_list.append(Panner())
-        elif 'image' in cur_fx.lower():
-            fx_list.append(MidSideImager())
-        elif 'algorithmic' in cur_fx.lower():
-            fx_list.append(AlgorithmicReverb(sample_rate=sample_rate))
-        elif 'reverb' in cur_fx.lower():
-            # algorithmic reverberation if ir_dir_path is not defined, convolution reverberation otherwise
-            if ir_dir_path is None:
-                fx_list.append(AlgorithmicReverb(sample_rate=sample_rate))
-            else:
-                fx_list.append(ConvolutionalReverb(load_impulse_responses(ir_dir_path, sample_rate), sample_rate))
-        else:
-            raise ValueError(f"make sure the target effects are in the Augment FX chain : received fx called {cur_fx}")
-
-    aug_chain_in = []
-    for cur_i, cur_fx in enumerate(fx_list):
-        normalize = False if isinstance(cur_fx, AugmentationChain) or cur_fx.name == 'Gain' else True
-        aug_chain_in.append((cur_fx, apply_prob[cur_i], normalize))
-
-    return AugmentationChain(fxs=aug_chain_in, shuffle=shuffle, parallel=parallel,
-                             parallel_weight_factor=parallel_weight_factor)
+    entries = []
+    for item in effects:
+        fx, prob = item if isinstance(item, tuple) else (item, 1)        # probability of applying the effect, 100 % by default
+        if not isinstance(fx, (AugmentationChain, Processor)):
+            fx = build(fx)
+        # nested chains and the gain are never RMS re-normalised (:92)
+        entries.append((fx, prob, not (isinstance(fx, AugmentationChain) or fx.name == 'Gain')))
+    return AugmentationChain(fxs=entries, shuffle=shuffle, parallel=parallel, parallel_weight_factor=parallel_weight_factor)
 
 
 def _one_shelf_equaliser(band, sample_rate):
