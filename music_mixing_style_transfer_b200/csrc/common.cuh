@@ -56,12 +56,10 @@ int enc_umma_conv(const void* x, const void* w_packed, const float* bias, void* 
 int enc_split_from_f32(const float* x, void* y, int B, int C, int T, int halo_l, int halo_r, cudaStream_t st);
 int enc_pool_split(const void* x, float* emb, int B, int C, int T, int halo_l, int t_pad, cudaStream_t st);
 
-// ---- TCN "f16 + 2 x e4m3" operand format (tcn_f8.cu): packer, block 0 and converters used by tcn.cu ----
+// ---- TCN "f16 + 2 x e4m3" operand format (tcn_f8.cu): packer and converters used by tcn.cu ----
 size_t tcn_f8_weight_bytes();
 int tcn_f8_pack_layer(const float* conv_w, const float* bn_w, const float* bn_var, void* w_out, float* inv_scale,
                       unsigned int* scratch, cudaStream_t st);
-int tcn_f8_launch_block0(int n_inputs, const float* x, const float* w0, const float* film, int n_cond, void* act, int B, int T,
-                         unsigned int* range_flag, cudaStream_t st);
 int tcn_f8_act_pack(const float* x, void* act, int B, int T, cudaStream_t st);
 int tcn_f8_act_unpack(const void* act, float* y, int B, int T, cudaStream_t st);
 

@@ -1095,12 +1095,30 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   return launch_ok("tcn_block_umma_kernel");
 }
 
+}  // namespace mst
+#include "tcn_b0.cuh"
+namespace mst {
+
 static int launch_block0(const mst_tcn_config* cfg, const uint8_t* packed, const TcnPacked& L, const float* x,
                          const float* film, int n_cond, uint8_t* act, int B, int T, int precision,
                          unsigned int* range_flag, cudaStream_t st) {
   dim3 grid(cdiv(T, 256), B);
   const float* w0 = reinterpret_cast<const float*>(packed + L.w0);
-  if (precision == MST_TCN_F16F8) return tcn_f8_launch_block0(cfg->n_inputs, x, w0, film, n_cond, act, B, T, range_flag, st);
+  if (precision == MST_TCN_F16F8) {
+    // block 0 on the tensor cores (tcn_b0.cuh): persistent, one CTA per SM, 128-row tiles
+    CUtensorMap tm_y, tm_y8;
+    if (encode_act_map_bytes(&tm_y, act, B, T, 128)) return 1;
+    if (encode_act_map_bytes(&tm_y8, act, B, T, 64)) return 1;
+    b0::Args a;
+    a.x = x; a.w0 = w0; a.film = reinterpret_cast<const float4*>(film); a.range_flag = range_flag;
+    a.n_cond = n_cond; a.B = B; a.T = T; a.nin = cfg->n_inputs;
+    a.tiles_per_seg = cdiv(T, b0::kRows);
+    a.n_tiles = B * a.tiles_per_seg;
+    MST_CUDA_OK(cudaFuncSetAttribute(b0::block0_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b0::kSmemBytes));
+    const int g = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
+    b0::block0_umma_kernel<<<g, b0::kThreads, b0::kSmemBytes, st>>>(tm_y, tm_y8, a);
+    return launch_ok("block0_umma_kernel");
+  }
   const float4* f = reinterpret_cast<const float4*>(film);
   if (cfg->n_inputs == 2) tcn_block0_kernel<2><<<grid, 256, 0, st>>>(x, w0, f, n_cond, act, T);
   else tcn_block0_kernel<1><<<grid, 256, 0, st>>>(x, w0, f, n_cond, act, T);

@@ -96,85 +96,8 @@ __global__ void pack_kernel(const float* __restrict__ w, const float* __restrict
 }
 
 // =====================================================================================================================
-// block 0 and format converters
+// format converters (block 0 of this format runs on the tensor cores: tcn_b0.cuh)
 // =====================================================================================================================
-template <int NIN>
-__global__ void __launch_bounds__(256, 2)
-block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const float4* __restrict__ film, int n_cond,
-              uint8_t* __restrict__ act, int T, unsigned int* __restrict__ range_flag) {
-  constexpr int ROWS = 256, HALO = 7, RB = 4;
-  __shared__ float xs[NIN][ROWS + 2 * HALO + 4];
-  const int b = blockIdx.y, t0 = blockIdx.x * ROWS;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < NIN * (ROWS + 2 * HALO); i += 256) {
-    const int ci = i / (ROWS + 2 * HALO), m = i % (ROWS + 2 * HALO);
-    const int t = t0 - HALO + m;
-    xs[ci][m] = (t >= 0 && t < T) ? __ldg(x + ((size_t)b * NIN + ci) * T + t) : 0.f;
-  }
-  const int half = warp & 1, rgrp = warp >> 1;
-  const int ch[2] = {64 * half + 2 * lane, 64 * half + 2 * lane + 1};
-  // the lane's two channels ride in one packed fma.rn.f32x2 (each half rounds like the scalar FMA, so the sums are bit-identical
-  // to the scalar kernel's): 120 FFMA2 instead of 240 FFMA per 4 rows, the input sample is the broadcast operand
-  f2::u64 wr[NIN * kTaps];
-  float4 P[2];
-#pragma unroll
-  for (int i = 0; i < NIN * kTaps; ++i) wr[i] = f2::pk(__ldg(w0 + ch[0] * NIN * kTaps + i), __ldg(w0 + ch[1] * NIN * kTaps + i));
-  {
-    // (bn_bias, gamma, beta, res) of the channel pair {ch[0], ch[1]}: two float4 of the pair-interleaved table (tcn.cu)
-    const float4* fp = film + (size_t)(n_cond > 1 ? b : 0) * kCh + ch[0];
-    const float4 A = __ldg(fp), Bq = __ldg(fp + 1);
-    P[0] = make_float4(A.x, A.z, Bq.x, Bq.z);
-    P[1] = make_float4(A.y, A.w, Bq.y, Bq.w);
-  }
-  const f2::u64 Pb = f2::pk(P[0].x, P[1].x), Pg = f2::pk(P[0].y, P[1].y), Pbe = f2::pk(P[0].z, P[1].z), Pr = f2::pk(P[0].w, P[1].w);
-  const int res_ci = ch[0] / (kCh / NIN);
-  float vmax = 0.f;     // max |activation| written by this thread (operand-range guard, see tcn.cu)
-  __syncthreads();
-  for (int r = rgrp * 64; r < rgrp * 64 + 64; r += RB) {
-    if (t0 + r >= T) break;
-    f2::u64 acc[RB];
-#pragma unroll
-    for (int u = 0; u < RB; ++u) acc[u] = 0ull;
-#pragma unroll
-    for (int ci = 0; ci < NIN; ++ci) {
-#pragma unroll
-      for (int m = 0; m < kTaps + RB - 1; ++m) {
-        const f2::u64 xv = f2::dup(xs[ci][r + m]);
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          const int j = m - u;
-          if (j >= 0 && j < kTaps) acc[u] = f2::fma2(wr[ci * kTaps + j], xv, acc[u]);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < RB; ++u) {
-      const int t = t0 + r + u;
-      if (t >= T) break;
-      // the channel pair stays packed through the epilogue (the arithmetic of tcn.cu's tensor-core epilogue: add, max(v, 0.01 v),
-      // two fused multiply-adds, exact remainder) and is converted two values per instruction
-      const f2::u64 xin = f2::dup(xs[res_ci][r + u + HALO]);
-      f2::u64 v = f2::add2(acc[u], Pb);
-      const f2::u64 vl = f2::mul2(v, f2::dup(0.01f));
-      v = f2::pk(fmaxf(f2::lo_of(v), f2::lo_of(vl)), fmaxf(f2::hi_of(v), f2::hi_of(vl)));
-      v = f2::fma2(Pr, xin, f2::fma2(Pg, v, Pbe));             // gamma v + beta + res x_in (the contraction nvcc applied to the scalar form)
-      const float v0 = f2::lo_of(v), v1 = f2::hi_of(v);
-      vmax = fmaxf(vmax, fmaxf(fabsf(v0), fabsf(v1)));
-      const uint32_t hbits = ptx::cvt_f16x2_satfinite(v0, v1);                     // fp16 pair, clamped to +-65504
-      const float2 hb = __half22float2(*reinterpret_cast<const __half2*>(&hbits));
-      const f2::u64 rem = f2::mul2(f2::fma2(f2::pk(hb.x, hb.y), f2::dup(-1.f), v), f2::dup(kLoScale));
-      const uint16_t l2 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(f2::lo_of(rem), f2::hi_of(rem)), __NV_SATFINITE, __NV_E4M3);
-      const uint16_t h2 = (uint16_t)__nv_cvt_float2_to_fp8x2(make_float2(v0, v1), __NV_SATFINITE, __NV_E4M3);
-      uint8_t* row = act + ((size_t)b * T + t) * kRowBytes;
-      reinterpret_cast<uint32_t*>(row + half * 128)[lane] = hbits;
-      reinterpret_cast<uint16_t*>(row + 256 + half * 64)[lane] = l2;
-      reinterpret_cast<uint16_t*>(row + 384 + half * 64)[lane] = h2;
-    }
-  }
-  // the e4m3 planes saturate at 448: report (rarely, so the atomic is not a hot spot) when this block left the format's range
-  if (range_flag != nullptr && vmax > MST_TCN_F16F8_RANGE) atomicMax(range_flag, __float_as_uint(vmax));
-}
-
 __global__ void __launch_bounds__(256) act_pack_kernel(const float* __restrict__ x, uint8_t* __restrict__ act, int T) {
   __shared__ float tile[kCh][33];
   const int b = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -235,15 +158,6 @@ int tcn_f8_pack_layer(const float* conv_w, const float* bn_w, const float* bn_va
   if (launch_ok("tcn f8 wmax_kernel")) return 1;
   f8::pack_kernel<<<256, 256, 0, st>>>(conv_w, bn_w, bn_var, scratch, (uint8_t*)w_out, inv_scale);
   return launch_ok("tcn f8 pack_kernel");
-}
-
-int tcn_f8_launch_block0(int n_inputs, const float* x, const float* w0, const float* film, int n_cond, void* act, int B, int T,
-                         unsigned int* range_flag, cudaStream_t st) {
-  dim3 grid(cdiv(T, 256), B);
-  const float4* f = reinterpret_cast<const float4*>(film);
-  if (n_inputs == 2) f8::block0_kernel<2><<<grid, 256, 0, st>>>(x, w0, f, n_cond, (uint8_t*)act, T, range_flag);
-  else f8::block0_kernel<1><<<grid, 256, 0, st>>>(x, w0, f, n_cond, (uint8_t*)act, T, range_flag);
-  return launch_ok("tcn f8 block0_kernel");
 }
 
 int tcn_f8_act_pack(const float* x, void* act, int B, int T, cudaStream_t st) {
