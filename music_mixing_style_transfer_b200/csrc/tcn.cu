@@ -32,6 +32,10 @@
 //            the LAST block instead fuses Conv1d(128->2,k=1)+clamp and writes the fp32 [B,2,L] output directly (the
 //            128-channel tensor of block 13 never touches HBM).
 // Taps whose shifted tile lies entirely in the zero padding are skipped by producer and issuer alike.
+// For the f16f8 format two CTAs on one TPC run as a PAIR (cluster of 2, tcgen05 cta_group::2): one M = 256 MMA stream issued by
+// the leader over two consecutive work items, every weight tile staged half in each CTA (template parameter CG, see the
+// kernel).  Block 0 (C_in = 2) of that format is its own small tensor-core kernel (tcn_b0.cuh); the bf16 x 3 format keeps the
+// CUDA-core block 0 below.
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 
