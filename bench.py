@@ -261,18 +261,36 @@ def file_to_file_leg(device, tmp_root):
     torch.save({"model": {"module." + k: v for k, v in W.make_tcn_state_dict(0).items()}}, os.path.join(root, "tcn.pt"))
     argv = ["--target_dir", os.path.join(root, "data") + "/", "--output_dir", os.path.join(root, "out") + "/",
             "--ckpt_path_enc", os.path.join(root, "enc.pt"), "--ckpt_path_conv", os.path.join(root, "tcn.pt"),
-            "--segment_length", str(SEG_LEN), "--segment_length_ref", str(SEG_LEN), "--normalize_input", "False",
-            "--do_not_separate", "True"]
+            "--segment_length", str(SEG_LEN), "--segment_length_ref", str(SEG_LEN), "--do_not_separate", "True"]
+    # the input FX normaliser on the GPU with synthetic per-stem targets; without 'compression', whose onset
+    # detector (aubio, on the host as in the reference) is not installed on the bench box
+    f = np.arange(32769) / 32768.0
+    feats = {"eq": {}, "loudness": {}, "imager": {}}
+    for i, inst in enumerate(("drums", "bass", "other", "vocals")):
+        feats["eq"][inst] = (30.0 / (1.0 + (150.0 + 50.0 * i) * f) + 0.02).astype(np.float32)
+        feats["loudness"][inst] = np.array([-28.0 - i])
+        feats["imager"][inst] = np.float32(0.93 + 0.01 * i)
+    np.save(os.path.join(root, "feats.npy"), feats, allow_pickle=True)
+    argv_norm = argv + ["--normalize_input", "True", "--precomputed_normalization_feature", os.path.join(root, "feats.npy"),
+                        "--normalization_order", "loudness", "eq", "imager", "loudness"]
+    argv = argv + ["--normalize_input", "False"]
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
         st.main(argv)                       # warm: weight packing, allocator
         stats = dict(st.main(argv))
+        try:
+            st.main(argv_norm)
+            stats_norm = dict(st.main(argv_norm))
+            normalized = {"audio_s_per_s": stats_norm["audio_seconds"] / stats_norm["wall_seconds"], "wall_s": stats_norm["wall_seconds"],
+                          "normalization_order": ["loudness", "eq", "imager", "loudness"]}
+        except Exception as exc:
+            normalized = {"error": repr(exc)}
     shutil.rmtree(root, ignore_errors=True)
     return {"workload": "inference/style_transfer.py entry, 2 songs x 4 stems x 60 s PCM_16 WAV in -> mixture WAV out, "
                         f"segment_length {SEG_LEN}, default batch_size 1",
             "audio_s_per_s": stats["audio_seconds"] / stats["wall_seconds"], "wall_s": stats["wall_seconds"],
-            "song_seconds": stats["audio_seconds"],
+            "song_seconds": stats["audio_seconds"], "with_input_normalizer": normalized,
             "note": "song seconds (4 stems each) per wall second, file reads / decode / remix / PCM_16 / file writes included"}
 
 

@@ -462,14 +462,18 @@ def build_parser():
     inference_args.add_argument('--segment_length', type=int, default=2**19)        # segmentize input according to this duration
     inference_args.add_argument('--segment_length_ref', type=int, default=2**19)    # segmentize reference according to this duration
     # stem-level instruments & separation
-    inference_args.add_argument('--instruments', type=str2bool, default=["drums", "bass", "other", "vocals"], help='instrumental tracks to perform style transfer')
+    # (declared with type=str2bool in the reference, :367: only the default is usable there; here the flag also takes the names)
+    inference_args.add_argument('--instruments', type=str, nargs='+', default=["drums", "bass", "other", "vocals"], help='instrumental tracks to perform style transfer')
     inference_args.add_argument('--stem_level_directory_name', type=str, default='separated')
     inference_args.add_argument('--save_each_inst', type=str2bool, default=False)
     inference_args.add_argument('--do_not_separate', type=str2bool, default=False)
     inference_args.add_argument('--separation_model', type=str, default='mdx_extra')
     # FX normalization
     inference_args.add_argument('--normalize_input', type=str2bool, default=True)
-    inference_args.add_argument('--normalization_order', type=str2bool, default=['loudness', 'eq', 'compression', 'imager', 'loudness'])  # Effects to be normalized, order matters
+    # Effects to be normalized, order matters.  The reference declares this flag with type=str2bool (:372), so there only the default
+    # list is usable; here the flag also takes the effect names: --normalization_order loudness eq imager loudness
+    inference_args.add_argument('--normalization_order', type=str, nargs='+',
+                                default=['loudness', 'eq', 'compression', 'imager', 'loudness'])
     # interpolation
     inference_args.add_argument('--interpolation', type=str2bool, default=False)
     inference_args.add_argument('--interpolate_segments', type=int, default=30)

@@ -97,6 +97,54 @@ def test_public_entry_on_wav_files(tmp_path, interp):
     assert os.path.exists(tmp_path / "out" / "style_transfer_inference_configurations.txt")
 
 
+def test_public_entry_with_input_normalizer(tmp_path):
+    """The reference's default `--normalize_input True` path (data_loader.py:586-590): the INPUT stems go through the FX
+    normaliser (here loudness -> eq -> imager -> loudness; 'compression' needs the aubio package) and are clamped, the
+    reference stems are not.  Entry output vs the oracle normaliser + oracle networks on the same PCM."""
+    oracle_threads()
+    from music_mixing_style_transfer_b200.inference import style_transfer as st
+    from oracle import norm_oracle as N
+    esd, tsd = state_dicts()
+    torch.save({"model": {"module." + k: v for k, v in esd.items()}}, tmp_path / "enc.pt")
+    torch.save({"model": {"module." + k: v for k, v in tsd.items()}}, tmp_path / "tcn.pt")
+    insts, seg = ["drums", "bass"], 16384
+    f = np.arange(32769) / 32768.0
+    feats = {"eq": {}, "loudness": {}, "imager": {}}
+    for i, inst in enumerate(insts):
+        feats["eq"][inst] = (30.0 / (1.0 + (150.0 + 50.0 * i) * f) + 0.02).astype(np.float32)
+        feats["loudness"][inst] = np.array([-20.0 - i])
+        feats["imager"][inst] = np.float32(0.9 + 0.02 * i)
+    np.save(tmp_path / "feats.npy", feats, allow_pickle=True)
+    song = tmp_path / "data" / "song0"
+    audio = {}
+    for name, L in (("input", 2 * seg + 501), ("reference", 2 * seg)):
+        for i, inst in enumerate(insts):
+            x = W.synthetic_audio(1, L, seed=700 + 10 * len(name) + i)[0].numpy()
+            x[1] = 0.4 * x[1] + 0.5 * np.roll(x[0], 300)                      # wide enough to stay off the randomised Haas branch
+            x = np.clip(np.rint(x * 32768.0), -32768, 32767) / 32768.0
+            audio[(name, inst)] = x.astype(np.float32)
+            _write_wav(str(song / "separated" / name / f"{inst}.wav"), x)
+    order = ["loudness", "eq", "imager", "loudness"]
+    st.main(["--target_dir", str(tmp_path / "data") + "/", "--output_dir", str(tmp_path / "out") + "/",
+             "--ckpt_path_enc", str(tmp_path / "enc.pt"), "--ckpt_path_conv", str(tmp_path / "tcn.pt"),
+             "--segment_length", str(seg), "--segment_length_ref", str(seg), "--batch_size", "2", "--instruments", *insts,
+             "--normalize_input", "True", "--precomputed_normalization_feature", str(tmp_path / "feats.npy"),
+             "--normalization_order", *order, "--do_not_separate", "True"])
+    got = st.load_wav_segment(str(tmp_path / "out" / "song0" / "mixture_output.wav"), axis=0)
+    smooth = dict(feats, eq={k: N.smooth_eq_feature(v, k) for k, v in feats["eq"].items()})
+    mix = 0
+    with torch.no_grad():
+        for inst in insts:
+            xin = N.normalize_audio(np.ascontiguousarray(audio[("input", inst)].T), order, smooth, src=inst).T
+            inp = torch.from_numpy(np.clip(xin, -1.0, 1.0).astype(np.float32))
+            y, _ = O.style_transfer_stem(inp, torch.from_numpy(audio[("reference", inst)]), esd, tsd, seg, seg, 2,
+                                         W.ENC_KERNELS, W.ENC_STRIDES)
+            mix = mix + y.numpy()
+    ref_pcm = np.clip(np.rint(mix * 32768.0), -32768, 32767) / 32768.0
+    assert got.shape == ref_pcm.shape
+    assert np.abs(got - ref_pcm).max() <= 2.0 / 32768.0 + 4e-4 and np.sqrt(np.mean((got - ref_pcm) ** 2)) <= RMS_TOL
+
+
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
