@@ -45,7 +45,7 @@ UNIT = "audio_s/s"
 FLOP_PER_ROW_UMMA = 2 * 128 * 128 * 15
 TCN_FLOP_PER_SAMPLE = 6397952        # whole TCN, SURVEY.md 8d
 ENC_FLOP_PER_SEG = 28.59e9           # encoder at L = 2^18
-TRAFFIC_PER_LAUNCH = 11.10e9         # dram bytes per tcn_block_umma_kernel launch at configs[1], from the committed ncu capture (r02d)
+TRAFFIC_PER_LAUNCH = 9.98e9          # dram bytes per tcn_block_umma_kernel launch at configs[1], from the committed ncu capture (r02e)
 
 
 def peaks():
@@ -432,8 +432,8 @@ def main():
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops_sustained"],
                 "peak_source": f"{pk['source']} bf16 dense (sustained: kernel timed inside a long step)",
                 # dram__bytes_read.sum + dram__bytes_write.sum, mean over the 13 launches of a step, from the committed ncu capture
-                # of this workload (profiles/r02d_tcn_ncu.csv: 7.16 GB read + 3.94 GB written = 1.29x the algorithmic bytes; the
-                # small-dilation layers read 4.5 GB, the far-paired ones 6-9 GB depending on the box)
+                # of this workload (profiles/r02e_tcn_ncu.csv: 6.04 GB read + 3.94 GB written = 1.16x the algorithmic bytes; the
+                # small-dilation layers read 4.4-5.1 GB, the far-paired ones 6-9 GB depending on the box)
                 "traffic": TRAFFIC_PER_LAUNCH if (B == BATCH_PER_GPU and L == SEG_LEN and f8) else None,
                 "traffic_algorithmic": 2.0 * B * L * 512, "ms_per_launch": umma_ms, "launches_per_step": n_umma, "share_of_step": share,
                 "algorithmic_flop_per_launch": flops_per_launch,

@@ -61,7 +61,9 @@ class StyleTransferPipeline:
         if flags:
             # did any converter call of this step leave the f16f8 range?  Reduced on the compute stream now and copied out with
             # the waveforms, so that collect() never waits on the compute stream (which already holds the next step)
-            fired_dev = (torch.cat(flags).view(torch.float32) > 0).any().to(torch.int32).reshape(1)
+            # (the raw flags travel: float bits of the largest out-of-range activation, 0 = none; positive floats order like
+            # their int32 bit patterns, so MAX over ranks is well defined and no device arithmetic is needed here)
+            fired_dev = flags[0] if len(flags) == 1 else torch.cat(flags)
             if self.world > 1:      # the repeat in collect() runs collectives: every rank must take the same branch
                 torch.distributed.all_reduce(fired_dev, op=torch.distributed.ReduceOp.MAX, group=self.kw["group"])
         slot["computed"] = torch.cuda.Event()
@@ -92,7 +94,7 @@ class StyleTransferPipeline:
             return conv
 
         def run(x, cond):
-            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            flag = torch.empty(1, dtype=torch.int32, device=self.device)     # mst_tcn_forward clears it (cudaMemsetAsync)
             flags.append(flag)
             conv.precision = "f16f8"
             try:
@@ -106,7 +108,7 @@ class StyleTransferPipeline:
         The buffer is reused by the step submitted `depth` submits later."""
         host, done, _, fired_host, (ref, x, lo, n_local) = self.pending.popleft()
         done.synchronize()
-        if fired_host is not None and int(fired_host[0]) != 0:
+        if fired_host is not None and bool((fired_host != 0).any()):
             # an activation left the f16f8 operand range: repeat this step with fp32-range operands (its inputs are still in
             # their slot: at most depth - 1 later steps have been submitted)
             self.converter.precision = "bf16x3"
