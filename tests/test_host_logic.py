@@ -312,3 +312,39 @@ def test_instrument_chain_factory_structure():
     assert low["fxs"][0][2] == ["high_shelf"] and high["fxs"][0][2] == ["low_shelf"]
     assert low["fxs"][0][3] == [("high_shelf_freq", 100.0), ("high_shelf_gain", -50.0)]
     assert abs(low["fxs"][1][-2] - 0.005) < 1e-12 and high["fxs"][1][-2] == 0.5
+
+
+def test_normalizer_host_logic_matches_oracle():
+    import numpy as np
+    """The host-side pieces of the input FX normaliser (no GPU involved): inter-onset peak statistics, BS.1770 gating and the
+    imager's three balance steps folded into one matrix, against oracle/norm_oracle.py (itself pinned to the reference)."""
+    from music_mixing_style_transfer_b200.mixing_manipulator import data_normalization as dn
+    from oracle import fixtures, norm_oracle as N
+    x = fixtures.fx_input(4, 60000)
+    got = dn.mean_peak(x[:, 0], N.stub_onsets, 44100, 75)
+    ref = N.get_mean_peak(x[:, :1])
+    assert got is not None and np.allclose(got, ref, rtol=0, atol=1e-9)
+    assert dn.mean_peak(np.zeros(5000, np.float32), N.stub_onsets) is None                  # no onset -> the reference's TypeError path
+    lo, hi = dn.gating_block_bounds(200000)
+    lo_o, hi_o = N.gating_block_bounds(200000)
+    assert np.array_equal(lo, lo_o) and np.array_equal(hi, hi_o)
+    z = np.abs(np.random.RandomState(0).randn(2, len(lo))) * 50.0 + 1e-3
+    assert abs(dn.gated_loudness(z) - N.gated_loudness(z)) < 1e-12
+    assert abs(dn.gated_loudness(z[:1]) - N.gated_loudness(z[:1])) < 1e-12                  # mono meter of the EQ matching
+    x64 = x.astype(np.float64)
+    x64[:, 1] = 0.3 * x64[:, 1] + 0.5 * np.roll(x64[:, 0], 100)
+    ll, rr, lr = np.sum(x64[:, 0] ** 2), np.sum(x64[:, 1] ** 2), np.sum(x64[:, 0] * x64[:, 1])
+    M = dn.imager_matrix(ll, rr, lr, 0.93)
+    ref = N.normalize_imager(x64, 0.93, 0.999)
+    assert np.abs(x64 @ M.T - ref).max() <= 1e-9 * np.abs(ref).max()
+
+
+def test_entry_flags_that_take_names():
+    """--normalization_order / --instruments: the reference declares them with type=str2bool (only the defaults are usable
+    there); here they also accept names, and the defaults are the reference's."""
+    from music_mixing_style_transfer_b200.inference.style_transfer import build_parser
+    a = build_parser().parse_args([])
+    assert a.normalization_order == ['loudness', 'eq', 'compression', 'imager', 'loudness'] and a.normalize_input is True
+    assert a.instruments == ["drums", "bass", "other", "vocals"]
+    a = build_parser().parse_args(["--normalization_order", "loudness", "imager", "--instruments", "drums", "bass"])
+    assert a.normalization_order == ['loudness', 'imager'] and a.instruments == ["drums", "bass"]
