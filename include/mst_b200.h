@@ -119,7 +119,8 @@ int mst_tcn_forward(const mst_tcn_config* cfg, const void* packed, const float* 
                     unsigned int* range_flag, void* stream);
 
 /* Layer-granular launches on the INTERNAL activation format (DESIGN.md "data layout": act[b][t][4 planes of 128 B],
- * 512 bytes per time step, B*L*512 bytes per buffer, 1024-byte aligned).  mst_tcn_forward is exactly
+ * 512 bytes per time step; a segment occupies ceil(L / 256) * 256 rows, i.e. a buffer is mst_tcn_workspace_bytes(cfg, B, L) / 2
+ * bytes, 1024-byte aligned; the rows beyond L of a segment are zero padding the library maintains).  mst_tcn_forward is exactly
  * block0 + layer(1) ... layer(n_blocks-1, fuse_out=1); these entry points exist so a host can time or interleave
  * individual launches (bench.py's roofline leg).
  *   block0: x fp32 [B,n_inputs,L] -> act_out.   layer n>=1: act_in -> act_out, or, when fuse_out != 0 (last block),

@@ -56,6 +56,10 @@ int enc_umma_conv(const void* x, const void* w_packed, const float* bias, void* 
 int enc_split_from_f32(const float* x, void* y, int B, int C, int T, int halo_l, int halo_r, cudaStream_t st);
 int enc_pool_split(const void* x, float* emb, int B, int C, int T, int halo_l, int t_pad, cudaStream_t st);
 
+// rows between two segments of a TCN activation buffer: the segment length rounded up to the 256-row work item, so that the
+// interleaved (5-D) tensor maps of the small dilations exist for every length; rows [T, tcn_seg_rows(T)) are kept at zero
+static inline int tcn_seg_rows(int T) { return (T + 255) / 256 * 256; }
+
 // ---- TCN "f16 + 2 x e4m3" operand format (tcn_f8.cu): packer and converters used by tcn.cu ----
 size_t tcn_f8_weight_bytes();
 int tcn_f8_pack_layer(const float* conv_w, const float* bn_w, const float* bn_var, void* w_out, float* inv_scale,

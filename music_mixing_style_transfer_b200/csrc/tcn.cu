@@ -208,7 +208,7 @@ tcn_film_kernel(const float* __restrict__ film_w, const float* __restrict__ film
 template <int NIN>
 __global__ void __launch_bounds__(256, 2)
 tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, const float4* __restrict__ film, int n_cond,
-                  uint8_t* __restrict__ act, int T) {
+                  uint8_t* __restrict__ act, int T, int Ts) {
   constexpr int ROWS = 256, HALO = 7;
   __shared__ float xs[NIN][ROWS + 2 * HALO + 4];
   const int b = blockIdx.y, t0 = blockIdx.x * ROWS;
@@ -268,7 +268,7 @@ tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, con
         v = fmaf(P[q].y, v, P[q].z) + P[q].w * xin;
         split_bf16(v, hi[q], lo[q]);
       }
-      uint32_t* row = reinterpret_cast<uint32_t*>(act + ((size_t)b * T + t) * kRowBytes);
+      uint32_t* row = reinterpret_cast<uint32_t*>(act + ((size_t)b * Ts + t) * kRowBytes);
       row[(2 * half) * 32 + lane] = pack_bf16(hi[0], hi[1]);
       row[(2 * half + 1) * 32 + lane] = pack_bf16(lo[0], lo[1]);
     }
@@ -276,7 +276,7 @@ tcn_block0_kernel(const float* __restrict__ x, const float* __restrict__ w0, con
 }
 
 // fp32 [B][128][T]  <->  split-bf16 activation rows (module-level TCNBlock surface and per-block parity tests)
-__global__ void __launch_bounds__(256) tcn_act_pack_kernel(const float* __restrict__ x, uint8_t* __restrict__ act, int T) {
+__global__ void __launch_bounds__(256) tcn_act_pack_kernel(const float* __restrict__ x, uint8_t* __restrict__ act, int T, int Ts) {
   __shared__ float tile[kCh][33];
   const int b = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int c = warp; c < kCh; c += 8) {
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) tcn_act_pack_kernel(const float* __restri
     const int ch[4] = {2 * lane, 2 * lane + 1, 64 + 2 * lane, 65 + 2 * lane};
 #pragma unroll
     for (int q = 0; q < 4; ++q) split_bf16(tile[ch[q]][r], hi[q], lo[q]);
-    uint32_t* row = reinterpret_cast<uint32_t*>(act + ((size_t)b * T + t) * kRowBytes);
+    uint32_t* row = reinterpret_cast<uint32_t*>(act + ((size_t)b * Ts + t) * kRowBytes);
     row[0 * 32 + lane] = pack_bf16(hi[0], hi[1]);
     row[1 * 32 + lane] = pack_bf16(lo[0], lo[1]);
     row[2 * 32 + lane] = pack_bf16(hi[2], hi[3]);
@@ -299,13 +299,13 @@ __global__ void __launch_bounds__(256) tcn_act_pack_kernel(const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) tcn_act_unpack_kernel(const uint8_t* __restrict__ act, float* __restrict__ y, int T) {
+__global__ void __launch_bounds__(256) tcn_act_unpack_kernel(const uint8_t* __restrict__ act, float* __restrict__ y, int T, int Ts) {
   __shared__ float tile[kCh][33];
   const int b = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int r = warp; r < 32; r += 8) {
     const int t = t0 + r;
     if (t >= T) continue;
-    const uint32_t* row = reinterpret_cast<const uint32_t*>(act + ((size_t)b * T + t) * kRowBytes);
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(act + ((size_t)b * Ts + t) * kRowBytes);
     const uint32_t h0 = row[lane], l0 = row[32 + lane], h1 = row[64 + lane], l1 = row[96 + lane];
     tile[2 * lane][r] = bf16_lo_f(h0) + bf16_lo_f(l0);
     tile[2 * lane + 1][r] = bf16_hi_f(h0) + bf16_hi_f(l0);
@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(256) tcn_act_unpack_kernel(const uint8_t* __re
 struct TcnLayerArgs {
   int B, T, dilation, tiles_per_seg, n_tiles, n_cond;
   int pair_m;           // mode 1: sub-tiles per half block = dilation / 128
+  int pad_rows;         // T is not a multiple of the 256-row segment stride unit: rows [T, tcn_seg_rows(T)) exist and must stay zero
   const float* inv_scale;   // FMT 1 (f16f8): 1 / (S * 2^11) of this layer's packed weights (tcn_f8.cu)
   unsigned int* range_flag; // FMT 1: receives max |activation| (float bits, atomicMax) if it exceeds the e4m3 range; may be null
   const float4* film;   // this block's [n_cond][128] (bn_bias, gamma, beta, res)
@@ -762,6 +763,9 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
         const int ts = (int)(sub == 0 ? c.r0 : c.r1);
         if (!c.sub0 || ts >= a.T || (MST_TCN_ABLATE & 2)) break;     // !c.sub0: the partner's item only (CTA pair)
         float o0 = 0.f, o1 = 0.f;
+        // interleaved sub-tiles run over the padded segment: a row at or beyond T is stored as zeros (it is zero padding for
+        // the next block's taps)
+        const bool dead_row = MODE == 2 && a.pad_rows && tile_row<MODE>(ts, rl, a.dilation) >= a.T;
         for (int h = 0; h < 2; ++h) {
           uint32_t acc[64];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * 2 + sub) * kCh + h * 64);
@@ -826,6 +830,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 }
               }
               if (!FUSE) {
+                if (MODE == 2 && dead_row) { oh[0] = oh[1] = oh[2] = oh[3] = 0u; ol[0] = ol[1] = 0u; oh8[0] = oh8[1] = 0u; }
                 *reinterpret_cast<uint4*>(rowp + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
                 *reinterpret_cast<uint2*>(lrow + off8) = make_uint2(ol[0], ol[1]);
                 *reinterpret_cast<uint2*>(hrow8 + off8) = make_uint2(oh8[0], oh8[1]);
@@ -865,6 +870,7 @@ tcn_block_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_con
                 ol[e] = pack_bf16(l0, l1);
               }
               if (!FUSE) {
+                if (MODE == 2 && dead_row) { oh[0] = oh[1] = oh[2] = oh[3] = 0u; ol[0] = ol[1] = ol[2] = ol[3] = 0u; }
                 *reinterpret_cast<uint4*>(rowp + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
                 *reinterpret_cast<uint4*>(rowp + 16384 + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
               }
@@ -931,8 +937,8 @@ static int encode_act_map(CUtensorMap* m, const void* base, int B, int T, int bo
   if (!enc) return 1;
   // dims (fastest first): 256 bf16 per time row (4 planes x 64), T rows, B segments; box = box_ch channels x 128 rows,
   // swizzle span = the box's row bytes (64 ch -> SWIZZLE_128B, 32 ch -> SWIZZLE_64B)
-  cuuint64_t dims[3] = {256, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)kRowBytes, (cuuint64_t)T * kRowBytes};
+  cuuint64_t dims[3] = {256, (cuuint64_t)T, (cuuint64_t)B};      // rows >= T: zero on load, clipped on store
+  cuuint64_t strides[2] = {(cuuint64_t)kRowBytes, (cuuint64_t)tcn_seg_rows(T) * kRowBytes};
   cuuint32_t box[3] = {(cuuint32_t)box_ch, (cuuint32_t)kSubRows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
@@ -962,7 +968,7 @@ static int encode_act_map_bytes(CUtensorMap* m, const void* base, int B, int T, 
   PFN_encodeTiled enc = tensor_map_encoder();
   if (!enc) return 1;
   cuuint64_t dims[3] = {(cuuint64_t)kRowBytes, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)kRowBytes, (cuuint64_t)T * kRowBytes};
+  cuuint64_t strides[2] = {(cuuint64_t)kRowBytes, (cuuint64_t)tcn_seg_rows(T) * kRowBytes};
   cuuint32_t box[3] = {(cuuint32_t)box_bytes, (cuuint32_t)kSubRows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
@@ -986,12 +992,13 @@ static int encode_w_map_bytes(CUtensorMap* m, const void* base, int box_rows = k
 }
 
 // mode-2 activation maps: the time axis viewed as [block of 2d rows][half][d rows], box = {box columns, d rows, 1 half, 128/d blocks}
-// = the 128 rows of an interleaved sub-tile (tcn_tile<2>).  Requires T % 2d == 0.  `bytes` = byte-typed map (f16f8) or bf16 elements.
+// = the 128 rows of an interleaved sub-tile (tcn_tile<2>).  The segment stride tcn_seg_rows(T) is a multiple of 2d.  `bytes` = byte-typed map (f16f8) or bf16 elements.
 static int encode_act_map5(CUtensorMap* m, const void* base, int B, int T, int d, int box_cols, bool bytes) {
   PFN_encodeTiled enc = tensor_map_encoder();
   if (!enc) return 1;
-  cuuint64_t dims[5] = {(cuuint64_t)(bytes ? kRowBytes : 256), (cuuint64_t)d, 2, (cuuint64_t)(T / (2 * d)), (cuuint64_t)B};
-  cuuint64_t strides[4] = {(cuuint64_t)kRowBytes, (cuuint64_t)d * kRowBytes, (cuuint64_t)2 * d * kRowBytes, (cuuint64_t)T * kRowBytes};
+  const int Ts = tcn_seg_rows(T);        // the view runs over the padded segment: the pad rows are in bounds and hold zeros
+  cuuint64_t dims[5] = {(cuuint64_t)(bytes ? kRowBytes : 256), (cuuint64_t)d, 2, (cuuint64_t)(Ts / (2 * d)), (cuuint64_t)B};
+  cuuint64_t strides[4] = {(cuuint64_t)kRowBytes, (cuuint64_t)d * kRowBytes, (cuuint64_t)2 * d * kRowBytes, (cuuint64_t)Ts * kRowBytes};
   cuuint32_t box[5] = {(cuuint32_t)box_cols, (cuuint32_t)d, 1, (cuuint32_t)(kSubRows / d), 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const int row_bytes = bytes ? box_cols : box_cols * 2;
@@ -999,6 +1006,15 @@ static int encode_act_map5(CUtensorMap* m, const void* base, int B, int T, int d
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MST_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(interleaved activation B=%d T=%d d=%d box=%d) failed: CUresult %d", B, T, d, box_cols, (int)r);
+  return 0;
+}
+
+// rows [T, tcn_seg_rows(T)) of every segment of an activation buffer are zero padding for the interleaved tensor maps: cleared
+// before every launch that writes the buffer (the 3-D stores clip at T, the interleaved ones write zeros there themselves)
+static int zero_pad_rows(uint8_t* act, int B, int T, cudaStream_t st) {
+  const int Ts = tcn_seg_rows(T);
+  if (Ts == T) return 0;
+  MST_CUDA_OK(cudaMemset2DAsync(act + (size_t)T * kRowBytes, (size_t)Ts * kRowBytes, 0, (size_t)(Ts - T) * kRowBytes, (size_t)B, st));
   return 0;
 }
 
@@ -1011,7 +1027,7 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   const bool f8 = precision == MST_TCN_F16F8;
   // work-item geometry (tcn_tile): far pairing for dilations that are a multiple of 128, interleaved pairing for the small
   // ones when the length allows it, plain 256-row tiles otherwise
-  const int mode = (d >= kSubRows && d % kSubRows == 0) ? 1 : ((d < kSubRows && kSubRows % d == 0 && T % (2 * d) == 0) ? 2 : 0);
+  const int mode = (d >= kSubRows && d % kSubRows == 0) ? 1 : ((d < kSubRows && kSubRows % d == 0) ? 2 : 0);
   // CTA pairs for the f16f8 format in the paired geometries (plain 256-row tiles need three slots per step: the half-filled
   // weight slot then costs ring depth, measured 8 % slower at L = 82,412)
   const int cg = (f8 && MST_TCN_CG == 2 && mode != 0 && sm_count() % 2 == 0) ? 2 : 1;
@@ -1051,6 +1067,8 @@ static int launch_umma_block(const mst_tcn_config* cfg, const uint8_t* packed, c
   a.range_flag = f8 ? range_flag : nullptr;
   a.B = B; a.T = T; a.dilation = (int)d;
   a.pair_m = mode == 1 ? (int)(d / kSubRows) : 1;
+  a.pad_rows = tcn_seg_rows(T) != T ? 1 : 0;
+  if (!fuse_out && zero_pad_rows(act_out, B, T, st)) return 1;
   a.tiles_per_seg = mode == 1 ? (int)(((T + 2 * d - 1) / (2 * d)) * a.pair_m) : cdiv(T, kTileRows);
   a.n_tiles = B * a.tiles_per_seg;
   a.n_cond = n_cond;
@@ -1108,6 +1126,7 @@ static int launch_block0(const mst_tcn_config* cfg, const uint8_t* packed, const
                          unsigned int* range_flag, cudaStream_t st) {
   dim3 grid(cdiv(T, 256), B);
   const float* w0 = reinterpret_cast<const float*>(packed + L.w0);
+  if (zero_pad_rows(act, B, T, st)) return 1;
   if (precision == MST_TCN_F16F8) {
     // block 0 on the tensor cores (tcn_b0.cuh): persistent, one CTA per SM, 128-row tiles
     CUtensorMap tm_y, tm_y8;
@@ -1124,12 +1143,12 @@ static int launch_block0(const mst_tcn_config* cfg, const uint8_t* packed, const
     return launch_ok("block0_umma_kernel");
   }
   const float4* f = reinterpret_cast<const float4*>(film);
-  if (cfg->n_inputs == 2) tcn_block0_kernel<2><<<grid, 256, 0, st>>>(x, w0, f, n_cond, act, T);
-  else tcn_block0_kernel<1><<<grid, 256, 0, st>>>(x, w0, f, n_cond, act, T);
+  if (cfg->n_inputs == 2) tcn_block0_kernel<2><<<grid, 256, 0, st>>>(x, w0, f, n_cond, act, T, tcn_seg_rows(T));
+  else tcn_block0_kernel<1><<<grid, 256, 0, st>>>(x, w0, f, n_cond, act, T, tcn_seg_rows(T));
   return launch_ok("tcn_block0_kernel");
 }
 
-static size_t act_bytes(int B, int L) { return align_up((size_t)B * L * kRowBytes, 1024); }
+static size_t act_bytes(int B, int L) { return align_up((size_t)B * tcn_seg_rows(L) * kRowBytes, 1024); }
 
 static int check_precision(int precision) {
   MST_CHECK(precision == MST_TCN_F16F8 || precision == MST_TCN_BF16X3, "tcn: precision must be MST_TCN_F16F8 (0) or MST_TCN_BF16X3 (1), got %d",
@@ -1279,17 +1298,18 @@ int mst_tcn_block_forward(const mst_tcn_config* cfg, const void* packed_v, int b
     // film for block 0 sits at the start of the table
     if (launch_block0(cfg, packed, P, x, film, n_cond, act[1], B, L, precision, nullptr, st)) return 1;
   } else {
+    if (zero_pad_rows(act[0], B, L, st)) return 1;
     if (f8) {
       if (tcn_f8_act_pack(x, act[0], B, L, st)) return 1;
     } else {
-      tcn_act_pack_kernel<<<grid, 256, 0, st>>>(x, act[0], L);
+      tcn_act_pack_kernel<<<grid, 256, 0, st>>>(x, act[0], L, tcn_seg_rows(L));
       if (launch_ok("tcn_act_pack_kernel")) return 1;
     }
     if (launch_umma_block(cfg, packed, P, block, act[0], act[1], film, n_cond, B, L, false, nullptr, precision, nullptr, st))
       return 1;
   }
   if (f8) return tcn_f8_act_unpack(act[1], y, B, L, st);
-  tcn_act_unpack_kernel<<<grid, 256, 0, st>>>(act[1], y, L);
+  tcn_act_unpack_kernel<<<grid, 256, 0, st>>>(act[1], y, L, tcn_seg_rows(L));
   return launch_ok("tcn_act_unpack_kernel");
 }
 

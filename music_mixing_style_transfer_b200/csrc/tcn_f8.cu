@@ -98,7 +98,7 @@ __global__ void pack_kernel(const float* __restrict__ w, const float* __restrict
 // =====================================================================================================================
 // format converters (block 0 of this format runs on the tensor cores: tcn_b0.cuh)
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) act_pack_kernel(const float* __restrict__ x, uint8_t* __restrict__ act, int T) {
+__global__ void __launch_bounds__(256) act_pack_kernel(const float* __restrict__ x, uint8_t* __restrict__ act, int T, int Ts) {
   __shared__ float tile[kCh][33];
   const int b = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int c = warp; c < kCh; c += 8) {
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) act_pack_kernel(const float* __restrict__
   for (int r = warp; r < 32; r += 8) {
     const int t = t0 + r;
     if (t >= T) continue;
-    uint8_t* row = act + ((size_t)b * T + t) * kRowBytes;
+    uint8_t* row = act + ((size_t)b * Ts + t) * kRowBytes;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       __half hi[2];
@@ -123,13 +123,13 @@ __global__ void __launch_bounds__(256) act_pack_kernel(const float* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) act_unpack_kernel(const uint8_t* __restrict__ act, float* __restrict__ y, int T) {
+__global__ void __launch_bounds__(256) act_unpack_kernel(const uint8_t* __restrict__ act, float* __restrict__ y, int T, int Ts) {
   __shared__ float tile[kCh][33];
   const int b = blockIdx.y, t0 = blockIdx.x * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int r = warp; r < 32; r += 8) {
     const int t = t0 + r;
     if (t >= T) continue;
-    const uint8_t* row = act + ((size_t)b * T + t) * kRowBytes;
+    const uint8_t* row = act + ((size_t)b * Ts + t) * kRowBytes;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const __half2 h2 = reinterpret_cast<const __half2*>(row + half * 128)[lane];
@@ -161,11 +161,11 @@ int tcn_f8_pack_layer(const float* conv_w, const float* bn_w, const float* bn_va
 }
 
 int tcn_f8_act_pack(const float* x, void* act, int B, int T, cudaStream_t st) {
-  f8::act_pack_kernel<<<dim3(cdiv(T, 32), B), 256, 0, st>>>(x, (uint8_t*)act, T);
+  f8::act_pack_kernel<<<dim3(cdiv(T, 32), B), 256, 0, st>>>(x, (uint8_t*)act, T, tcn_seg_rows(T));
   return launch_ok("tcn f8 act_pack_kernel");
 }
 int tcn_f8_act_unpack(const void* act, float* y, int B, int T, cudaStream_t st) {
-  f8::act_unpack_kernel<<<dim3(cdiv(T, 32), B), 256, 0, st>>>((const uint8_t*)act, y, T);
+  f8::act_unpack_kernel<<<dim3(cdiv(T, 32), B), 256, 0, st>>>((const uint8_t*)act, y, T, tcn_seg_rows(T));
   return launch_ok("tcn f8 act_unpack_kernel");
 }
 

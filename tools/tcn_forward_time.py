@@ -1,7 +1,7 @@
 """Sustained whole-TCN forward (block 0 + 13 dilated blocks through mst_tcn_forward) at config 2 shapes: ms per forward over a
 few seconds, with the SM clock / board power nvidia-smi saw.  The step is energy-bound under the 1000 W cap, so A/B comparisons
 of a sub-kernel have to be made on the whole forward, alternating libraries inside one gpurun call.
-usage: tcn_forward_time.py [reps];  MST_DEV_LIB=<build.py --variant library> selects a side build."""
+usage: tcn_forward_time.py [reps] [batch] [length];  MST_DEV_LIB=<build.py --variant library> selects a side build."""
 import os, statistics, subprocess, sys, threading, time, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -13,7 +13,9 @@ from oracle import fixtures, weights as W
 _, tcn = models()
 tcn.precision = "f16f8"
 REPS = int(sys.argv[1]) if len(sys.argv) > 1 else 30
-x = W.synthetic_audio(32, 262144, seed=3).cuda()
+BATCH = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+LEN = int(sys.argv[3]) if len(sys.argv) > 3 else 262144
+x = W.synthetic_audio(BATCH, LEN, seed=3).cuda()
 c = fixtures.make_cond(1, 4).cuda()
 out = torch.empty_like(x)
 samples = []
@@ -36,5 +38,5 @@ for ts, l in samples:
         f = l.split(",")
         try: clk.append(float(f[0])); pw.append(float(f[1]))
         except ValueError: pass
-print("%s: %.2f ms per TCN forward (%d reps) | SM %.0f MHz, %.0f W" % (os.environ.get("MST_DEV_LIB", "product") or "product",
+print("%s: B %d L %d: %.2f ms per TCN forward (%d reps) | SM %.0f MHz, %.0f W" % (os.environ.get("MST_DEV_LIB", "product") or "product", BATCH, LEN,
       e0.elapsed_time(e1) / REPS, REPS, statistics.median(clk) if clk else float("nan"), statistics.median(pw) if pw else float("nan")))
