@@ -173,3 +173,15 @@ def test_panner_and_haas_processors_in_a_chain():
     assert y.shape == x.shape and np.isfinite(y).all()
     # both effects are RMS re-normalised by the chain (common_audioeffects.py:142-145)
     assert abs(np.sqrt(np.mean(y ** 2)) / np.sqrt(np.mean(x ** 2)) - 1.0) < 1e-4
+
+
+def test_normalizer_against_reference_golden():
+    """The CUDA normaliser against outputs of the UNMODIFIED reference class (tests/golden/normalizer.npz: the reference's own
+    drums targets, a real drum window; EQ matching, the four-effect chain, compression matching with the stand-in detector)."""
+    import golden_checks
+    from music_mixing_style_transfer_b200.mixing_manipulator import Audio_Effects_Normalizer
+
+    def normalize(x, order, feats):
+        norm = Audio_Effects_Normalizer(feats, STEMS=['drums'], EFFECTS=order, onset_detector=N.stub_onsets)
+        return norm.normalize_audio(x, src='drums')
+    golden_checks.check_normalizer(normalize, rel_tol=2e-5, smooth=False)

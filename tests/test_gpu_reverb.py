@@ -88,3 +88,22 @@ def test_one_shelf_equaliser_and_instrument_chain():
         chain = create_inst_effects_augmentation_chain(inst, prob, algorithmic=True)
         y = chain([x.copy()])[0]
         assert y.shape == x.shape and np.isfinite(y).all() and np.abs(y).max() > 1e-3, inst
+
+
+def test_reverbs_against_reference_golden():
+    """Both reverbs against outputs of the reference's own classes (tests/golden/reverbs.npz)."""
+    import golden_checks
+    from music_mixing_style_transfer_b200.mixing_manipulator import AlgorithmicReverb, ConvolutionalReverb
+
+    def algo(x, room_size, damping, dry_mix, wet_mix, width):
+        r = AlgorithmicReverb(sample_rate=44100)
+        for name, v in zip(("room_size", "damping", "dry_mix", "wet_mix", "width"), (room_size, damping, dry_mix, wet_mix, width)):
+            getattr(r.parameters, name).value = v
+        return r.process(x)
+
+    def conv(x, h, pre_delay_ms, wet, dry):
+        cr = ConvolutionalReverb([[{'impulse_response': lambda: h}]], 44100)
+        cr.parameters.wet.value, cr.parameters.dry.value, cr.parameters.pre_delay.value = wet, dry, pre_delay_ms
+        cr.update()
+        return cr.process(x)
+    golden_checks.check_reverbs(algo, conv, tol=1e-5)

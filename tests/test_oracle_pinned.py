@@ -289,3 +289,12 @@ def test_reverb_oracles_and_factory_equal_reference_code():
         a = _chain_structure(ref_chain.create_inst_effects_augmentation_chain(inst, prob, algorithmic=True))
         b = _chain_structure(create_inst_effects_augmentation_chain(inst, prob, algorithmic=True))
         assert a == b, inst
+
+
+def test_oracles_match_normalizer_and_reverb_goldens():
+    """The CPU oracles against the committed reference outputs (runs everywhere: the goldens travel, /root/reference does not).
+    float32 storage of the goldens bounds the agreement at ~1e-7."""
+    import golden_checks
+    from oracle import norm_oracle as N
+    golden_checks.check_normalizer(lambda x, order, feats: N.normalize_audio(x, order, feats, src="drums"), rel_tol=2e-7, smooth=True)
+    golden_checks.check_reverbs(fx_oracle.algorithmic_reverb, fx_oracle.convolutional_reverb, tol=2e-7)
